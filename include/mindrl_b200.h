@@ -1,0 +1,206 @@
+/*
+ * mindrl_b200.h -- C ABI of the B200-native experience data path.
+ *
+ * This is the drop-in boundary for the MindSpore primitives that MindRL's
+ * experience data path calls (reference paths relative to /root/reference):
+ *
+ *   P.BufferAppend / BufferGetItem / BufferSample
+ *       mindspore_rl/core/uniform_replay_buffer.py:82-89, 114, 128, 139
+ *   _rl_inner_ops.PriorityReplayBuffer{Create,Push,Sample,Update,Destroy}
+ *       mindspore_rl/core/priority_replay_buffer.py:62-76, 90, 106, 120, 138
+ *   rl_ops.DiscountedReturn
+ *       mindspore_rl/utils/discounted_return.py:71, 82 (CPU loop :84-92)
+ *   in-learner reverse scans (GAE, discounted reward, V-trace, TD(lambda))
+ *       mindspore_rl/algorithm/ppo/ppo.py:320-350
+ *       mindspore_rl/algorithm/mappo/mappo.py:478-497
+ *       mindspore_rl/algorithm/impala/vtrace.py:88-93
+ *
+ * Shape of the ABI follows the reference's only in-repo native operator ABI
+ * (MindSpore AOT custom ops, mindspore_rl/utils/mcts/cpu/cpu_mcts_ops.cc:38-53,
+ * mindspore_rl/utils/mcts/mcts_factory.h:39-82): extern "C", raw pointers,
+ * an explicit cudaStream_t passed as void*, int return code (0 = ok),
+ * state behind an int64 handle held in a process-global registry
+ * (invalid handle = -1).
+ *
+ * Conventions
+ *   - every pointer argument is a DEVICE pointer unless the function name ends
+ *     in _host (then data pointers are host pointers; the library stages the
+ *     host<->device copies on `stream` and the host buffers are reusable on
+ *     return);
+ *   - arrays of pointers / sizes (col tables) are always HOST arrays;
+ *   - `stream` is a cudaStream_t (NULL = legacy default stream); every launch
+ *     of a call goes to that stream, nothing synchronises unless stated;
+ *   - calls on one handle must be issued from one thread at a time and are
+ *     stream-ordered; different handles are independent (same contract as the
+ *     reference registry, which has no locking);
+ *   - no exceptions, no exit(): errors are the return code, text through
+ *     mrl_last_error().
+ *   - there is NO CPU fallback: without a CUDA device every compute entry
+ *     point returns MRL_ERR_CUDA.
+ */
+#ifndef MINDRL_B200_H_
+#define MINDRL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRL_OK 0
+#define MRL_ERR_INVALID 1 /* bad argument */
+#define MRL_ERR_CUDA 2    /* CUDA runtime error (kErrorCode = 2 in cpu_mcts_ops.cc:25) */
+#define MRL_ERR_HANDLE 3  /* unknown / destroyed handle */
+#define MRL_ERR_STATE 4   /* e.g. sample size larger than buffer size */
+
+#define MRL_INVALID_HANDLE (-1) /* mcts_factory.h:32 kInvalidHandle */
+#define MRL_MAX_COLS 32
+
+/* scan layouts */
+#define MRL_TIME_MAJOR 0  /* [T, B, E...]  (DiscountedReturn, MAPPO, V-trace) */
+#define MRL_BATCH_MAJOR 1 /* [B, T]        (PPO gae / discounted_reward) */
+/* scan modes */
+#define MRL_SCAN_AUTO 0
+#define MRL_SCAN_SEQUENTIAL 1 /* one thread walks t = T-1..0: bit-identical to the reference loop order */
+#define MRL_SCAN_PARALLEL 2   /* chunked / warp-shuffle affine scan: re-associates fp32, <=1e-5 rel */
+
+/* ---- library / device ------------------------------------------------- */
+int mrl_version(void);
+const char *mrl_last_error(void);
+int mrl_device_count(int *count);
+int mrl_set_device(int device);
+int mrl_get_device(int *device);
+/* number of kernels this library has launched since load (per process) */
+int64_t mrl_launch_count(void);
+
+/* carrier-free memory helpers (PyTorch is optional; these are plain cudaMalloc etc.) */
+int mrl_malloc(void **dptr, size_t bytes);
+int mrl_free(void *dptr);
+int mrl_host_alloc(void **hptr, size_t bytes); /* pinned */
+int mrl_host_free(void *hptr);
+int mrl_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream);
+int mrl_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream);
+int mrl_memcpy_d2d(void *dst, const void *src, size_t bytes, void *stream);
+int mrl_memset(void *dst, int value, size_t bytes, void *stream);
+int mrl_stream_sync(void *stream);
+/* synthetic fill for benches: row r of a [nrows,row_bytes] column gets its slot id
+ * (int64, little endian) in bytes 0..7 (when row_bytes>=8) and a hash of (seed,r,offset) after */
+int mrl_fill_rows(void *col, int64_t nrows, int64_t row_bytes, uint64_t seed, void *stream);
+
+/* ---- UniformReplayBuffer: BufferAppend / BufferGetItem / BufferSample --
+ * (uniform_replay_buffer.py:75-172).  Storage is caller-visible, as in the
+ * reference where `.buffer` Parameters are passed into every op: pass the
+ * column base pointers in `col_ptrs` (each capacity*row_bytes[i] bytes), or
+ * NULL to let the library allocate zeroed columns (read them back with
+ * mrl_urb_columns).  `seed` seeds the BufferSample draw (:84-89). */
+int mrl_urb_create(int64_t capacity, int32_t ncols, const int64_t *row_bytes,
+                   void *const *col_ptrs, uint64_t seed, int64_t *handle);
+int mrl_urb_destroy(int64_t handle);
+int mrl_urb_columns(int64_t handle, void **col_ptrs_out);
+/* BufferAppend (:114): append nrows>=1 rows; src_cols[i] holds nrows*row_bytes[i] bytes.
+ * FIFO overwrite when full. */
+int mrl_urb_append(int64_t handle, int64_t nrows, const void *const *src_cols, void *stream);
+int mrl_urb_append_host(int64_t handle, int64_t nrows, const void *const *src_cols, void *stream);
+/* BufferGetItem (:128): row at LOGICAL position index (0 = oldest, negative = from the end) */
+int mrl_urb_get_item(int64_t handle, int64_t index, void *const *out_cols, void *stream);
+int mrl_urb_get_item_host(int64_t handle, int64_t index, void *const *out_cols, void *stream);
+/* gather rows at the given PHYSICAL slots (the second half of BufferSample) */
+int mrl_urb_gather(int64_t handle, const int64_t *slots, int64_t n, void *const *out_cols,
+                   void *stream);
+/* BufferSample (:139): draw n slots uniformly with replacement from the `count` valid rows and
+ * gather them; slots_out may be NULL. MRL_ERR_STATE when n exceeds the valid rows. */
+int mrl_urb_sample(int64_t handle, int64_t n, int64_t *slots_out, void *const *out_cols,
+                   void *stream);
+int mrl_urb_sample_host(int64_t handle, int64_t n, int64_t *slots_out, void *const *out_cols,
+                        void *stream);
+/* reset (:141-150): count <- 0, head and data untouched */
+int mrl_urb_reset(int64_t handle, void *stream);
+/* size()/full() (:152-172) read these; the host mirror is exact because the cursor rule is
+ * deterministic in the number of rows appended */
+int mrl_urb_state(int64_t handle, int32_t *count, int32_t *head);
+int mrl_urb_set_state(int64_t handle, int32_t count, int32_t head);
+
+/* ---- PriorityReplayBuffer (priority_replay_buffer.py:60-138) ---------- */
+/* PriorityReplayBufferCreate(capacity, alpha, shapes, types, seed0, seed1) (:62-66) */
+int mrl_prb_create(int64_t capacity, float alpha, int32_t ncols, const int64_t *row_bytes,
+                   uint64_t seed0, uint64_t seed1, int64_t *handle);
+/* PriorityReplayBufferDestroy (:138) */
+int mrl_prb_destroy(int64_t handle);
+/* PriorityReplayBufferPush (:90): one transition row; the new leaf gets max_priority */
+int mrl_prb_push(int64_t handle, const void *const *row_cols, void *stream);
+int mrl_prb_push_host(int64_t handle, const void *const *row_cols, void *stream);
+/* nrows consecutive pushes in one call (same result as nrows calls of mrl_prb_push) */
+int mrl_prb_push_batch(int64_t handle, int64_t nrows, const void *const *src_cols, void *stream);
+int mrl_prb_push_batch_host(int64_t handle, int64_t nrows, const void *const *src_cols,
+                            void *stream);
+/* PriorityReplayBufferSample (:106): stratified proportional sampling of n transitions.
+ * uniforms: n floats in [0,1) to use as the per-stratum draws (parity / reproducibility), or
+ * NULL to draw them from the buffer's counter-based generator.
+ * out: indices int64[n], weights float[n], out_cols[i] = n*row_bytes[i] bytes (out_cols may be
+ * NULL to skip the row gather). */
+int mrl_prb_sample(int64_t handle, int64_t n, float beta, const float *uniforms,
+                   int64_t *indices, float *weights, void *const *out_cols, void *stream);
+int mrl_prb_sample_host(int64_t handle, int64_t n, float beta, const float *uniforms,
+                        int64_t *indices, float *weights, void *const *out_cols, void *stream);
+/* PriorityReplayBufferUpdate (:120): leaf[indices[k]] <- priorities[k]^alpha in order k=0..n-1
+ * (duplicates: last occurrence wins), ancestors recomputed, max_priority tracked. */
+int mrl_prb_update(int64_t handle, const int64_t *indices, const float *priorities, int64_t n,
+                   void *stream);
+int mrl_prb_update_host(int64_t handle, const int64_t *indices, const float *priorities,
+                        int64_t n, void *stream);
+/* host-side facts: valid rows, ring cursor (slot of the newest row, -1 when empty), padded leaf
+ * count (power of two) */
+int mrl_prb_info(int64_t handle, int64_t *size, int64_t *head, int64_t *leaf_capacity);
+/* reads max_priority from the device (synchronises `stream`) */
+int mrl_prb_max_priority(int64_t handle, float *max_priority, void *stream);
+/* parity helper: copies the 2*leaf_capacity node arrays (index 0 unused, root = 1) to HOST
+ * buffers; synchronises `stream`. */
+int mrl_prb_tree_dump(int64_t handle, float *sum_nodes, float *min_nodes, void *stream);
+/* device pointers of the ring columns (capacity rows each) */
+int mrl_prb_columns(int64_t handle, void **col_ptrs_out);
+/* sharded buffer (one sub-buffer + tree per rank):
+ *   mrl_prb_root_stats writes {root_sum, root_min, (float)size, max_priority} to stats4 (device);
+ *   ranks all-gather those 16 bytes (NCCL) into gstats[world][4];
+ *   mrl_prb_sample_sharded draws n local strata from the local tree and computes the
+ *   importance weights against the GLOBAL sum / min / size. */
+int mrl_prb_root_stats(int64_t handle, float *stats4, void *stream);
+int mrl_prb_sample_sharded(int64_t handle, int64_t n, float beta, const float *uniforms,
+                           const float *gstats, int32_t world, int64_t *indices, float *weights,
+                           void *const *out_cols, void *stream);
+
+/* ---- reverse scans ----------------------------------------------------- */
+/* DiscountedReturn (discounted_return.py:84-92):
+ *   last <- reward[t] + ((1 - done[t]) * gamma) * last ; out[t] <- last,  t = T-1..0
+ * time-major: reward/out [T,B,E], done [T,B] (uint8, broadcast over E), last_value [B,E]
+ * batch-major: reward/out [B,T], done [B,T], last_value [B]  (E must be 1)
+ * done may be NULL (PPO discounted_reward, ppo.py:320-332); last_value may be NULL (= 0). */
+int mrl_discounted_return(const float *reward, const uint8_t *done, const float *last_value,
+                          float *out, int64_t T, int64_t B, int64_t E, float gamma,
+                          int32_t layout, int32_t mode, void *stream);
+int mrl_discounted_return_host(const float *reward, const uint8_t *done, const float *last_value,
+                               float *out, int64_t T, int64_t B, int64_t E, float gamma,
+                               int32_t layout, int32_t mode, void *stream);
+/* GAE (ppo.py:334-350 without done, mappo.py:478-497 with masks):
+ *   m = 1 - done[t]
+ *   delta = reward[t] + (gamma * V[t+1]) * m - V[t]
+ *   adv[t] = delta + ((gamma*lambda) * m) * adv[t+1],  adv[T] = 0
+ *   ret[t] = adv[t] + V[t]
+ * V[t+1] comes from next_value[t] when next_value != NULL (PPO: critic(next_state)), otherwise
+ * from value[t+1] with last_value[B] as V[T] (for a [T+1,B] value array pass value+T*B).
+ * done, ret may be NULL. */
+int mrl_gae(const float *reward, const float *value, const float *next_value,
+            const float *last_value, const uint8_t *done, float *adv, float *ret, int64_t T,
+            int64_t B, float gamma, float lambda, int32_t layout, int32_t mode, void *stream);
+int mrl_gae_host(const float *reward, const float *value, const float *next_value,
+                 const float *last_value, const uint8_t *done, float *adv, float *ret, int64_t T,
+                 int64_t B, float gamma, float lambda, int32_t layout, int32_t mode, void *stream);
+/* generic first-order reverse recurrence x[t] = a[t] + b[t] * x[t+1], x[T] = x_last (NULL = 0):
+ * V-trace (vtrace.py:88-93, b = discount*c*mask) and TD(lambda) (coma.py:489-501). */
+int mrl_affine_scan(const float *a, const float *b, const float *x_last, float *out, int64_t T,
+                    int64_t B, int32_t layout, int32_t mode, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MINDRL_B200_H_ */
