@@ -74,6 +74,10 @@ int mrl_get_device(int *device);
 /* number of kernels this library has launched since load (per process) */
 int64_t mrl_launch_count(void);
 
+/* tunables: "gather_path" (0 auto, 1 register path only, 2 TMA ring whenever aligned),
+ * "bulk_min_row", "bulk_chunk", "bulk_ctas_per_sm" */
+int mrl_set_option(const char *key, int64_t value);
+
 /* carrier-free memory helpers (PyTorch is optional; these are plain cudaMalloc etc.) */
 int mrl_malloc(void **dptr, size_t bytes);
 int mrl_free(void *dptr);

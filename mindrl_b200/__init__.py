@@ -1,0 +1,12 @@
+"""mindrl_b200: B200-native (sm_100a) experience data path of MindSpore Reinforcement.
+
+Replay-buffer ops and reverse scans only; see DESIGN.md.  Python is a thin ctypes layer over
+include/mindrl_b200.h; there is no CPU fallback.
+"""
+from . import _ffi
+from .core import PriorityReplayBuffer, ShardedPriorityReplayBuffer, UniformReplayBuffer
+from .utils import DiscountedReturn, affine_scan, discounted_reward, gae
+
+__version__ = "0.1.0"
+__all__ = ["UniformReplayBuffer", "PriorityReplayBuffer", "ShardedPriorityReplayBuffer",
+           "DiscountedReturn", "discounted_reward", "gae", "affine_scan"]

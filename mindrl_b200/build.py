@@ -1,0 +1,69 @@
+"""Builds libmindrl_b200.so in-tree with nvcc for sm_100a (no torch, no CPU fallback)."""
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT_DIR = os.path.join(HERE, "lib")
+LIB = os.path.join(OUT_DIR, "libmindrl_b200.so")
+SOURCES = ["abi.cu", "copy.cu", "urb.cu", "prb.cu", "scan.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
+    # parity rule of include/mrl_arith.h: no fast-math, no implicit fma contraction
+    "-fmad=false", "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off",
+    "-Xptxas", "-v", "--cudart", "shared",
+]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    return "nvcc"
+
+
+def _deps():
+    hdrs = [os.path.join(CSRC, "common.cuh"), os.path.join(HERE, "..", "include", "mindrl_b200.h"),
+            os.path.join(HERE, "..", "include", "mrl_arith.h")]
+    return [h for h in hdrs if os.path.exists(h)]
+
+
+def build(force=False, verbose=False):
+    os.makedirs(OUT_DIR, exist_ok=True)
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    newest = max(os.path.getmtime(p) for p in srcs + _deps() + [os.path.abspath(__file__)])
+    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= newest:
+        return LIB
+    nvcc = _nvcc()
+    objs = [os.path.join(OUT_DIR, s.replace(".cu", ".o")) for s in SOURCES]
+
+    def compile_one(pair):
+        src, obj = pair
+        cmd = [nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        return src, r
+
+    with ThreadPoolExecutor(max_workers=len(srcs)) as ex:
+        results = list(ex.map(compile_one, zip(srcs, objs)))
+    log = []
+    for src, r in results:
+        log.append(f"== {os.path.basename(src)}\n{r.stdout}{r.stderr}")
+        if r.returncode != 0:
+            sys.stderr.write("\n".join(log))
+            raise RuntimeError(f"nvcc failed on {src}")
+    with open(os.path.join(OUT_DIR, "ptxas.log"), "w") as f:
+        f.write("\n".join(log))
+    if verbose:
+        print("\n".join(log))
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["--cudart", "shared"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("link failed")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

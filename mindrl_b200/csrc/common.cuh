@@ -1,0 +1,114 @@
+// common.cuh -- shared host/device helpers of libmindrl_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+
+#include "../../include/mindrl_b200.h"
+#include "../../include/mrl_arith.h"
+
+namespace mrl {
+
+constexpr int kNumSM = 148;  // B200: 2 dies x 74 SMs
+
+void set_error(const char *fmt, ...);
+extern std::atomic<int64_t> g_launches;
+
+inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+#define MRL_CUDA(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      ::mrl::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                       __LINE__);                                                        \
+      return MRL_ERR_CUDA;                                                               \
+    }                                                                                    \
+  } while (0)
+
+#define MRL_REQUIRE(cond, ...)      \
+  do {                              \
+    if (!(cond)) {                  \
+      ::mrl::set_error(__VA_ARGS__); \
+      return MRL_ERR_INVALID;       \
+    }                               \
+  } while (0)
+
+// call right after every <<<>>> launch: counts it and surfaces launch-config errors
+#define MRL_LAUNCHED()                          \
+  do {                                          \
+    ::mrl::g_launches.fetch_add(1);             \
+    MRL_CUDA(cudaPeekAtLastError());            \
+  } while (0)
+
+// process-global handle registry (mcts_factory.h:39-82 is the reference's model)
+template <class T>
+class Registry {
+ public:
+  int64_t put(T *obj) {
+    std::lock_guard<std::mutex> g(mu_);
+    int64_t h = next_++;
+    map_[h] = obj;
+    return h;
+  }
+  T *get(int64_t h) {
+    std::lock_guard<std::mutex> g(mu_);
+    auto it = map_.find(h);
+    return it == map_.end() ? nullptr : it->second;
+  }
+  T *take(int64_t h) {
+    std::lock_guard<std::mutex> g(mu_);
+    auto it = map_.find(h);
+    if (it == map_.end()) return nullptr;
+    T *o = it->second;
+    map_.erase(it);
+    return o;
+  }
+
+ private:
+  std::mutex mu_;
+  std::unordered_map<int64_t, T *> map_;
+  int64_t next_ = 1;
+};
+
+// ------------------------------------------------------------------------------------------
+// column table passed by value to the copy kernels (<= MRL_MAX_COLS columns)
+// ------------------------------------------------------------------------------------------
+struct ColTable {
+  uint8_t *col[MRL_MAX_COLS];       // ring column base (capacity rows)
+  uint8_t *io[MRL_MAX_COLS];        // per-call source (append) or destination (gather)
+  int64_t row_bytes[MRL_MAX_COLS];
+  int32_t vec[MRL_MAX_COLS];        // widest unit (16/8/4/2/1 bytes) every row address is aligned to
+  int32_t ncols;
+};
+
+inline int32_t align_unit(uintptr_t a, uintptr_t b, uint64_t row_bytes) {
+  uint64_t x = a | b | row_bytes | 16u;
+  return (int32_t)(x & (~x + 1));  // lowest set bit, capped at 16
+}
+
+// pinned + device staging used by the *_host entry points
+struct Staging {
+  uint8_t *host = nullptr;
+  uint8_t *dev = nullptr;
+  size_t bytes = 0;
+  cudaEvent_t done = nullptr;  // last async use of `host`
+  int ensure(size_t need);
+  int wait();
+  void release();
+};
+
+int gather_rows(const ColTable &tab, const int64_t *slots, int64_t n, int64_t capacity,
+                cudaStream_t st);
+int copy_segments(const ColTable &tab, int64_t dst_row, int64_t src_row, int64_t nrows,
+                  cudaStream_t st);
+// to_ring = 1: io rows -> ring rows; 0: ring rows -> io rows
+int copy_segments_dir(const ColTable &tab, int64_t ring_row, int64_t io_row, int64_t nrows,
+                      int to_ring, cudaStream_t st);
+
+}  // namespace mrl

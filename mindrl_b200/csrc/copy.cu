@@ -1,0 +1,402 @@
+// copy.cu -- row movers of the experience data path (sm_100a).
+//
+//   copy_seg_kernel      ring append / get_item: contiguous runs of rows, widest aligned unit
+//                        (128-bit when the column allows), 4 units in flight per thread.
+//   gather_ldg_kernel    index-driven row gather through registers (small rows / fallback).
+//   gather_bulk_kernel   index-driven row gather through the TMA engine: one thread per CTA drives
+//                        a STAGES-deep shared-memory ring with cp.async.bulk global->shared
+//                        (mbarrier complete_tx) and cp.async.bulk shared->global (bulk groups).
+//                        SASS: UBLKCP.  No register traffic, no per-byte instructions.
+//   fill_rows_kernel     synthetic rows for benches (slot id in bytes 0..7, hash after).
+//
+// Replaces the copy halves of BufferAppend / BufferGetItem / BufferSample and
+// PriorityReplayBufferSample (uniform_replay_buffer.py:114,128,139; priority_replay_buffer.py:106).
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace mrl {
+
+// ---- segment copy ------------------------------------------------------------------------
+template <class V>
+__device__ __forceinline__ void copy_units(const uint8_t *__restrict__ src,
+                                           uint8_t *__restrict__ dst, int64_t bytes) {
+  const V *s = reinterpret_cast<const V *>(src);
+  V *d = reinterpret_cast<V *>(dst);
+  const int64_t n = bytes / (int64_t)sizeof(V);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n; i += 4 * stride) {
+    V a = s[i], b = s[i + stride], c = s[i + 2 * stride], e = s[i + 3 * stride];
+    d[i] = a;
+    d[i + stride] = b;
+    d[i + 2 * stride] = c;
+    d[i + 3 * stride] = e;
+  }
+  for (; i < n; i += stride) d[i] = s[i];
+}
+
+__global__ void __launch_bounds__(256)
+    copy_seg_kernel(ColTable tab, int64_t ring_row, int64_t io_row, int64_t nrows, int to_ring) {
+  const int c = blockIdx.y;
+  const int64_t rb = tab.row_bytes[c];
+  uint8_t *ring = tab.col[c] + ring_row * rb;
+  uint8_t *io = tab.io[c] + io_row * rb;
+  const uint8_t *src = to_ring ? io : ring;
+  uint8_t *dst = to_ring ? ring : io;
+  const int64_t bytes = nrows * rb;
+  switch (tab.vec[c]) {
+    case 16: copy_units<uint4>(src, dst, bytes); break;
+    case 8: copy_units<uint2>(src, dst, bytes); break;
+    case 4: copy_units<uint32_t>(src, dst, bytes); break;
+    case 2: copy_units<uint16_t>(src, dst, bytes); break;
+    default: copy_units<uint8_t>(src, dst, bytes); break;
+  }
+}
+
+int copy_segments_dir(const ColTable &tab, int64_t ring_row, int64_t io_row, int64_t nrows,
+                      int to_ring, cudaStream_t st) {
+  if (nrows <= 0) return MRL_OK;
+  int64_t max_units = 1;
+  for (int c = 0; c < tab.ncols; ++c) {
+    int64_t u = nrows * tab.row_bytes[c] / tab.vec[c];
+    if (u > max_units) max_units = u;
+  }
+  int64_t blocks = (max_units + 256 * 4 - 1) / (256 * 4);
+  if (blocks < 1) blocks = 1;
+  if (blocks > kNumSM * 8) blocks = kNumSM * 8;
+  dim3 grid((unsigned)blocks, (unsigned)tab.ncols);
+  copy_seg_kernel<<<grid, 256, 0, st>>>(tab, ring_row, io_row, nrows, to_ring);
+  MRL_LAUNCHED();
+  return MRL_OK;
+}
+
+int copy_segments(const ColTable &tab, int64_t dst_row, int64_t src_row, int64_t nrows,
+                  cudaStream_t st) {
+  return copy_segments_dir(tab, dst_row, src_row, nrows, 1, st);
+}
+
+// ---- gather through registers ------------------------------------------------------------
+template <class V, class I>
+__device__ __forceinline__ void gather_units(const uint8_t *__restrict__ col,
+                                             uint8_t *__restrict__ out,
+                                             const int64_t *__restrict__ slots, int64_t n,
+                                             int64_t rb, int64_t capacity) {
+  const I upr = (I)(rb / (int64_t)sizeof(V));
+  const I total = (I)n * upr;
+  const I stride = (I)gridDim.x * blockDim.x;
+  I u = (I)blockIdx.x * blockDim.x + threadIdx.x;
+  V *d = reinterpret_cast<V *>(out);
+  for (; u < total; u += 4 * stride) {
+    V v[4];
+    I uu[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      uu[k] = u + (I)k * stride;
+      if (uu[k] < total) {
+        const I i = uu[k] / upr;
+        const I off = uu[k] - i * upr;
+        int64_t slot = __ldg(slots + i);
+        slot = slot < 0 ? 0 : (slot >= capacity ? capacity - 1 : slot);
+        v[k] = reinterpret_cast<const V *>(col + slot * rb)[off];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (uu[k] < total) d[uu[k]] = v[k];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    gather_ldg_kernel(ColTable tab, const int64_t *__restrict__ slots, int64_t n,
+                      int64_t capacity, uint32_t col_mask) {
+  int c = blockIdx.y;
+  // blockIdx.y enumerates the set bits of col_mask
+  {
+    uint32_t m = col_mask;
+    for (int k = 0; k < c; ++k) m &= m - 1;
+    c = __ffs(m) - 1;
+  }
+  const int64_t rb = tab.row_bytes[c];
+  const bool small = n * rb < (int64_t)0x7fffffff;
+  switch (tab.vec[c]) {
+    case 16:
+      if (small) gather_units<uint4, uint32_t>(tab.col[c], tab.io[c], slots, n, rb, capacity);
+      else gather_units<uint4, uint64_t>(tab.col[c], tab.io[c], slots, n, rb, capacity);
+      break;
+    case 8:
+      if (small) gather_units<uint2, uint32_t>(tab.col[c], tab.io[c], slots, n, rb, capacity);
+      else gather_units<uint2, uint64_t>(tab.col[c], tab.io[c], slots, n, rb, capacity);
+      break;
+    case 4:
+      if (small) gather_units<uint32_t, uint32_t>(tab.col[c], tab.io[c], slots, n, rb, capacity);
+      else gather_units<uint32_t, uint64_t>(tab.col[c], tab.io[c], slots, n, rb, capacity);
+      break;
+    case 2:
+      if (small) gather_units<uint16_t, uint32_t>(tab.col[c], tab.io[c], slots, n, rb, capacity);
+      else gather_units<uint16_t, uint64_t>(tab.col[c], tab.io[c], slots, n, rb, capacity);
+      break;
+    default:
+      if (small) gather_units<uint8_t, uint32_t>(tab.col[c], tab.io[c], slots, n, rb, capacity);
+      else gather_units<uint8_t, uint64_t>(tab.col[c], tab.io[c], slots, n, rb, capacity);
+      break;
+  }
+}
+
+// ---- gather through the TMA engine -------------------------------------------------------
+struct BulkPlan {
+  int32_t ncols;
+  int32_t col_id[MRL_MAX_COLS];
+  int32_t chunk_bytes[MRL_MAX_COLS];
+  int32_t nchunks[MRL_MAX_COLS];
+  int64_t item_begin[MRL_MAX_COLS + 1];  // items of column k: [item_begin[k], item_begin[k+1])
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes,
+                                         uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(smem_dst)),
+      "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *gdst, const void *smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+               "r"(smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+struct BulkItem {
+  const uint8_t *src;
+  uint8_t *dst;
+  uint32_t bytes;
+};
+
+__device__ __forceinline__ void bulk_decode(const ColTable &tab, const BulkPlan &plan,
+                                            const int64_t *__restrict__ slots, int64_t capacity,
+                                            int64_t item, BulkItem &it) {
+  int k = 0;
+  while (k + 1 < plan.ncols && item >= plan.item_begin[k + 1]) ++k;
+  const int c = plan.col_id[k];
+  const int64_t local = item - plan.item_begin[k];
+  const int32_t nch = plan.nchunks[k];
+  const int64_t i = local / nch;
+  const int32_t j = (int32_t)(local - i * nch);
+  const int64_t rb = tab.row_bytes[c];
+  const int64_t off = (int64_t)j * plan.chunk_bytes[k];
+  int64_t rem = rb - off;
+  it.bytes = (uint32_t)(rem < plan.chunk_bytes[k] ? rem : plan.chunk_bytes[k]);
+  int64_t slot = __ldg(slots + i);
+  slot = slot < 0 ? 0 : (slot >= capacity ? capacity - 1 : slot);
+  it.src = tab.col[c] + slot * rb + off;
+  it.dst = tab.io[c] + i * rb + off;
+}
+
+template <int STAGES>
+__global__ void __launch_bounds__(32)
+    gather_bulk_kernel(const __grid_constant__ ColTable tab, const __grid_constant__ BulkPlan plan,
+                       const int64_t *__restrict__ slots, int64_t capacity, int32_t stage_bytes) {
+  extern __shared__ __align__(128) uint8_t stage_mem[];
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  if (threadIdx.x != 0) return;  // one thread drives the DMA ring
+
+  for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1);
+  fence_async_smem();
+
+  const int64_t total = plan.item_begin[plan.ncols];
+  const int64_t first = blockIdx.x;
+  const int64_t step = gridDim.x;
+  const int64_t nmine = total > first ? (total - first + step - 1) / step : 0;
+
+  uint8_t *dst_of[STAGES];
+  uint32_t bytes_of[STAGES];
+  BulkItem next;
+  if (nmine > 0) bulk_decode(tab, plan, slots, capacity, first, next);
+
+#pragma unroll 1
+  for (int64_t k = 0; k < nmine + STAGES - 1; ++k) {
+    BulkItem cur = next;
+    if (k + 1 < nmine) bulk_decode(tab, plan, slots, capacity, first + (k + 1) * step, next);
+    if (k >= STAGES - 1) {  // drain: item j has landed -> write it out
+      const int64_t j = k - (STAGES - 1);
+      const int s = (int)(j % STAGES);
+      mbar_wait(&full_bar[s], (uint32_t)((j / STAGES) & 1));
+      fence_async_smem();
+#pragma unroll
+      for (int q = 0; q < STAGES; ++q)
+        if (q == s) bulk_s2g(dst_of[q], stage_mem + (size_t)q * stage_bytes, bytes_of[q]);
+      bulk_commit();
+    }
+    if (k < nmine) {  // fill: stage k%STAGES was last read by the store of item k-STAGES
+      const int s = (int)(k % STAGES);
+      if (k >= STAGES) bulk_wait_read<1>();
+#pragma unroll
+      for (int q = 0; q < STAGES; ++q)
+        if (q == s) {
+          dst_of[q] = cur.dst;
+          bytes_of[q] = cur.bytes;
+        }
+      mbar_expect_tx(&full_bar[s], cur.bytes);
+      bulk_g2s(stage_mem + (size_t)s * stage_bytes, cur.src, cur.bytes, &full_bar[s]);
+    }
+  }
+  bulk_wait_all();
+}
+
+// tunables (mrl_set_option / environment): gather_path 0 = auto, 1 = registers only, 2 = TMA ring
+// whenever the column is 16-byte aligned
+static int64_t env_i64(const char *name, int64_t dflt) {
+  const char *e = getenv(name);
+  return e ? atoll(e) : dflt;
+}
+static int64_t g_gather_path = env_i64("MRL_GATHER_PATH", 0);
+static int64_t g_bulk_min_row = env_i64("MRL_BULK_MIN_ROW", 2048);
+static int64_t g_bulk_chunk = env_i64("MRL_BULK_CHUNK", 8192);
+static int64_t g_bulk_ctas_per_sm = env_i64("MRL_BULK_CTAS_PER_SM", 4);
+
+int set_copy_option(const char *key, int64_t value) {
+  std::string k(key);
+  if (k == "gather_path" && value >= 0 && value <= 2) g_gather_path = value;
+  else if (k == "bulk_min_row" && value >= 16) g_bulk_min_row = value;
+  else if (k == "bulk_chunk" && value >= 16 && value <= 49152 && value % 16 == 0) g_bulk_chunk = value;
+  else if (k == "bulk_ctas_per_sm" && value >= 1 && value <= 16) g_bulk_ctas_per_sm = value;
+  else return MRL_ERR_INVALID;
+  return MRL_OK;
+}
+
+constexpr int kBulkStages = 4;
+
+int gather_rows(const ColTable &tab, const int64_t *slots, int64_t n, int64_t capacity,
+                cudaStream_t st) {
+  if (n <= 0) return MRL_OK;
+  const int64_t bulk_min_row = g_bulk_min_row, bulk_chunk = g_bulk_chunk;
+  const int64_t bulk_ctas_per_sm = g_bulk_ctas_per_sm;
+  const int path = (int)g_gather_path;
+  uint32_t ldg_mask = 0;
+  BulkPlan plan;
+  plan.ncols = 0;
+  plan.item_begin[0] = 0;
+  int32_t stage_bytes = 0;
+  for (int c = 0; c < tab.ncols; ++c) {
+    const int64_t rb = tab.row_bytes[c];
+    const bool eligible = tab.vec[c] == 16 && path != 1 && (path == 2 || rb >= bulk_min_row);
+    if (!eligible) {
+      ldg_mask |= 1u << c;
+      continue;
+    }
+    const int k = plan.ncols++;
+    int64_t nch = (rb + bulk_chunk - 1) / bulk_chunk;
+    int64_t chunk = ((rb + nch - 1) / nch + 15) / 16 * 16;
+    nch = (rb + chunk - 1) / chunk;
+    plan.col_id[k] = c;
+    plan.chunk_bytes[k] = (int32_t)chunk;
+    plan.nchunks[k] = (int32_t)nch;
+    plan.item_begin[k + 1] = plan.item_begin[k] + n * nch;
+    if (chunk > stage_bytes) stage_bytes = (int32_t)chunk;
+  }
+  if (plan.ncols > 0) {
+    const int64_t total = plan.item_begin[plan.ncols];
+    int64_t blocks = kNumSM * bulk_ctas_per_sm;
+    if (blocks > total) blocks = total;
+    stage_bytes = (stage_bytes + 127) / 128 * 128;
+    const size_t smem = (size_t)stage_bytes * kBulkStages;
+    static size_t configured = 0;
+    if (smem > configured) {
+      MRL_CUDA(cudaFuncSetAttribute(gather_bulk_kernel<kBulkStages>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = smem;
+    }
+    gather_bulk_kernel<kBulkStages>
+        <<<(unsigned)blocks, 32, smem, st>>>(tab, plan, slots, capacity, stage_bytes);
+    MRL_LAUNCHED();
+  }
+  if (ldg_mask) {
+    int ncols = __builtin_popcount(ldg_mask);
+    int64_t max_units = 1;
+    for (int c = 0; c < tab.ncols; ++c)
+      if (ldg_mask & (1u << c)) {
+        int64_t u = n * tab.row_bytes[c] / tab.vec[c];
+        if (u > max_units) max_units = u;
+      }
+    int64_t blocks = (max_units + 256 * 4 - 1) / (256 * 4);
+    if (blocks > kNumSM * 8) blocks = kNumSM * 8;
+    dim3 grid((unsigned)blocks, (unsigned)ncols);
+    gather_ldg_kernel<<<grid, 256, 0, st>>>(tab, slots, n, capacity, ldg_mask);
+    MRL_LAUNCHED();
+  }
+  return MRL_OK;
+}
+
+// ---- synthetic fill ----------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    fill_rows_kernel(uint8_t *col, int64_t nrows, int64_t row_bytes, uint64_t seed) {
+  const int64_t words_per_row = (row_bytes + 3) / 4;
+  const int64_t total = nrows * words_per_row;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += stride) {
+    const int64_t r = w / words_per_row;
+    const int64_t wi = w - r * words_per_row;
+    uint32_t v = mrl_hash32(seed ^ (uint64_t)r * 0x100000001B3ULL, (uint64_t)wi);
+    if (row_bytes >= 8 && wi < 2) v = (uint32_t)((uint64_t)r >> (32 * wi));
+    uint8_t *p = col + r * row_bytes + wi * 4;
+    const int64_t left = row_bytes - wi * 4;
+    if (left >= 4 && (((uintptr_t)p) & 3) == 0) {
+      *reinterpret_cast<uint32_t *>(p) = v;
+    } else {
+      for (int b = 0; b < 4 && b < left; ++b) p[b] = (uint8_t)(v >> (8 * b));
+    }
+  }
+}
+
+}  // namespace mrl
+
+extern "C" int mrl_set_option(const char *key, int64_t value) {
+  MRL_REQUIRE(key, "mrl_set_option: NULL key");
+  int rc = mrl::set_copy_option(key, value);
+  if (rc) mrl::set_error("mrl_set_option: unknown key or value out of range: %s=%lld", key, (long long)value);
+  return rc;
+}
+
+extern "C" int mrl_fill_rows(void *col, int64_t nrows, int64_t row_bytes, uint64_t seed,
+                             void *stream) {
+  MRL_REQUIRE(col && nrows >= 0 && row_bytes > 0, "mrl_fill_rows: bad arguments");
+  if (nrows == 0) return MRL_OK;
+  mrl::fill_rows_kernel<<<mrl::kNumSM * 8, 256, 0, mrl::as_stream(stream)>>>(
+      (uint8_t *)col, nrows, row_bytes, seed);
+  MRL_LAUNCHED();
+  return MRL_OK;
+}

@@ -1,0 +1,186 @@
+"""Generates tests/golden/discounted_return_ref.npz by running the REFERENCE's own Python loop
+(/root/reference/mindspore_rl/utils/discounted_return.py:84-92, the CPU path of DiscountedReturn).
+
+MindSpore itself cannot be installed here, so the reference file is executed against a minimal
+numpy stand-in for the handful of MindSpore names it touches (Tensor, nn.Cell, P.ZerosLike,
+context.get_context, rl_ops.DiscountedReturn).  The stand-in follows MindSpore's type promotion
+(an integer tensor times a float32 tensor is float32).  The loop body, its operation order and
+its indexing are the reference's, untouched: the file is loaded from /root/reference at run time
+and never copied.
+
+A second fixture, ppo_scans_ref.npz, comes from PPOLearner.learn's nested functions
+`discounted_reward` and `gae` (/root/reference/mindspore_rl/algorithm/ppo/ppo.py:320-350).  They
+cannot be imported (they are closures inside learn()), so their FunctionDef nodes are taken from
+the reference file with `ast` at run time and compiled unmodified against a stand-in `self`
+(add, mul, reshape, squeeze, zeros_like, zero_int, critic_net = a lookup of precomputed values).
+
+Run in the build container only (the GPU box has no /root/reference):
+    python tests/golden/make_golden.py
+"""
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+
+REF = "/root/reference/mindspore_rl/utils/discounted_return.py"
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "discounted_return_ref.npz")
+
+
+class Tensor(np.ndarray):
+    """ndarray with MindSpore-like promotion: float32 wins over integer operands"""
+
+    def __new__(cls, data, dtype=None):
+        return np.asarray(data, dtype=dtype).view(cls)
+
+    def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
+        raw = [np.asarray(i).view(np.ndarray) if isinstance(i, np.ndarray) else i for i in inputs]
+        out = getattr(ufunc, method)(*raw, **kwargs)
+        had64 = any(isinstance(i, np.ndarray) and i.dtype == np.float64 for i in inputs)
+        if isinstance(out, np.ndarray) and out.dtype == np.float64 and not had64:
+            out = out.astype(np.float32)
+        return np.asarray(out).view(Tensor)
+
+    def asnumpy(self):
+        return np.asarray(self).view(np.ndarray)
+
+
+def install_shim():
+    ms = types.ModuleType("mindspore")
+    ms.float32, ms.float16, ms.bool_, ms.int32 = np.float32, np.float16, np.bool_, np.int32
+    ms.Tensor = Tensor
+
+    class Cell:
+        def __init__(self, *a, **k):
+            pass
+
+        def __call__(self, *a, **k):
+            return self.construct(*a, **k)
+
+    nn = types.ModuleType("mindspore.nn")
+    nn.Cell = Cell
+    ms.nn = nn
+    context = types.ModuleType("mindspore.context")
+    context.get_context = lambda key: "CPU"
+    ms.context = context
+    ops = types.ModuleType("mindspore.ops")
+    operations = types.ModuleType("mindspore.ops.operations")
+    operations.ZerosLike = lambda: (lambda x: Tensor(np.zeros_like(np.asarray(x))))
+    rl = types.ModuleType("mindspore.ops.operations._rl_inner_ops")
+    rl.DiscountedReturn = lambda gamma: None
+    operations._rl_inner_ops = rl
+    ops.operations = operations
+    ms.ops = ops
+    for name, mod in [("mindspore", ms), ("mindspore.nn", nn), ("mindspore.context", context),
+                      ("mindspore.ops", ops), ("mindspore.ops.operations", operations),
+                      ("mindspore.ops.operations._rl_inner_ops", rl)]:
+        sys.modules[name] = mod
+
+
+def load_reference():
+    install_shim()
+    spec = importlib.util.spec_from_file_location("ref_discounted_return", REF)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.DiscountedReturn
+
+
+PPO_REF = "/root/reference/mindspore_rl/algorithm/ppo/ppo.py"
+OUT_PPO = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ppo_scans_ref.npz")
+
+
+def load_ppo_closures(next_values):
+    """compiles ppo.py's nested discounted_reward()/gae() as they stand in the reference"""
+    import ast
+    tree = ast.parse(open(PPO_REF).read())
+    wanted = {}
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name in ("discounted_reward", "gae"):
+            wanted[node.name] = node
+
+    class Self:
+        zero_int = 0
+        add = staticmethod(lambda a, b: a + b)
+        mul = staticmethod(lambda a, b: a * b)
+        reshape = staticmethod(lambda a, shp: np.asarray(a).reshape(shp).view(Tensor))
+        squeeze = staticmethod(lambda a: np.squeeze(np.asarray(a), -1).view(Tensor))
+        zeros_like = staticmethod(lambda a: Tensor(np.zeros_like(np.asarray(a))))
+        critic_net = staticmethod(lambda x: next_values)
+
+    ns = {"self": Self(), "len": len}
+    mod = ast.Module(body=[wanted["discounted_reward"], wanted["gae"]], type_ignores=[])
+    exec(compile(mod, PPO_REF, "exec"), ns)
+    return ns["discounted_reward"], ns["gae"]
+
+
+def make_ppo():
+    install_shim()
+    rng = np.random.default_rng(7)
+    cases = {}
+    for name, (B, T), gamma, lam in [("a", (3, 17), 0.99, 0.95), ("b", (30, 200), 0.99, 0.95),
+                                     ("c", (5, 128), 0.9, 0.8), ("d", (2, 1), 0.99, 0.95),
+                                     ("e", (7, 260), 0.995, 0.97)]:
+        reward = rng.normal(size=(B, T, 1)).astype(np.float32)
+        value = rng.normal(size=(B, T, 1)).astype(np.float32)
+        next_value = rng.normal(size=(B, T, 1)).astype(np.float32)
+        disc, gae = load_ppo_closures(Tensor(next_value))
+        g = Tensor([gamma], np.float32).reshape(())  # self.gamma = Tensor(gamma, float32), ppo.py
+        v_last = Tensor(np.zeros((B,), np.float32))
+        dr = disc(Tensor(np.squeeze(reward, -1)), v_last, g)
+        adv = gae(Tensor(reward), None, Tensor(value), v_last, g, lam)
+        cases[f"{name}/reward"] = reward[..., 0]
+        cases[f"{name}/value"] = value[..., 0]
+        cases[f"{name}/next_value"] = next_value[..., 0]
+        cases[f"{name}/gamma"] = np.float32(gamma)
+        cases[f"{name}/lam"] = np.float32(lam)
+        cases[f"{name}/discounted_r"] = np.asarray(dr).view(np.ndarray).astype(np.float32)
+        cases[f"{name}/advantage"] = np.asarray(adv).view(np.ndarray).astype(np.float32)
+        assert np.asarray(adv).dtype == np.float32 and np.asarray(dr).dtype == np.float32
+    np.savez_compressed(OUT_PPO, **cases)
+    print("wrote", OUT_PPO, os.path.getsize(OUT_PPO), "bytes")
+
+
+def main():
+    make_ppo()
+    DR = load_reference()
+    rng = np.random.default_rng(20261019)
+    cases = {}
+    # the reference's own two known-answer vectors (tests/st/test_discounted_return.py:39-53)
+    specs = [("kat0", (4, 1), (4, 1), (1,), 0.99), ("kat1", (4,), (4,), (), 0.99)]
+    shapes = [((7, 3), (7, 3), (3,)), ((64, 8), (64, 8), (8,)), ((33, 5, 4), (33, 5, 1), (5, 4)),
+              ((200, 2), (200, 2), (2,)), ((1, 6), (1, 6), (6,)), ((300, 16, 2), (300, 16, 1), (16, 2))]
+    for i, (rs, ds, ls) in enumerate(shapes):
+        for gamma in (0.99, 0.9, 1.0, 0.0):
+            specs.append((f"rand{i}_g{gamma}", rs, ds, ls, gamma))
+    for name, rs, ds, ls, gamma in specs:
+        if name == "kat0":
+            reward = np.ones(rs, np.float32)
+            done = np.array([[False], [False], [True], [False]])
+            last = np.array([2.0], np.float32)
+        elif name == "kat1":
+            reward = np.ones(rs, np.float32)
+            done = np.array([False, True, False, True])
+            last = np.array(2.0, np.float32)
+        else:
+            reward = rng.normal(size=rs).astype(np.float32)
+            done = rng.random(size=ds) < 0.1
+            last = rng.normal(size=ls).astype(np.float32)
+        net = DR(gamma=gamma)
+        out = net(Tensor(reward, np.float32), Tensor(done), Tensor(last, np.float32))
+        out = np.asarray(out).view(np.ndarray)
+        assert out.dtype == np.float32 and out.shape == reward.shape
+        cases[name + "/reward"] = reward
+        cases[name + "/done"] = done
+        cases[name + "/last"] = last
+        cases[name + "/gamma"] = np.float32(gamma)
+        cases[name + "/out"] = out
+    # sanity: the reference's own expectations
+    assert np.allclose(cases["kat0/out"], np.array([[2.9701], [1.99], [1.0], [2.98]], np.float32))
+    assert np.allclose(cases["kat1/out"], np.array([1.99, 1, 1.99, 1.0], np.float32))
+    np.savez_compressed(OUT, **cases)
+    print("wrote", OUT, len(specs), "cases", os.path.getsize(OUT), "bytes")
+
+
+if __name__ == "__main__":
+    main()

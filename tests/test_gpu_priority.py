@@ -1,0 +1,224 @@
+"""GPU parity of PriorityReplayBuffer against the CPU oracle.  Bit-exact: sampled indices, every
+node of the sum tree and the min tree, max_priority, gathered rows, importance weights."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+from oracle import oracle as O  # noqa: E402
+
+import mindrl_b200 as M  # noqa: E402
+from mindrl_b200 import _ffi  # noqa: E402
+
+
+def dev(a):
+    return torch.as_tensor(np.ascontiguousarray(a)).cuda()
+
+
+def host(t):
+    return t.cpu().numpy() if hasattr(t, "cpu") else np.asarray(t)
+
+
+def same_tree(g, o):
+    gs, gm = g.tree()
+    os_, om = o.tree()
+    assert np.array_equal(gs[1:].view(np.uint32), os_[1:].view(np.uint32)), "sum tree differs"
+    assert np.array_equal(gm[1:].view(np.uint32), om[1:].view(np.uint32)), "min tree differs"
+    assert g.max_priority() == o.max_priority()
+    assert g.info() == o.info()
+
+
+def same_sample(got, want):
+    assert np.array_equal(host(got[0]), want[0]), "indices differ"
+    assert np.array_equal(host(got[1]).view(np.uint32), want[1].view(np.uint32)), "weights differ"
+    for a, b in zip(got[2:], want[2:]):
+        assert np.array_equal(host(a), b), "rows differ"
+
+
+def test_reference_behaviour():
+    # tests/st/test_priority_replay_buffer.py:36-66 with insert() instead of the missing push()
+    capacity, batch = 200, 32
+    prb = M.PriorityReplayBuffer(1.0, capacity, batch, ((17,), (6,)), (np.float32, np.int32), seed0=0, seed1=42)
+    for i in range(100):
+        h = prb.insert(dev(np.ones(17, np.float32) * i), dev(np.ones(6, np.int32) * i))
+    assert h.shape == (1,) and h.dtype == np.int64
+    indices, weights, states, actions = prb.sample(1.0)
+    idx = host(indices)
+    assert idx.dtype == np.int64 and np.all(idx < 100)
+    assert np.allclose(host(states), np.broadcast_to(idx.reshape(-1, 1), states.shape))
+    assert np.allclose(host(actions), np.broadcast_to(idx.reshape(-1, 1), actions.shape))
+    prb.update_priorities(indices, dev(np.ones(batch, np.float32) * 1e-7))
+    indices_new, _, states_new, actions_new = prb.sample(1.0)
+    idx2 = host(indices_new)
+    assert np.all(idx2 < 100) and np.all(idx != idx2)
+    assert np.allclose(host(states_new), np.broadcast_to(idx2.reshape(-1, 1), states_new.shape))
+    assert prb.full() == False  # noqa: E712  (constant, :122-124)
+    with pytest.raises(ValueError):
+        prb.reset()
+    assert prb.destroy().shape == (1,)
+
+
+@pytest.mark.parametrize("capacity,batch", [(1, 1), (2, 2), (3, 4), (37, 8), (64, 16), (1000, 32),
+                                            (2048, 64), (5000, 128), (70000, 256)])
+@pytest.mark.parametrize("carrier", ["device"])
+def test_random_program_against_oracle(capacity, batch, carrier):
+    rng = np.random.default_rng(capacity)
+    shapes, types = [(4,), (1,), (1,), (4,)], [np.float32, np.int32, np.float32, np.float32]
+    g = M.PriorityReplayBuffer(0.6, capacity, batch, shapes, types, 5, 9)
+    o = O.PriorityBufferOracle(0.6, capacity, batch, shapes, types, 5, 9)
+
+    def mk(n):
+        return [rng.normal(size=(n, 4)).astype(np.float32), rng.integers(0, 4, (n, 1)).astype(np.int32),
+                rng.normal(size=(n, 1)).astype(np.float32), rng.normal(size=(n, 4)).astype(np.float32)]
+
+    # single pushes, then batched pushes (with wrap-around), interleaved with sample/update
+    for _ in range(min(capacity, 5)):
+        row = [c[0] for c in mk(1)]
+        g.insert(*[dev(c) for c in row])
+        o.insert(*row)
+    same_tree(g, o)
+    for n in (max(1, capacity // 3), capacity, max(2, capacity // 2 + 1)):
+        b = mk(n)
+        g.insert(*[dev(c) for c in b])
+        o.insert_batch(b)
+        same_tree(g, o)
+        for it in range(3):
+            u = rng.random(batch).astype(np.float32)
+            got = g.sample(0.4, uniforms=dev(u))
+            want = o.sample(0.4, uniforms=u)
+            same_sample(got, want)
+            pr = (np.abs(rng.normal(size=batch)) + 1e-3).astype(np.float32)
+            if it == 1:  # duplicates inside one update batch: last writer wins
+                idx = rng.integers(0, g.info()[0], size=batch)
+                idx[: batch // 2] = idx[batch // 2: 2 * (batch // 2)] if batch > 1 else idx[:0]
+            else:
+                idx = want[0]
+            g.update_priorities(dev(idx), dev(pr))
+            o.update_priorities(idx, pr)
+            same_tree(g, o)
+    # the buffer's own generator (no injected uniforms) is the same stream on both sides
+    same_sample(g.sample(0.7), o.sample(0.7))
+    same_sample(g.sample(0.7), o.sample(0.7))
+
+
+def test_host_carrier_matches_oracle():
+    rng = np.random.default_rng(3)
+    shapes, types = [(4,), (1,)], [np.float32, np.int32]
+    g = M.PriorityReplayBuffer(0.6, 500, 32, shapes, types, 1, 2, carrier="numpy")
+    o = O.PriorityBufferOracle(0.6, 500, 32, shapes, types, 1, 2)
+    for i in range(20):
+        row = [rng.normal(size=4).astype(np.float32), np.array([i], np.int32)]
+        g.insert(*row)
+        o.insert(*row)
+    b = [rng.normal(size=(700, 4)).astype(np.float32), np.arange(700, dtype=np.int32)[:, None]]
+    g.insert(*b)
+    o.insert_batch(b)
+    for _ in range(4):
+        u = rng.random(32).astype(np.float32)
+        got, want = g.sample(0.5, uniforms=u), o.sample(0.5, uniforms=u)
+        assert isinstance(got[0], np.ndarray)
+        same_sample(got, want)
+        pr = (rng.random(32) * 3).astype(np.float32)
+        g.update_priorities(want[0], pr)
+        o.update_priorities(want[0], pr)
+    same_tree(g, o)
+
+
+def test_zero_and_negative_priorities_are_clamped():
+    g = M.PriorityReplayBuffer(0.6, 16, 4, [(1,)], [np.int32])
+    o = O.PriorityBufferOracle(0.6, 16, 4, [(1,)], [np.int32])
+    b = [np.arange(16, dtype=np.int32)[:, None]]
+    g.insert(*[dev(c) for c in b])
+    o.insert_batch(b)
+    idx = np.array([0, 1, 2, 3]); pr = np.array([0.0, 5.0, 1e-30, 2.0], np.float32)
+    g.update_priorities(dev(idx), dev(pr))
+    o.update_priorities(idx, pr)
+    same_tree(g, o)
+    assert g.tree()[0][16] == np.float32(1e-7)
+
+
+def test_c2_shape_loop_bit_exact():
+    """BASELINE config 2: capacity 1M (2^20 leaves), 40-byte rows, batch 256, alpha .6 beta .4"""
+    rng = np.random.default_rng(2)
+    cap, batch = 1_000_000, 256
+    shapes, types = [(4,), (1,), (1,), (4,)], [np.float32, np.int32, np.float32, np.float32]
+    g = M.PriorityReplayBuffer(0.6, cap, batch, shapes, types, 0, 1)
+    o = O.PriorityBufferOracle(0.6, cap, batch, shapes, types, 0, 1)
+    obs = rng.normal(size=(cap, 4)).astype(np.float32)
+    b = [obs, rng.integers(0, 2, (cap, 1)).astype(np.int32), rng.normal(size=(cap, 1)).astype(np.float32), obs[::-1].copy()]
+    g.insert(*[dev(c) for c in b])
+    o.insert_batch(b)
+    pr0 = (np.abs(rng.normal(size=cap)) + 1e-3).astype(np.float32)
+    for s in range(0, cap, 4096):  # initial priorities through the update path itself
+        idx = np.arange(s, min(cap, s + 4096))
+        g.update_priorities(dev(idx), dev(pr0[idx]))
+        o.update_priorities(idx, pr0[idx])
+    same_tree(g, o)
+    for step in range(60):
+        u = rng.random(batch).astype(np.float32)
+        got, want = g.sample(0.4, uniforms=dev(u)), o.sample(0.4, uniforms=u)
+        same_sample(got, want)
+        pr = (np.abs(rng.normal(size=batch)) + 1e-3).astype(np.float32)
+        g.update_priorities(got[0], dev(pr))
+        o.update_priorities(want[0], pr)
+    same_tree(g, o)
+    gs, _ = g.tree()
+    assert np.isfinite(gs[1]) and gs[1] > 0
+
+
+def test_wide_rows_embed_their_slot():
+    """C3-shaped rows (84x84x4 uint8 twice + small columns) at a capacity that fits quickly: the
+    gather goes through the TMA ring; every sampled row must carry its own index."""
+    cap, batch = 4096, 512
+    rb = np.asarray([28224, 4, 4, 1, 28224], dtype=np.int64)
+    h = C.c_int64(-1)
+    L = _ffi.lib()
+    _ffi.check(L.mrl_prb_create(cap, 0.6, 5, rb.ctypes.data, 0, 0, C.byref(h)))
+    src = [torch.empty((cap, int(r)), dtype=torch.uint8, device="cuda") for r in rb]
+    for c, t in enumerate(src):
+        _ffi.check(L.mrl_fill_rows(t.data_ptr(), cap, int(rb[c]), 100 + c, 0))
+    _ffi.check(L.mrl_prb_push_batch(h.value, cap, _ffi.ptr_table([t.data_ptr() for t in src]), 0))
+    rng = np.random.default_rng(8)
+    pr = (np.abs(rng.normal(size=cap)) + 1e-3).astype(np.float32)
+    _ffi.check(L.mrl_prb_update(h.value, dev(np.arange(cap)).data_ptr(), dev(pr).data_ptr(), cap, 0))
+    idx = torch.empty(batch, dtype=torch.int64, device="cuda")
+    w = torch.empty(batch, dtype=torch.float32, device="cuda")
+    outs = [torch.empty((batch, int(r)), dtype=torch.uint8, device="cuda") for r in rb]
+    _ffi.check(L.mrl_prb_sample(h.value, batch, 0.4, None, idx.data_ptr(), w.data_ptr(),
+                                _ffi.ptr_table([t.data_ptr() for t in outs]), 0))
+    torch.cuda.synchronize()
+    i = idx.cpu().numpy()
+    assert i.min() >= 0 and i.max() < cap and len(np.unique(i)) > batch // 2
+    for c in (0, 4):
+        got = outs[c].cpu().numpy()
+        assert np.array_equal(got[:, :8].copy().view(np.int64)[:, 0], i)
+        assert np.array_equal(got, O.fill_rows(cap, int(rb[c]), 100 + c)[i])
+    for c in (1, 2, 3):
+        assert np.array_equal(outs[c].cpu().numpy(), O.fill_rows(cap, int(rb[c]), 100 + c)[i])
+    ww = w.cpu().numpy()
+    assert np.all(ww > 0) and np.all(ww <= 1.0)
+    _ffi.check(L.mrl_prb_destroy(h.value))
+
+
+def test_sharded_weights_against_oracle():
+    rng = np.random.default_rng(6)
+    shapes, types = [(2,)], [np.float32]
+    g = M.PriorityReplayBuffer(0.6, 1024, 64, shapes, types, 3, 4)
+    o = O.PriorityBufferOracle(0.6, 1024, 64, shapes, types, 3, 4)
+    b = [rng.normal(size=(1024, 2)).astype(np.float32)]
+    g.insert(*[dev(c) for c in b])
+    o.insert_batch(b)
+    pr = (rng.random(1024) + 0.01).astype(np.float32)
+    g.update_priorities(dev(np.arange(1024)), dev(pr))
+    o.update_priorities(np.arange(1024), pr)
+    st = host(g.root_stats())
+    assert np.array_equal(st, o.root_stats())
+    others = np.array([[st[0] * 2.5, st[1] * 0.5, 777.0, 3.0], [st[0] * 0.1, st[1] * 4, 10.0, 1.0]], np.float32)
+    gstats = np.concatenate([others[:1], st[None], others[1:]], 0)
+    u = rng.random(64).astype(np.float32)
+    got = g.sample(0.4, uniforms=dev(u), gstats=dev(gstats))
+    want = o.sample(0.4, uniforms=u, gstats=gstats)
+    same_sample(got, want)

@@ -1,0 +1,213 @@
+"""GPU parity of the reverse scans against the CPU oracle, the reference's known answers and the
+golden vectors.  Tolerances: sequential mode bit-exact; parallel modes |gpu-oracle| <= 1e-5 *
+max(|oracle|, 1) (spec: 1e-5 relative in fp32)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+from oracle import oracle as O  # noqa: E402
+
+import mindrl_b200 as M  # noqa: E402
+
+RTOL = 1e-5
+
+
+def dev(a):
+    return torch.as_tensor(np.ascontiguousarray(a)).cuda()
+
+
+def close(gpu, ref):
+    gpu = gpu.cpu().numpy() if hasattr(gpu, "cpu") else np.asarray(gpu)
+    err = np.abs(gpu.astype(np.float64) - ref.astype(np.float64))
+    bound = RTOL * np.maximum(np.abs(ref.astype(np.float64)), 1.0)
+    assert gpu.shape == ref.shape
+    assert np.all(err <= bound), f"max err {err.max()} at {np.unravel_index(err.argmax(), err.shape)}"
+
+
+def exact(gpu, ref):
+    gpu = gpu.cpu().numpy() if hasattr(gpu, "cpu") else np.asarray(gpu)
+    assert gpu.shape == ref.shape
+    assert np.array_equal(gpu.view(np.uint32), ref.view(np.uint32))
+
+
+def test_known_answers_device_and_host():
+    net = M.DiscountedReturn(gamma=0.99)
+    r = np.array([[1], [1], [1], [1]], np.float32)
+    d = np.array([[False], [False], [True], [False]])
+    want = np.array([[2.9701], [1.99], [1.0], [2.98]], np.float32)
+    out = net(dev(r), dev(d), dev(np.array([2.0], np.float32)))
+    assert out.is_cuda and np.allclose(out.cpu().numpy(), want)
+    out = net(r, d, np.array([2.0], np.float32))  # numpy carrier -> host entry point
+    assert isinstance(out, np.ndarray) and np.allclose(out, want)
+    r = np.array([1, 1, 1, 1], np.float32)
+    d = np.array([False, True, False, True])
+    want = np.array([1.99, 1, 1.99, 1.0], np.float32)
+    assert np.allclose(net(dev(r), dev(d), dev(np.float32(2.0))).cpu().numpy(), want)
+    assert np.allclose(net(r, d, np.float32(2.0)), want)
+    with pytest.raises(ValueError):
+        M.DiscountedReturn(gamma=1.5)
+
+
+def test_discounted_return_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "discounted_return_ref.npz"))
+    for n in sorted({k.split("/")[0] for k in g.files}):
+        args = (dev(g[n + "/reward"]), dev(g[n + "/done"]), dev(g[n + "/last"]))
+        gamma = float(g[n + "/gamma"])
+        exact(M.DiscountedReturn(gamma, mode="sequential")(*args), g[n + "/out"])
+        close(M.DiscountedReturn(gamma, mode="parallel")(*args), g[n + "/out"])
+        close(M.DiscountedReturn(gamma)(*args), g[n + "/out"])
+
+
+def test_ppo_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "ppo_scans_ref.npz"))
+    for n in sorted({k.split("/")[0] for k in g.files}):
+        gamma, lam = float(g[n + "/gamma"]), float(g[n + "/lam"])
+        r, v, nv = dev(g[n + "/reward"]), dev(g[n + "/value"]), dev(g[n + "/next_value"])
+        exact(M.discounted_reward(r, gamma, layout="batch_major", mode="sequential"), g[n + "/discounted_r"])
+        close(M.discounted_reward(r, gamma, layout="batch_major"), g[n + "/discounted_r"])
+        adv, ret = M.gae(r, v, gamma, lam, next_value=nv, layout="batch_major", mode="sequential")
+        exact(adv, g[n + "/advantage"])
+        adv, ret = M.gae(r, v, gamma, lam, next_value=nv, layout="batch_major")
+        close(adv, g[n + "/advantage"])
+        close(ret, g[n + "/advantage"] + g[n + "/value"])
+
+
+@pytest.mark.parametrize("T,B,E", [(1, 1, 1), (5, 3, 1), (64, 33, 1), (257, 40, 3), (1000, 30, 1),
+                                   (2048, 96, 1), (300, 5000, 1), (513, 7, 2)])
+def test_discounted_return_time_major(T, B, E):
+    rng = np.random.default_rng(T * 131 + B)
+    shape = (T, B, E) if E > 1 else (T, B)
+    r = rng.normal(size=shape).astype(np.float32)
+    d = rng.random((T, B)) < 0.05
+    lv = rng.normal(size=shape[1:]).astype(np.float32)
+    ref = O.discounted_return(r, d, lv, 0.99)
+    exact(M.DiscountedReturn(0.99, mode="sequential")(dev(r), dev(d), dev(lv)), ref)
+    close(M.DiscountedReturn(0.99, mode="parallel")(dev(r), dev(d), dev(lv)), ref)
+    close(M.DiscountedReturn(0.99)(dev(r), dev(d), dev(lv)), ref)
+    # no done flags, no bootstrap
+    ref = O.discounted_return(r, None, None, 0.9)
+    close(M.discounted_reward(dev(r.reshape(T, -1)), 0.9, layout="time_major"), ref.reshape(T, -1))
+
+
+@pytest.mark.parametrize("B,T", [(1, 1), (3, 5), (7, 128), (30, 1000), (17, 130), (64, 2048), (5, 127),
+                                 (9, 4), (2, 4099)])
+@pytest.mark.parametrize("with_done", [False, True])
+def test_batch_major(B, T, with_done):
+    rng = np.random.default_rng(B * 1009 + T)
+    r = rng.normal(size=(B, T)).astype(np.float32)
+    v = rng.normal(size=(B, T)).astype(np.float32)
+    nv = rng.normal(size=(B, T)).astype(np.float32)
+    lv = rng.normal(size=(B,)).astype(np.float32)
+    d = (rng.random((B, T)) < 0.05) if with_done else None
+    dd = None if d is None else dev(d)
+    ref = O.discounted_return(r, d, lv, 0.99, layout=1)
+    close(M.discounted_reward(dev(r), 0.99, last_value=dev(lv), done=dd), ref)
+    exact(M.discounted_reward(dev(r), 0.99, last_value=dev(lv), done=dd, mode="sequential"), ref)
+    # GAE, bootstrap from value[t+1] / last_value
+    adv_r, ret_r = O.gae(r, v, None, lv, d, 0.99, 0.95, layout=1)
+    adv, ret = M.gae(dev(r), dev(v), 0.99, 0.95, last_value=dev(lv), done=dd, layout="batch_major")
+    close(adv, adv_r)
+    close(ret, ret_r)
+    adv, ret = M.gae(dev(r), dev(v), 0.99, 0.95, last_value=dev(lv), done=dd, layout="batch_major",
+                     mode="sequential")
+    exact(adv, adv_r)
+    exact(ret, ret_r)
+    # GAE, PPO form with a separate next_value array
+    adv_r, ret_r = O.gae(r, v, nv, None, d, 0.99, 0.95, layout=1)
+    adv, ret = M.gae(dev(r), dev(v), 0.99, 0.95, next_value=dev(nv), done=dd, layout="batch_major")
+    close(adv, adv_r)
+    close(ret, ret_r)
+
+
+@pytest.mark.parametrize("T,B", [(1, 1), (25, 8), (64, 33), (1000, 30), (2048, 128), (100, 6000)])
+@pytest.mark.parametrize("with_done", [False, True])
+def test_gae_time_major(T, B, with_done):
+    rng = np.random.default_rng(T * 7 + B)
+    r = rng.normal(size=(T, B)).astype(np.float32)
+    val = rng.normal(size=(T + 1, B)).astype(np.float32)
+    d = (rng.random((T, B)) < 0.05) if with_done else None
+    dd = None if d is None else dev(d)
+    adv_r, ret_r = O.gae(r, val[:T], None, val[T], d, 0.99, 0.95, layout=0)
+    vd = dev(val)
+    for mode, cmp in (("sequential", exact), ("parallel", close), ("auto", close)):
+        adv, ret = M.gae(dev(r), vd[:T], 0.99, 0.95, last_value=vd[T], done=dd, mode=mode)
+        cmp(adv, adv_r)
+        cmp(ret, ret_r)
+    adv, ret = M.gae(dev(r), vd[:T], 0.99, 0.95, last_value=vd[T], done=dd, want_returns=False)
+    assert ret is None
+    close(adv, adv_r)
+
+
+def test_gae_host_path():
+    rng = np.random.default_rng(11)
+    T, B = 300, 64
+    r = rng.normal(size=(T, B)).astype(np.float32)
+    v = rng.normal(size=(T, B)).astype(np.float32)
+    lv = rng.normal(size=(B,)).astype(np.float32)
+    d = rng.random((T, B)) < 0.05
+    adv_r, ret_r = O.gae(r, v, None, lv, d, 0.99, 0.95, layout=0)
+    adv, ret = M.gae(r, v, 0.99, 0.95, last_value=lv, done=d)
+    assert isinstance(adv, np.ndarray)
+    close(adv, adv_r)
+    close(ret, ret_r)
+
+
+def test_affine_scan_vtrace_form():
+    rng = np.random.default_rng(12)
+    for layout, shape in (("time_major", (80, 40)), ("batch_major", (40, 80)), ("batch_major", (3, 77))):
+        a = rng.normal(size=shape).astype(np.float32)
+        b = (0.99 * np.minimum(1.0, rng.random(shape) * 2) * (rng.random(shape) > 0.1)).astype(np.float32)
+        lay = 0 if layout == "time_major" else 1
+        xl = rng.normal(size=(shape[1] if lay == 0 else shape[0],)).astype(np.float32)
+        ref = O.affine_scan(a, b, xl, layout=lay)
+        close(M.affine_scan(dev(a), dev(b), dev(xl), layout=layout), ref)
+        exact(M.affine_scan(dev(a), dev(b), dev(xl), layout=layout, mode="sequential"), ref)
+
+
+def test_full_size_c4_against_oracle_and_float64():
+    """BASELINE config 4: 4096 envs x 2048 steps, gamma .99 lambda .95, random done flags"""
+    rng = np.random.default_rng(4)
+    T, B = 2048, 4096
+    r = rng.normal(size=(T, B)).astype(np.float32)
+    val = rng.normal(size=(T + 1, B)).astype(np.float32)
+    d = rng.random((T, B)) < 1 / 200
+    adv_r, ret_r = O.gae(r, val[:T], None, val[T], d, 0.99, 0.95, layout=0)
+    vd = dev(val)
+    adv, ret = M.gae(dev(r), vd[:T], 0.99, 0.95, last_value=vd[T], done=dev(d))
+    close(adv, adv_r)
+    close(ret, ret_r)
+    adv_s, _ = M.gae(dev(r), vd[:T], 0.99, 0.95, last_value=vd[T], done=dev(d), mode="sequential")
+    exact(adv_s, adv_r)
+    # float64 ground truth: the parallel kernel is no further from it than the fp32 oracle (x4)
+    m = 1.0 - d.astype(np.float64)
+    delta = r.astype(np.float64) + np.float32(0.99).astype(np.float64) * np.concatenate([val[1:T], val[T:]]).astype(np.float64) * m - val[:T].astype(np.float64)
+    gl = np.float64(np.float32(0.99) * np.float32(0.95))
+    truth = np.zeros((T, B))
+    acc = np.zeros(B)
+    for t in range(T - 1, -1, -1):
+        acc = delta[t] + gl * m[t] * acc
+        truth[t] = acc
+    e_gpu = np.abs(adv.cpu().numpy() - truth).max()
+    e_orc = np.abs(adv_r - truth).max()
+    assert e_gpu <= 4 * e_orc + 1e-6
+    # batch-major twin of the same problem
+    adv_b, ret_b = M.gae(dev(r.T.copy()), dev(val[:T].T.copy()), 0.99, 0.95, last_value=vd[T],
+                         done=dev(d.T.copy()), layout="batch_major")
+    close(adv_b, adv_r.T)
+    close(ret_b, ret_r.T)
+    dr_r = O.discounted_return(r, d, val[T], 0.99)
+    close(M.DiscountedReturn(0.99)(dev(r), dev(d), vd[T]), dr_r)
+    exact(M.DiscountedReturn(0.99, mode="sequential")(dev(r), dev(d), vd[T]), dr_r)
+
+
+def test_empty_and_errors():
+    out = M.DiscountedReturn(0.9)(torch.zeros((0, 4), device="cuda"), torch.zeros((0, 4), dtype=torch.bool, device="cuda"),
+                                  torch.zeros((4,), device="cuda"))
+    assert tuple(out.shape) == (0, 4)
+    with pytest.raises(ValueError):
+        M.DiscountedReturn(0.9)(torch.zeros((3, 4), device="cuda"), torch.zeros((3, 5), dtype=torch.bool, device="cuda"),
+                                torch.zeros((4,), device="cuda"))

@@ -1,0 +1,150 @@
+"""GPU parity of UniformReplayBuffer (BufferAppend / BufferGetItem / BufferSample) against the CPU
+oracle: cursor state, column bytes, logical indexing, drawn slots and gathered rows, all bit-exact."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+from oracle import oracle as O  # noqa: E402
+
+import mindrl_b200 as M  # noqa: E402
+from mindrl_b200 import _ffi  # noqa: E402
+
+SHAPES = [(4,), (1,), (1,), (4,)]
+TYPES = [np.float32, np.int32, np.float32, np.float32]
+
+
+def dev(a):
+    return torch.as_tensor(np.ascontiguousarray(a)).cuda()
+
+
+def rows(rng, n):
+    return [rng.normal(size=(n, 4)).astype(np.float32), rng.integers(0, 2, size=(n, 1)).astype(np.int32),
+            rng.normal(size=(n, 1)).astype(np.float32), rng.normal(size=(n, 4)).astype(np.float32)]
+
+
+def same_columns(gpu, orc):
+    for g, o in zip(gpu.buffer, orc.columns()):
+        assert np.array_equal(g.cpu().numpy().view(np.uint8), o.view(np.uint8))
+
+
+@pytest.mark.parametrize("carrier", ["device", "host"])
+def test_append_get_item_sequence(carrier):
+    rng = np.random.default_rng(0)
+    cap = 100
+    g = M.UniformReplayBuffer(8, cap, SHAPES, TYPES, seed=3)
+    o = O.UniformBufferOracle(8, cap, SHAPES, TYPES, seed=3)
+    assert g.count == 0 and g.head == 0 and not g.full()[0] and g.size() == 0
+    for n in (1, 1, 7, 50, 41, 1, 13, 99, 100, 250, 1, 3):
+        batch = rows(rng, n)
+        if n == 1:  # single transition without the batch dim, as trainers pass it
+            batch = [b[0] for b in batch]
+        ret = g.insert([dev(b) for b in batch] if carrier == "device" else batch)
+        assert ret is g.buffer
+        o.insert(batch)
+        assert (g.count, g.head) == o.state()
+        same_columns(g, o)
+        for idx in (0, 1, g.count - 1, -1, g.count // 2):
+            if -g.count <= idx < g.count:
+                got = g.get_item(idx)
+                want = o.get_item(idx)
+                for a, b in zip(got, want):
+                    assert np.array_equal(a.cpu().numpy(), b)
+    assert g.full()[0] and int(g.size()) == cap
+    with pytest.raises(IndexError):
+        g.get_item(cap)
+    assert g.reset() is True
+    assert g.count == 0 and g.head == o.state()[1]
+
+
+def test_sample_draws_and_rows_match_oracle():
+    rng = np.random.default_rng(1)
+    cap = 1000
+    g = M.UniformReplayBuffer(64, cap, SHAPES, TYPES, seed=11)
+    o = O.UniformBufferOracle(64, cap, SHAPES, TYPES, seed=11)
+    with pytest.raises(RuntimeError):
+        g.sample()
+    batch = rows(rng, 600)
+    g.insert([dev(b) for b in batch])
+    o.insert(batch)
+    for _ in range(5):
+        got = g.sample()
+        slots, want = o.sample()
+        for a, b in zip(got, want):
+            assert tuple(a.shape) == b.shape and np.array_equal(a.cpu().numpy(), b)
+    # explicit slots, host carrier
+    gh = M.UniformReplayBuffer(64, cap, SHAPES, TYPES, seed=11, carrier="numpy")
+    gh.insert(batch)
+    for _ in range(2):
+        o2 = O.UniformBufferOracle(64, cap, SHAPES, TYPES, seed=11)
+        o2.insert(batch)
+        got = gh.sample()
+        _, want = o2.sample()
+        assert all(isinstance(a, np.ndarray) for a in got)
+        for a, b in zip(got, want):
+            assert np.array_equal(a, b)
+        break
+    slots = rng.integers(0, 600, size=333)
+    got = g.gather(dev(slots))
+    want = o.gather(slots)
+    for a, b in zip(got, want):
+        assert np.array_equal(a.cpu().numpy(), b)
+
+
+@pytest.mark.parametrize("path", ["bulk", "ldg"])
+def test_wide_rows_gather_paths(path):
+    """Atari-shaped rows (84*84*4 bytes) through the TMA ring and through the register path, plus
+    odd row sizes; rows are the deterministic fill so every byte is checked."""
+    cap, n = 2000, 257
+    _ffi.set_option("gather_path", 2 if path == "bulk" else 1)
+    for row_bytes in (28224, 4096, 28224 + 16, 1000, 6, 3):
+        rb = np.asarray([row_bytes, 8], dtype=np.int64)
+        h = C.c_int64(-1)
+        _ffi.check(_ffi.lib().mrl_urb_create(cap, 2, rb.ctypes.data, None, 0, C.byref(h)))
+        cols = (C.c_void_p * 2)()
+        _ffi.check(_ffi.lib().mrl_urb_columns(h.value, cols))
+        _ffi.check(_ffi.lib().mrl_fill_rows(cols[0], cap, row_bytes, 77, 0))
+        _ffi.check(_ffi.lib().mrl_fill_rows(cols[1], cap, 8, 78, 0))
+        ref0, ref1 = O.fill_rows(cap, row_bytes, 77), O.fill_rows(cap, 8, 78)
+        slots = np.random.default_rng(row_bytes).integers(0, cap, size=n)
+        slots[:3] = [0, cap - 1, cap - 1]
+        ds = dev(slots)
+        out0 = torch.empty((n, row_bytes), dtype=torch.uint8, device="cuda")
+        out1 = torch.empty((n, 8), dtype=torch.uint8, device="cuda")
+        tab = _ffi.ptr_table([out0.data_ptr(), out1.data_ptr()])
+        _ffi.check(_ffi.lib().mrl_urb_gather(h.value, ds.data_ptr(), n, tab, 0))
+        torch.cuda.synchronize()
+        assert np.array_equal(out0.cpu().numpy(), ref0[slots])
+        assert np.array_equal(out1.cpu().numpy(), ref1[slots])
+        if row_bytes >= 8:
+            assert np.array_equal(out0.cpu().numpy()[:, :8].copy().view(np.int64)[:, 0], slots)
+        _ffi.check(_ffi.lib().mrl_urb_destroy(h.value))
+    _ffi.set_option("gather_path", 0)
+
+
+def test_bulk_append_wide_rows_and_wrap():
+    cap = 300
+    shapes, types = [(84, 84, 4), (1,)], [np.uint8, np.int32]
+    g = M.UniformReplayBuffer(16, cap, shapes, types)
+    o = O.UniformBufferOracle(16, cap, shapes, types)
+    rng = np.random.default_rng(2)
+    for n in (200, 170, 5):
+        obs = rng.integers(0, 256, size=(n, 84, 84, 4), dtype=np.uint8)
+        act = rng.integers(0, 18, size=(n, 1)).astype(np.int32)
+        g.insert([dev(obs), dev(act)])
+        o.insert([obs, act])
+        assert (g.count, g.head) == o.state()
+    same_columns(g, o)
+    got, want = g.sample(), None
+    assert tuple(got[0].shape) == (16, 84, 84, 4)
+
+
+def test_launch_counter_moves():
+    before = _ffi.launch_count()
+    g = M.UniformReplayBuffer(4, 10, [(1,)], [np.float32])
+    g.insert([dev(np.ones((3, 1), np.float32))])
+    g.sample()
+    assert _ffi.launch_count() >= before + 2

@@ -1,0 +1,145 @@
+"""Host-side logic that needs no GPU: dtype / column bookkeeping, API quirks the reference keeps,
+and the N>1 path of the sharded buffer (world_size 2 over gloo) with the oracle standing in for the
+per-rank device buffer."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_dtype_mapping():
+    from mindrl_b200 import _carrier as K
+    import torch
+    assert K.np_dtype(np.float32) == np.float32 and K.np_dtype("int32") == np.int32
+    assert K.np_dtype(torch.float32) == np.float32 and K.np_dtype(torch.bool) == np.bool_
+    assert K.np_dtype(torch.uint8) == np.uint8 and K.np_dtype(torch.int64) == np.int64
+
+    class FakeMsType:  # mindspore.dtype objects print as "Float32", "Int32", "Bool"
+        def __init__(self, n):
+            self.n = n
+
+        def __str__(self):
+            return self.n
+
+    assert K.np_dtype(FakeMsType("Float32")) == np.float32
+    assert K.np_dtype(FakeMsType("Bool")) == np.bool_
+    with pytest.raises(TypeError):
+        K.np_dtype(FakeMsType("Tuple"))
+
+
+def test_column_spec_rows():
+    from mindrl_b200.core._columns import ColumnSpec
+    spec = ColumnSpec([(4,), (1,), (84, 84, 4)], [np.float32, np.int32, np.uint8])
+    assert spec.row_bytes == [16, 4, 28224]
+    one = [np.zeros(4, np.float32), np.zeros(1, np.int32), np.zeros((84, 84, 4), np.uint8)]
+    assert spec.rows_in(one) == 1
+    many = [np.zeros((7, 4)), np.zeros((7, 1)), np.zeros((7, 84, 84, 4), np.uint8)]
+    assert spec.rows_in(many) == 7
+    with pytest.raises(ValueError):
+        spec.rows_in([np.zeros((7, 4)), np.zeros((6, 1)), np.zeros((7, 84, 84, 4), np.uint8)])
+    with pytest.raises(ValueError):
+        spec.rows_in(one[:2])
+    kind, arrs, tab = spec.prepare_inputs(many)
+    assert kind == "host" and arrs[0].dtype == np.float32 and arrs[1].dtype == np.int32
+
+
+def test_gamma_validation_matches_reference():
+    import mindrl_b200 as M
+    for bad in (-0.1, 1.0001):
+        with pytest.raises(ValueError, match=r"range \[0, 1\]"):
+            M.DiscountedReturn(gamma=bad)
+    M.DiscountedReturn(gamma=0.0)
+    M.DiscountedReturn(gamma=1.0)
+
+
+def test_sharded_index_math():
+    from mindrl_b200.core import sharded_priority_replay_buffer as S
+    assert S.split_capacity(8_000_000, 8) == 1_000_000
+    with pytest.raises(ValueError):
+        S.split_capacity(10, 3)
+    loc = np.array([0, 5, 999_999])
+    glob = S.to_global(loc, 3, 1_000_000)
+    assert np.array_equal(glob, loc + 3_000_000)
+    assert np.array_equal(S.to_local(glob, 3, 1_000_000), loc)
+    assert np.array_equal(S.owner_of(glob, 1_000_000), [3, 3, 3])
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from oracle import oracle as O
+    from mindrl_b200.core.sharded_priority_replay_buffer import ShardedPriorityReplayBuffer
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    class Local:  # oracle-backed stand-in with the device buffer's interface
+        def __init__(self):
+            self.b = O.PriorityBufferOracle(0.6, 256, 16, [(2,)], [np.float32], 7, rank)
+            rng = np.random.default_rng(100 + rank)
+            self.b.insert_batch([rng.normal(size=(200 + 20 * rank, 2)).astype(np.float32)])
+            n = self.b.info()[0]
+            self.b.update_priorities(np.arange(n), (rng.random(n) * (rank + 1) + 0.01).astype(np.float32))
+
+        def insert(self, *t):
+            self.b.insert(*t)
+
+        def root_stats(self):
+            return self.b.root_stats()
+
+        def sample(self, beta, uniforms=None, gstats=None):
+            out = self.b.sample(beta, uniforms=uniforms, gstats=gstats.numpy())
+            return tuple(torch.as_tensor(o) for o in out)
+
+        def update_priorities(self, idx, pr):
+            self.b.update_priorities(np.asarray(idx), np.asarray(pr))
+
+    local = Local()
+    sh = ShardedPriorityReplayBuffer(local, 256)
+    g = sh.global_stats()
+    u = np.linspace(0.01, 0.99, 16).astype(np.float32)
+    idx, w, rows = sh.sample(0.4, uniforms=u)
+    # every rank recomputes the expected weights from the gathered stats
+    exp_idx, exp_w, _ = local.b.sample(0.4, uniforms=u, gstats=g.numpy())
+    ok = (tuple(g.shape) == (world, 4)
+          and np.array_equal(idx.numpy(), exp_idx + rank * 256)
+          and np.array_equal(w.numpy(), exp_w)
+          and float(g[rank, 2]) == 200 + 20 * rank
+          and bool(np.all(w.numpy() <= 1.0)))
+    before = local.b.tree()[0].copy()
+    sh.update_priorities(idx, torch.full((16,), 2.5))
+    after = local.b.tree()[0]
+    ok = ok and not np.array_equal(before, after) and after[256 + int(exp_idx[0])] == O.detpow(np.float32(2.5), np.float32(0.6))[0]
+    gathered = [None] * world
+    dist.all_gather_object(gathered, g.numpy().tolist())
+    ok = ok and all(x == gathered[0] for x in gathered)
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_sharded_buffer_world2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(results) == [(0, True), (1, True)]
