@@ -183,7 +183,8 @@ def test_wide_rows_embed_their_slot():
     _ffi.check(L.mrl_prb_push_batch(h.value, cap, _ffi.ptr_table([t.data_ptr() for t in src]), 0))
     rng = np.random.default_rng(8)
     pr = (np.abs(rng.normal(size=cap)) + 1e-3).astype(np.float32)
-    _ffi.check(L.mrl_prb_update(h.value, dev(np.arange(cap)).data_ptr(), dev(pr).data_ptr(), cap, 0))
+    d_all, d_pr = dev(np.arange(cap)), dev(pr)  # keep both alive across the asynchronous call
+    _ffi.check(L.mrl_prb_update(h.value, d_all.data_ptr(), d_pr.data_ptr(), cap, 0))
     idx = torch.empty(batch, dtype=torch.int64, device="cuda")
     w = torch.empty(batch, dtype=torch.float32, device="cuda")
     outs = [torch.empty((batch, int(r)), dtype=torch.uint8, device="cuda") for r in rb]

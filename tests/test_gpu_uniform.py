@@ -145,6 +145,6 @@ def test_bulk_append_wide_rows_and_wrap():
 def test_launch_counter_moves():
     before = _ffi.launch_count()
     g = M.UniformReplayBuffer(4, 10, [(1,)], [np.float32])
-    g.insert([dev(np.ones((3, 1), np.float32))])
+    g.insert([dev(np.ones((5, 1), np.float32))])
     g.sample()
     assert _ffi.launch_count() >= before + 2
