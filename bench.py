@@ -350,9 +350,9 @@ def bench_gae(ctx, steps, warmup):
         ffi.check(L.mrl_gae(r.data_ptr(), v.data_ptr(), None, v[T].data_ptr(), d.data_ptr(),
                             adv.data_ptr(), ret.data_ptr(), T, B, 0.99, 0.95, 0, 1, st))
 
-    def gae_bm(i):  # same bytes read as [B, T]
+    def gae_bm(i):  # the same buffers read as [B envs, T steps] (PPO layout)
         ffi.check(L.mrl_gae(r.data_ptr(), v.data_ptr(), None, v[T].data_ptr(), d.data_ptr(),
-                            adv.data_ptr(), ret.data_ptr(), B, T, 0.99, 0.95, 1, 0, st))
+                            adv.data_ptr(), ret.data_ptr(), T, B, 0.99, 0.95, 1, 0, st))
 
     def dr_tm(i):
         ffi.check(L.mrl_discounted_return(r.data_ptr(), d.data_ptr(), v[T].data_ptr(), adv.data_ptr(),
@@ -360,13 +360,13 @@ def bench_gae(ctx, steps, warmup):
 
     def dr_bm(i):
         ffi.check(L.mrl_discounted_return(r.data_ptr(), d.data_ptr(), v[T].data_ptr(), adv.data_ptr(),
-                                          B, T, 1, 0.99, 1, 0, st))
+                                          T, B, 1, 0.99, 1, 0, st))
 
     run("gae_time_major[T,B]", gae_tm, 17, 4 * B)
     run("gae_time_major_sequential(bit-exact)", gae_tm_seq, 17, 4 * B)
-    run("gae_batch_major[B,T]", gae_bm, 17, 4 * T)
+    run("gae_batch_major[B,T]", gae_bm, 17, 4 * B)
     run("discounted_return_time_major", dr_tm, 9, 4 * B)
-    run("discounted_return_batch_major", dr_bm, 9, 4 * T)
+    run("discounted_return_batch_major", dr_bm, 9, 4 * B)
     main = out["gae_time_major[T,B]"]
     roofline = {"bound": "hbm", "kernel": "scan_tm_chunked_kernel<GAE>", "achieved": main["GBps"],
                 "peak": hbm, "unit": "GB/s", "frac": main["frac"], "traffic": None,

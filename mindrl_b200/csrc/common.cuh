@@ -103,8 +103,9 @@ struct Staging {
   void release();
 };
 
+// gathers the columns selected by col_mask (bit c = column c)
 int gather_rows(const ColTable &tab, const int64_t *slots, int64_t n, int64_t capacity,
-                cudaStream_t st);
+                cudaStream_t st, uint32_t col_mask = 0xffffffffu);
 int copy_segments(const ColTable &tab, int64_t dst_row, int64_t src_row, int64_t nrows,
                   cudaStream_t st);
 // to_ring = 1: io rows -> ring rows; 0: ring rows -> io rows

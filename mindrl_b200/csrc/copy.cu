@@ -301,7 +301,7 @@ int set_copy_option(const char *key, int64_t value) {
 constexpr int kBulkStages = 4;
 
 int gather_rows(const ColTable &tab, const int64_t *slots, int64_t n, int64_t capacity,
-                cudaStream_t st) {
+                cudaStream_t st, uint32_t col_mask) {
   if (n <= 0) return MRL_OK;
   const int64_t bulk_min_row = g_bulk_min_row, bulk_chunk = g_bulk_chunk;
   const int64_t bulk_ctas_per_sm = g_bulk_ctas_per_sm;
@@ -312,6 +312,7 @@ int gather_rows(const ColTable &tab, const int64_t *slots, int64_t n, int64_t ca
   plan.item_begin[0] = 0;
   int32_t stage_bytes = 0;
   for (int c = 0; c < tab.ncols; ++c) {
+    if (!(col_mask & (1u << c))) continue;
     const int64_t rb = tab.row_bytes[c];
     const bool eligible = tab.vec[c] == 16 && path != 1 && (path == 2 || rb >= bulk_min_row);
     if (!eligible) {

@@ -26,6 +26,7 @@
 //                       recomputed through shuffles.
 //   prb_rebuild_kernel  range rebuild after a batched push.
 #include <float.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -57,7 +58,7 @@ static Registry<PrbBuffer> g_prb;
 
 constexpr int kTopLevels = 11;          // levels 0..10 (2047 nodes) staged in shared memory
 constexpr int kSampleWarps = 8;         // warps (= samples) per CTA of prb_sample_kernel
-constexpr int64_t kFusedRowLimit = 512;  // total row bytes up to which sample() gathers in-kernel
+constexpr int64_t kFusedRowLimit = 512;  // column row bytes up to which sample() gathers in-kernel
 
 __global__ void __launch_bounds__(256)
     prb_init_kernel(float *sum, float *mn, unsigned long long *tag, PrbState *state, int64_t cap2) {
@@ -82,7 +83,7 @@ struct SampleArgs {
   int32_t levels, world;
   float beta;
   uint64_t seed, ctr;
-  int32_t gather;  // 1: copy rows of tab inside this kernel
+  uint32_t gather_mask;  // columns whose rows this kernel copies itself (narrow rows)
 };
 
 __global__ void __launch_bounds__(kSampleWarps * 32)
@@ -160,9 +161,10 @@ __global__ void __launch_bounds__(kSampleWarps * 32)
     S.indices[i] = leaf;
     S.weights[i] = __fdiv_rn(mrl_is_weight(leaf_p, w_sum, w_size, S.beta), max_w);
   }
-  if (S.gather) {
+  if (S.gather_mask) {
     const int64_t slot = leaf < S.capacity ? leaf : S.capacity - 1;
     for (int c = 0; c < tab.ncols; ++c) {
+      if (!((S.gather_mask >> c) & 1u)) continue;
       const int64_t rb = tab.row_bytes[c];
       const uint8_t *src = tab.col[c] + slot * rb;
       uint8_t *dst = tab.io[c] + i * rb;
@@ -247,6 +249,174 @@ __global__ void __launch_bounds__(1024) prb_update_kernel(const __grid_constant_
   }
 
   // 3) top `split` levels rebuilt in shared memory from the 2^split nodes of level `split`
+  const int width = 1 << split;
+  for (int i = tid; i < width; i += nthr) {
+    ssum[width + i] = __ldcg(U.sum + width + i);
+    smin[width + i] = __ldcg(U.mn + width + i);
+  }
+  __syncthreads();
+  for (int level = split - 1; level >= 0; --level) {
+    const int w = 1 << level;
+    for (int i = tid; i < w; i += nthr) {
+      const int node = w + i;
+      ssum[node] = __fadd_rn(ssum[2 * node], ssum[2 * node + 1]);
+      const float ma = smin[2 * node], mb = smin[2 * node + 1];
+      smin[node] = ma < mb ? ma : mb;
+    }
+    __syncthreads();
+  }
+  for (int i = tid + 1; i < width; i += nthr) {
+    __stcg(U.sum + i, ssum[i]);
+    __stcg(U.mn + i, smin[i]);
+  }
+}
+
+// ---- update, low-latency variant (n <= kFastUpdateMax) -------------------------------------
+// Same result as prb_update_kernel, organised around the number of DEPENDENT memory round trips
+// (the tree is cold in L2 whenever a learner step ran in between):
+//   * duplicates are arbitrated in a shared-memory hash table (leaf -> highest batch position),
+//     no global tag traffic;
+//   * the lower levels are rebuilt three levels per barrier: a thread loads the aligned group of 8
+//     nodes below its ancestor (one 32-byte sector per array), rebuilds the 4+2+1 nodes above them
+//     and stores them -- 9 levels cost 3 round trips instead of 9;
+//   * every line a later round will need is prefetched into L2 in the first phase.
+constexpr int kFastUpdateMax = 4096;
+constexpr int kFastItems = kFastUpdateMax / 1024;
+
+__device__ __forceinline__ uint32_t upd_hash(int64_t leaf, int bits) {
+  return ((uint32_t)leaf * 2654435761u) >> (32 - bits);
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+__global__ void __launch_bounds__(1024)
+    prb_update_fast_kernel(const __grid_constant__ UpdateArgs U, int slot_bits) {
+  __shared__ float ssum[2 << kTopLevels];
+  __shared__ float smin[2 << kTopLevels];
+  extern __shared__ __align__(16) unsigned char upd_dyn[];
+  const int nslots = 1 << slot_bits;
+  unsigned long long *table = reinterpret_cast<unsigned long long *>(upd_dyn);
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int split = U.levels < kTopLevels ? U.levels : kTopLevels;
+
+  for (int i = tid; i < nslots; i += nthr) table[i] = 0ull;
+  // prefetch the inputs of the shared-memory top rebuild (level `split`)
+  {
+    const int width = 1 << split;
+    for (int i = tid * 32; i < width; i += nthr * 32) {
+      prefetch_l2(U.sum + width + i);
+      prefetch_l2(U.mn + width + i);
+    }
+  }
+  __syncthreads();
+
+  int64_t leaf_of[kFastItems];
+  float p_of[kFastItems];
+  int slot_of[kFastItems];
+  float local_max = 0.0f;
+#pragma unroll
+  for (int r = 0; r < kFastItems; ++r) {
+    const int64_t k = tid + (int64_t)r * nthr;
+    leaf_of[r] = -1;
+    p_of[r] = 0.0f;
+    slot_of[r] = 0;
+    if (k < U.n) {
+      const int64_t leaf = __ldg(U.indices + k);
+      leaf_of[r] = leaf;
+      // lines of the three-level rounds
+      for (int lvl = U.levels; lvl > split; lvl -= 3) {
+        const int64_t g = ((U.cap2 + leaf) >> (U.levels - lvl)) & ~(int64_t)7;
+        prefetch_l2(U.sum + g);
+        prefetch_l2(U.mn + g);
+      }
+      const float p = mrl_priority_pow(__ldg(U.priorities + k), U.alpha);
+      p_of[r] = p;
+      local_max = p > local_max ? p : local_max;
+      const unsigned long long mine = ((unsigned long long)(leaf + 1) << 32) | (unsigned long long)k;
+      uint32_t h = upd_hash(leaf, slot_bits);
+      while (true) {
+        unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(table + h);
+        if (cur == 0ull) {
+          cur = atomicCAS(table + h, 0ull, mine);
+          if (cur == 0ull) break;
+        }
+        if ((cur >> 32) == (unsigned long long)(leaf + 1)) {
+          atomicMax(table + h, mine);
+          break;
+        }
+        h = (h + 1) & (nslots - 1);
+      }
+      slot_of[r] = (int)h;
+    }
+  }
+#pragma unroll
+  for (int off = 16; off; off >>= 1) {
+    const float o = __shfl_xor_sync(0xffffffffu, local_max, off);
+    local_max = o > local_max ? o : local_max;
+  }
+  if ((tid & 31) == 0 && local_max > 0.0f)
+    atomicMax(reinterpret_cast<int *>(&U.state->max_priority), __float_as_int(local_max));
+  __syncthreads();
+
+  // winners (highest batch position of a leaf) write their leaf
+#pragma unroll
+  for (int r = 0; r < kFastItems; ++r) {
+    if (leaf_of[r] >= 0) {
+      const int64_t k = tid + (int64_t)r * nthr;
+      if ((uint32_t)table[slot_of[r]] == (uint32_t)k) {
+        __stcg(U.sum + U.cap2 + leaf_of[r], p_of[r]);
+        __stcg(U.mn + U.cap2 + leaf_of[r], p_of[r]);
+      }
+    }
+  }
+  __syncthreads();
+
+  // lower levels: h <= 3 levels per barrier
+  for (int lvl = U.levels; lvl > split;) {
+    const int h = (lvl - split) < 3 ? (lvl - split) : 3;
+    const int gsz = 1 << h;
+#pragma unroll
+    for (int r = 0; r < kFastItems; ++r) {
+      if (leaf_of[r] < 0) continue;
+      const int64_t node = (U.cap2 + leaf_of[r]) >> (U.levels - lvl);
+      const int64_t g = node & ~(int64_t)(gsz - 1);
+      float vs[8], vm[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        vs[j] = 0.0f, vm[j] = FLT_MAX;
+        if (j < gsz) {
+          vs[j] = __ldcg(U.sum + g + j);
+          vm[j] = __ldcg(U.mn + g + j);
+        }
+      }
+      // rebuild h levels above the group; level lvl-1 nodes start at g>>1, lvl-2 at g>>2, ...
+      int cnt = gsz;
+      int64_t base = g;
+#pragma unroll
+      for (int step = 0; step < 3; ++step) {
+        if (step < h) {
+          cnt >>= 1;
+          base >>= 1;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (j < cnt) {
+              const float a = vs[2 * j], b = vs[2 * j + 1];
+              const float ma = vm[2 * j], mb = vm[2 * j + 1];
+              vs[j] = __fadd_rn(a, b);
+              vm[j] = ma < mb ? ma : mb;
+              __stcg(U.sum + base + j, vs[j]);
+              __stcg(U.mn + base + j, vm[j]);
+            }
+          }
+        }
+      }
+    }
+    lvl -= h;
+    __syncthreads();
+  }
+
+  // top `split` levels in shared memory
   const int width = 1 << split;
   for (int i = tid; i < width; i += nthr) {
     ssum[width + i] = __ldcg(U.sum + width + i);
@@ -448,25 +618,51 @@ static int prb_sample_impl(PrbBuffer *b, int64_t n, float beta, const float *uni
   S.n = n, S.cap2 = b->cap2, S.capacity = b->capacity, S.size = b->size;
   S.levels = b->levels, S.world = world, S.beta = beta;
   S.seed = b->seed, S.ctr = b->ctr;
-  S.gather = (out_cols && b->small_rows) ? 1 : 0;
+  // narrow columns are copied by the warp that found the leaf; wide ones go to the TMA gather
+  uint32_t fused = 0, wide = 0;
+  if (out_cols)
+    for (int c = 0; c < b->ncols; ++c) {
+      if (b->row_bytes[c] <= kFusedRowLimit) fused |= 1u << c;
+      else wide |= 1u << c;
+    }
+  S.gather_mask = fused;
   ColTable tab;
   fill_table(tab, b, out_cols);
   const int64_t blocks = (n + kSampleWarps - 1) / kSampleWarps;
   prb_sample_kernel<<<(unsigned)blocks, kSampleWarps * 32, 0, st>>>(S, tab);
   MRL_LAUNCHED();
   if (!uniforms) b->ctr += (uint64_t)n;
-  if (out_cols && !b->small_rows) return gather_rows(tab, indices, n, b->capacity, st);
+  if (wide) return gather_rows(tab, indices, n, b->capacity, st, wide);
   return MRL_OK;
 }
 
+static int g_update_path = -1;  // MRL_UPDATE_PATH=tags forces the global-tag kernel
+
 static int prb_update_impl(PrbBuffer *b, const int64_t *indices, const float *priorities,
                            int64_t n, cudaStream_t st) {
+  if (g_update_path < 0) {
+    const char *e = getenv("MRL_UPDATE_PATH");
+    g_update_path = (e && e[0] == 't') ? 1 : 0;
+  }
   UpdateArgs U;
   U.sum = b->sum, U.mn = b->mn, U.tag = b->tag, U.state = b->state;
   U.indices = indices, U.priorities = priorities;
   U.n = n, U.cap2 = b->cap2, U.levels = b->levels, U.alpha = b->alpha;
   U.epoch = ++b->epoch;
-  prb_update_kernel<<<1, 1024, 0, st>>>(U);
+  if (n <= kFastUpdateMax && g_update_path == 0) {
+    int bits = 6;
+    while ((1 << bits) < 2 * n) ++bits;
+    const size_t smem = (size_t)(1 << bits) * 8;
+    static size_t configured = 0;
+    if (smem > configured) {
+      MRL_CUDA(cudaFuncSetAttribute(prb_update_fast_kernel,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8192 * 8)));
+      configured = 8192 * 8;
+    }
+    prb_update_fast_kernel<<<1, 1024, smem, st>>>(U, bits);
+  } else {
+    prb_update_kernel<<<1, 1024, 0, st>>>(U);
+  }
   MRL_LAUNCHED();
   return MRL_OK;
 }

@@ -45,10 +45,18 @@ __device__ __forceinline__ float scan_init(const ScanArgs &A, int64_t col) {
   return A.last ? __ldg(A.last + col) : 0.0f;
 }
 
-// one element: produces (a, b) of x = a + b*x_next and the value needed by the store
+// V[T] of a column for the GAE bootstrap (value[t+1] form)
 template <int OP>
-__device__ __forceinline__ void scan_load(const ScanArgs &A, int64_t t, int64_t col, float &a,
-                                          float &b, float &aux) {
+__device__ __forceinline__ float scan_lastv(const ScanArgs &A, int64_t col) {
+  return (OP == OP_GAE && !A.nv && A.last) ? __ldg(A.last + col) : 0.0f;
+}
+
+// One element: (a, b) of x = a + b*x_next plus the value the store needs.  (t, col) must be in range:
+// every load here is unconditional and address selection is branch-free, so that an unrolled caller
+// gets all its loads in flight at once (predicated loads are serialised by the compiler).
+template <int OP, bool HD>
+__device__ __forceinline__ void scan_load(const ScanArgs &A, int64_t t, int64_t col, float lastv,
+                                          float &a, float &b, float &aux) {
   const int64_t i = t * A.st + col * A.sc;
   if (OP == OP_AFFINE) {
     a = __ldg(A.a + i);
@@ -57,7 +65,7 @@ __device__ __forceinline__ void scan_load(const ScanArgs &A, int64_t t, int64_t 
     return;
   }
   float m = 1.0f;
-  if (A.done) {
+  if (HD) {
     const int64_t bcol = A.E == 1 ? col : col / A.E;
     m = __fsub_rn(1.0f, __ldg(A.done + t * A.dst + bcol * A.dsc) ? 1.0f : 0.0f);
   }
@@ -68,10 +76,10 @@ __device__ __forceinline__ void scan_load(const ScanArgs &A, int64_t t, int64_t 
     aux = 0.0f;
   } else {
     const float v = __ldg(A.v + i);
-    float nv;
-    if (A.nv) nv = __ldg(A.nv + i);
-    else if (t == A.T - 1) nv = A.last ? __ldg(A.last + col) : 0.0f;
-    else nv = __ldg(A.v + i + A.st);
+    const bool boot = !A.nv && t == A.T - 1;
+    const float *np = A.nv ? A.nv + i : (boot ? A.v + i : A.v + i + A.st);
+    float nv = __ldg(np);
+    nv = boot ? lastv : nv;
     const float gvm = __fmul_rn(__fmul_rn(A.gamma, nv), m);
     a = __fsub_rn(__fadd_rn(r, gvm), v);
     b = __fmul_rn(A.gl, m);
@@ -92,15 +100,16 @@ __device__ __forceinline__ void scan_store(const ScanArgs &A, int64_t t, int64_t
 }
 
 // walk [t_lo, t_hi) downwards from carry x, U rows of loads in flight
-template <int OP, int U>
-__device__ __forceinline__ float scan_walk(const ScanArgs &A, int64_t col, int64_t t_lo,
+template <int OP, bool HD, int U>
+__device__ __forceinline__ float scan_walk(const ScanArgs &A, int64_t col, float lastv, int64_t t_lo,
                                            int64_t t_hi, float x) {
   for (int64_t t0 = t_hi; t0 > t_lo; t0 -= U) {
     float a[U], b[U], aux[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int64_t t = t0 - 1 - u;
-      if (t >= t_lo) scan_load<OP>(A, t, col, a[u], b[u], aux[u]);
+      int64_t t = t0 - 1 - u;
+      t = t < t_lo ? t_lo : t;  // clamped: the load is always legal, the result may be unused
+      scan_load<OP, HD>(A, t, col, lastv, a[u], b[u], aux[u]);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -114,14 +123,14 @@ __device__ __forceinline__ float scan_walk(const ScanArgs &A, int64_t col, int64
   return x;
 }
 
-template <int OP>
+template <int OP, bool HD>
 __global__ void __launch_bounds__(128) scan_seq_kernel(const __grid_constant__ ScanArgs A) {
   const int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= A.N) return;
-  scan_walk<OP, 8>(A, col, 0, A.T, scan_init<OP>(A, col));
+  scan_walk<OP, HD, 8>(A, col, scan_lastv<OP>(A, col), 0, A.T, scan_init<OP>(A, col));
 }
 
-template <int OP>
+template <int OP, bool HD>
 __global__ void __launch_bounds__(1024)
     scan_tm_chunked_kernel(const __grid_constant__ ScanArgs A, int64_t chunk) {
   __shared__ float sA[32][32];
@@ -129,20 +138,23 @@ __global__ void __launch_bounds__(1024)
   const int lane = threadIdx.x, w = threadIdx.y, W = blockDim.y;
   const int64_t col = (int64_t)blockIdx.x * 32 + lane;
   const bool valid = col < A.N;
+  const int64_t colc = valid ? col : A.N - 1;
   int64_t t_lo = (int64_t)w * chunk, t_hi = t_lo + chunk;
   if (t_lo > A.T) t_lo = A.T;
   if (t_hi > A.T) t_hi = A.T;
+  const float lastv = scan_lastv<OP>(A, colc);
 
   // pass 1: x[t_lo] = ca + cb * x[t_hi]
   float ca = 0.0f, cb = 1.0f;
-  if (valid) {
+  {
     constexpr int U = 8;
     for (int64_t t0 = t_hi; t0 > t_lo; t0 -= U) {
       float a[U], b[U], aux[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int64_t t = t0 - 1 - u;
-        if (t >= t_lo) scan_load<OP>(A, t, col, a[u], b[u], aux[u]);
+        int64_t t = t0 - 1 - u;
+        t = t < t_lo ? t_lo : t;
+        scan_load<OP, HD>(A, t, colc, lastv, a[u], b[u], aux[u]);
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -161,8 +173,8 @@ __global__ void __launch_bounds__(1024)
   // carry into this chunk = later chunks applied to the boundary value, last chunk first
   float x = scan_init<OP>(A, col);
   for (int j = W - 1; j > w; --j) x = scan_step(sA[j][lane], sB[j][lane], x);
-  // pass 2: replay the chunk (inputs are L2-resident from pass 1)
-  scan_walk<OP, 8>(A, col, t_lo, t_hi, x);
+  // pass 2: replay the chunk
+  scan_walk<OP, HD, 8>(A, col, lastv, t_lo, t_hi, x);
 }
 
 // ---- time-major single-pass tile scan -----------------------------------------------------
@@ -183,7 +195,7 @@ struct TileWs {
   float2 *agg;           // [n_chunks * n_groups][32]
 };
 
-template <int OP>
+template <int OP, bool HD>
 __global__ void __launch_bounds__(TM_W * 32)
     scan_tm_tile_kernel(const __grid_constant__ ScanArgs A, TileWs ws, int n_chunks, int n_groups) {
   __shared__ float sA[TM_W][32];
@@ -198,49 +210,51 @@ __global__ void __launch_bounds__(TM_W * 32)
   const int group = (int)(ticket % (unsigned)n_groups);
   const int64_t col = (int64_t)group * 32 + lane;
   const bool valid = col < A.N;
+  const int64_t colc = valid ? col : A.N - 1;  // clamped: loads stay legal, results unused
   const int64_t t_base = (int64_t)chunk * TM_TC + (int64_t)w * TM_S;
+  const int64_t t_max = A.T - 1;
+  const float lastv = scan_lastv<OP>(A, colc);
 
   float a[TM_S], b[TM_S], aux[TM_S];
   if (OP == OP_GAE && !A.nv) {
-    // V[t+1] of step s is V[t] of step s+1: load TM_S+1 values once instead of 2*TM_S
+    // V[t+1] of step s is V[t] of step s+1: TM_S+1 loads instead of 2*TM_S
     float vv[TM_S + 1], rr[TM_S], mm[TM_S];
 #pragma unroll
     for (int s = 0; s <= TM_S; ++s) {
-      const int64_t t = t_base + s;
-      vv[s] = 0.0f;
-      if (valid && t < A.T) vv[s] = __ldg(A.v + t * A.st + col);
-      else if (valid && t == A.T && A.last) vv[s] = __ldg(A.last + col);
+      int64_t t = t_base + s;
+      t = t > t_max ? t_max : t;
+      vv[s] = __ldg(A.v + t * A.st + colc);
+    }
+#pragma unroll
+    for (int s = 0; s < TM_S; ++s) {
+      int64_t t = t_base + s;
+      t = t > t_max ? t_max : t;
+      rr[s] = __ldg(A.a + t * A.st + colc);
+      mm[s] = 1.0f;
+      if (HD) mm[s] = __fsub_rn(1.0f, __ldg(A.done + t * A.dst + colc) ? 1.0f : 0.0f);
     }
 #pragma unroll
     for (int s = 0; s < TM_S; ++s) {
       const int64_t t = t_base + s;
-      rr[s] = 0.0f, mm[s] = 1.0f;
-      if (valid && t < A.T) {
-        rr[s] = __ldg(A.a + t * A.st + col);
-        if (A.done) mm[s] = __fsub_rn(1.0f, __ldg(A.done + t * A.dst + col) ? 1.0f : 0.0f);
-      }
-    }
-#pragma unroll
-    for (int s = 0; s < TM_S; ++s) {
-      const int64_t t = t_base + s;
-      if (valid && t < A.T) {
-        const float gvm = __fmul_rn(__fmul_rn(A.gamma, vv[s + 1]), mm[s]);
-        a[s] = __fsub_rn(__fadd_rn(rr[s], gvm), vv[s]);
-        b[s] = __fmul_rn(A.gl, mm[s]);
-        aux[s] = vv[s];
-      } else {
-        a[s] = 0.0f, b[s] = 1.0f, aux[s] = 0.0f;
-      }
+      const float vn = (t + 1 > t_max) ? lastv : vv[s + 1];
+      const float gvm = __fmul_rn(__fmul_rn(A.gamma, vn), mm[s]);
+      const bool in = valid && t <= t_max;
+      a[s] = in ? __fsub_rn(__fadd_rn(rr[s], gvm), vv[s]) : 0.0f;
+      b[s] = in ? __fmul_rn(A.gl, mm[s]) : 1.0f;
+      aux[s] = vv[s];
     }
   } else {
 #pragma unroll
     for (int s = 0; s < TM_S; ++s) {
-      const int64_t t = t_base + s;
-      if (valid && t < A.T) {
-        scan_load<OP>(A, t, col, a[s], b[s], aux[s]);
-      } else {
-        a[s] = 0.0f, b[s] = 1.0f, aux[s] = 0.0f;
-      }
+      int64_t t = t_base + s;
+      t = t > t_max ? t_max : t;
+      scan_load<OP, HD>(A, t, colc, lastv, a[s], b[s], aux[s]);
+    }
+#pragma unroll
+    for (int s = 0; s < TM_S; ++s) {
+      const bool in = valid && (t_base + s) <= t_max;
+      a[s] = in ? a[s] : 0.0f;
+      b[s] = in ? b[s] : 1.0f;
     }
   }
   float ca = 0.0f, cb = 1.0f;  // x[t_base] = ca + cb * x[t_base + TM_S]
@@ -270,19 +284,33 @@ __global__ void __launch_bounds__(TM_W * 32)
         asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ws.flag + tile), "r"(1u) : "memory");
       }
     }
-    // carry from all later chunks of this column group
-    float x = valid ? scan_init<OP>(A, col) : 0.0f;
-    for (int c = n_chunks - 1; c > chunk; --c) {
-      const int other = c * n_groups + group;
-      if (lane == 0) {
+    // carry from all later chunks of this column group: the flags are polled lane-parallel and the
+    // aggregates fetched in independent batches, so the wait is one round trip, not one per chunk
+    const int n_later = n_chunks - 1 - chunk;
+    for (int j0 = 0; j0 < n_later; j0 += 32) {
+      const int j = j0 + lane;
+      if (j < n_later) {
+        const unsigned int *fp = ws.flag + (size_t)(chunk + 1 + j) * n_groups + group;
         unsigned int f;
         do {
-          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(ws.flag + other) : "memory");
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(fp) : "memory");
         } while (f == 0u);
       }
-      __syncwarp();
-      const float2 g = __ldcg(&ws.agg[(size_t)other * 32 + lane]);
-      x = scan_step(g.x, g.y, x);
+    }
+    __syncwarp();
+    float x = valid ? scan_init<OP>(A, col) : 0.0f;
+    for (int c0 = n_chunks - 1; c0 > chunk; c0 -= 8) {
+      float2 g[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        int c = c0 - u;
+        const bool in = c > chunk;
+        c = in ? c : chunk + 1;
+        const float2 q = __ldcg(&ws.agg[((size_t)c * n_groups + group) * 32 + lane]);
+        g[u] = in ? q : make_float2(0.0f, 1.0f);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) x = scan_step(g[u].x, g[u].y, x);
     }
     s_ext[lane] = x;
   }
@@ -293,9 +321,669 @@ __global__ void __launch_bounds__(TM_W * 32)
 #pragma unroll
   for (int s = TM_S - 1; s >= 0; --s) {
     const int64_t t = t_base + s;
-    if (t < A.T) {
+    if (t <= t_max) {
       x = scan_step(a[s], b[s], x);
       scan_store<OP>(A, t, col, x, aux[s]);
+    }
+  }
+}
+
+// ---- time-major single-pass tile scan, 512-byte rows ---------------------------------------
+// Same scheme as scan_tm_tile_kernel, but a lane owns 4 adjacent columns (one 16-byte load per
+// array and step), so every warp-level access is a contiguous 512-byte piece of a time row instead
+// of 128 bytes: the 32-column variant leaves DRAM pages after 128 bytes and reaches only ~1/4 of
+// the bandwidth.  Tile = 128 columns x (T4_W warps x T4_S steps).  The carry comes from a decoupled
+// look-back: every tile publishes its aggregate (flag 1) and later its inclusive value at the tile
+// start (flag 2); a tile walks towards later chunks, composing aggregates until it meets an
+// inclusive value.
+constexpr int T4_W = 4;
+constexpr int T4_S = 8;
+constexpr int T4_TC = T4_W * T4_S;  // 32 steps
+constexpr int T4_COLS = 128;
+
+struct Tile4Ws {
+  unsigned int *ticket;
+  unsigned int *flag;  // [tiles] 0 none, 1 aggregate, 2 inclusive
+  float2 *agg;         // [tiles][128] (a, b)
+  float *incl;         // [tiles][128] x at the tile start
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned int *p, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <int OP, bool HD>
+__global__ void __launch_bounds__(T4_W * 32, 3)
+    scan_tm_tile4_kernel(const __grid_constant__ ScanArgs A, Tile4Ws ws, int n_chunks, int n_groups) {
+  __shared__ __align__(16) float sA[T4_W][T4_COLS];
+  __shared__ __align__(16) float sB[T4_W][T4_COLS];
+  __shared__ __align__(16) float s_ext[T4_COLS];
+  __shared__ unsigned int s_ticket;
+  __shared__ int s_zero;
+  const int lane = threadIdx.x, w = threadIdx.y;
+  if (lane == 0 && w == 0) {
+    s_ticket = atomicAdd(ws.ticket, 1u);
+    s_zero = 0;
+  }
+  __syncthreads();
+  const unsigned int ticket = s_ticket;
+  const int chunk = n_chunks - 1 - (int)(ticket / (unsigned)n_groups);
+  const int group = (int)(ticket % (unsigned)n_groups);
+  const int64_t col = (int64_t)group * T4_COLS + lane * 4;
+  const bool valid = col < A.N;  // N % 4 == 0: a lane's 4 columns are valid together
+  const int64_t colc = valid ? col : A.N - 4;
+  const int64_t t_base = (int64_t)chunk * T4_TC + (int64_t)w * T4_S;
+  const int64_t t_max = A.T - 1;
+
+  // ---- loads: all unconditional (clamped), all in flight together -------------------------
+  float4 rr[T4_S], vv[T4_S + 1], nn[T4_S];
+  uint32_t dd[T4_S];
+#pragma unroll
+  for (int s = 0; s < T4_S; ++s) {
+    int64_t t = t_base + s;
+    t = t > t_max ? t_max : t;
+    rr[s] = __ldcs(reinterpret_cast<const float4 *>(A.a + t * A.N + colc));
+    dd[s] = HD ? __ldcs(reinterpret_cast<const uint32_t *>(A.done + t * A.N + colc)) : 0u;
+  }
+  if (OP != OP_DR) {
+#pragma unroll
+    for (int s = 0; s <= T4_S; ++s) {
+      int64_t t = t_base + s;
+      t = t > t_max ? t_max : t;
+      if (s < T4_S || OP == OP_GAE)
+        vv[s] = __ldcs(reinterpret_cast<const float4 *>(A.v + t * A.N + colc));
+    }
+  }
+  const bool has_nv = OP == OP_GAE && A.nv != nullptr;
+  if (has_nv) {
+#pragma unroll
+    for (int s = 0; s < T4_S; ++s) {
+      int64_t t = t_base + s;
+      t = t > t_max ? t_max : t;
+      nn[s] = __ldcs(reinterpret_cast<const float4 *>(A.nv + t * A.N + colc));
+    }
+  }
+  float4 lastv = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (OP == OP_GAE && !has_nv && A.last) lastv = __ldcg(reinterpret_cast<const float4 *>(A.last + colc));
+  // Scheduling fence: ptxas otherwise sinks the first consumer between the loads, and the in-order
+  // warp then sits out a full memory latency before it issues the rest.  The barrier pins the loads,
+  // the never-taken branch on an opaque zero pins the consumers behind it.
+  __syncthreads();
+  if (*reinterpret_cast<volatile int *>(&s_zero) != 0) return;
+
+  // ---- per-element maps ------------------------------------------------------------------
+  float a[T4_S][4], b[T4_S][4];
+#pragma unroll
+  for (int s = 0; s < T4_S; ++s) {
+    const int64_t t = t_base + s;
+    const bool in = valid && t <= t_max;
+    const float r4[4] = {rr[s].x, rr[s].y, rr[s].z, rr[s].w};
+    float v4[4] = {0.f, 0.f, 0.f, 0.f}, n4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (OP != OP_DR) {
+      v4[0] = vv[s].x, v4[1] = vv[s].y, v4[2] = vv[s].z, v4[3] = vv[s].w;
+    }
+    if (OP == OP_GAE) {
+      const float4 q = has_nv ? nn[s] : ((t + 1 > t_max) ? lastv : vv[s + 1]);
+      n4[0] = q.x, n4[1] = q.y, n4[2] = q.z, n4[3] = q.w;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float aa, bb;
+      if (OP == OP_AFFINE) {
+        aa = r4[c];
+        bb = v4[c];
+      } else {
+        const float m = __fsub_rn(1.0f, ((dd[s] >> (8 * c)) & 0xffu) ? 1.0f : 0.0f);
+        if (OP == OP_DR) {
+          aa = r4[c];
+          bb = __fmul_rn(m, A.gamma);
+        } else {
+          const float gvm = __fmul_rn(__fmul_rn(A.gamma, n4[c]), m);
+          aa = __fsub_rn(__fadd_rn(r4[c], gvm), v4[c]);
+          bb = __fmul_rn(A.gl, m);
+        }
+      }
+      a[s][c] = in ? aa : 0.0f;
+      b[s][c] = in ? bb : 1.0f;
+    }
+  }
+  float ca[4] = {0.f, 0.f, 0.f, 0.f}, cb[4] = {1.f, 1.f, 1.f, 1.f};
+#pragma unroll
+  for (int s = T4_S - 1; s >= 0; --s)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      ca[c] = scan_step(a[s][c], b[s][c], ca[c]);
+      cb[c] = __fmul_rn(b[s][c], cb[c]);
+    }
+  *reinterpret_cast<float4 *>(&sA[w][lane * 4]) = make_float4(ca[0], ca[1], ca[2], ca[3]);
+  *reinterpret_cast<float4 *>(&sB[w][lane * 4]) = make_float4(cb[0], cb[1], cb[2], cb[3]);
+  __syncthreads();
+
+  const size_t tile = (size_t)chunk * n_groups + group;
+  if (w == 0) {
+    float ta[4] = {0.f, 0.f, 0.f, 0.f}, tb[4] = {1.f, 1.f, 1.f, 1.f};
+#pragma unroll
+    for (int j = T4_W - 1; j >= 0; --j) {
+      const float4 ja = *reinterpret_cast<const float4 *>(&sA[j][lane * 4]);
+      const float4 jb = *reinterpret_cast<const float4 *>(&sB[j][lane * 4]);
+      const float ja4[4] = {ja.x, ja.y, ja.z, ja.w}, jb4[4] = {jb.x, jb.y, jb.z, jb.w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        ta[c] = scan_step(ja4[c], jb4[c], ta[c]);
+        tb[c] = __fmul_rn(jb4[c], tb[c]);
+      }
+    }
+    if (chunk > 0) {  // somebody looks back at this tile
+      float4 *dst = reinterpret_cast<float4 *>(ws.agg + tile * T4_COLS + lane * 4);
+      __stcg(dst, make_float4(ta[0], tb[0], ta[1], tb[1]));
+      __stcg(dst + 1, make_float4(ta[2], tb[2], ta[3], tb[3]));
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) st_release_u32(ws.flag + tile, 1u);
+    }
+    // Decoupled look-back towards later chunks, one window of 32 chunks per round trip: lane j
+    // polls chunk+1+j until it has at least an aggregate; the nearest chunk that already has its
+    // inclusive value (or the end of the trajectory) closes the window.  x_in = P(x at that point).
+    float pa[4] = {0.f, 0.f, 0.f, 0.f}, pb[4] = {1.f, 1.f, 1.f, 1.f};
+    float xin[4];
+    int c = chunk + 1;
+    while (true) {
+      const int cj = c + lane;
+      unsigned int f = 2u;  // beyond the last chunk: the boundary value plays the inclusive role
+      if (cj < n_chunks) {
+        const unsigned int *fp = ws.flag + (size_t)cj * n_groups + group;
+        do {
+          f = ld_acquire_u32(fp);
+        } while (f == 0u);
+      }
+      const unsigned int closed = __ballot_sync(0xffffffffu, f == 2u);
+      const int jstop = closed ? __ffs(closed) - 1 : 32;  // aggregates c .. c+jstop-1, then inclusive
+      for (int j0 = 0; j0 < jstop; j0 += 4) {
+        float4 g0[4], g1[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = j0 + u < jstop ? j0 + u : jstop - 1;
+          const float4 *src = reinterpret_cast<const float4 *>(
+              ws.agg + ((size_t)(c + j) * n_groups + group) * T4_COLS + lane * 4);
+          g0[u] = __ldcg(src);
+          g1[u] = __ldcg(src + 1);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (j0 + u < jstop) {
+            const float ga[4] = {g0[u].x, g0[u].z, g1[u].x, g1[u].z};
+            const float gb[4] = {g0[u].y, g0[u].w, g1[u].y, g1[u].w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              pa[k] = scan_step(pa[k], pb[k], ga[k]);  // P o M
+              pb[k] = __fmul_rn(pb[k], gb[k]);
+            }
+          }
+        }
+      }
+      if (jstop < 32) {
+        const int cs = c + jstop;
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cs >= n_chunks) {
+          if (OP != OP_GAE && A.last) q = __ldg(reinterpret_cast<const float4 *>(A.last + colc));
+        } else {
+          q = __ldcg(reinterpret_cast<const float4 *>(
+              ws.incl + ((size_t)cs * n_groups + group) * T4_COLS + lane * 4));
+        }
+        const float q4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) xin[k] = scan_step(pa[k], pb[k], q4[k]);
+        break;
+      }
+      c += 32;
+    }
+    if (chunk > 0) {  // inclusive value at this tile's start for the tiles before it
+      float inc[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) inc[k] = scan_step(ta[k], tb[k], xin[k]);
+      __stcg(reinterpret_cast<float4 *>(ws.incl + tile * T4_COLS + lane * 4),
+             make_float4(inc[0], inc[1], inc[2], inc[3]));
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) st_release_u32(ws.flag + tile, 2u);
+    }
+    *reinterpret_cast<float4 *>(&s_ext[lane * 4]) = make_float4(xin[0], xin[1], xin[2], xin[3]);
+  }
+  __syncthreads();
+  if (!valid) return;
+  const float4 e = *reinterpret_cast<const float4 *>(&s_ext[lane * 4]);
+  float x[4] = {e.x, e.y, e.z, e.w};
+  for (int j = T4_W - 1; j > w; --j) {
+    const float4 ja = *reinterpret_cast<const float4 *>(&sA[j][lane * 4]);
+    const float4 jb = *reinterpret_cast<const float4 *>(&sB[j][lane * 4]);
+    x[0] = scan_step(ja.x, jb.x, x[0]);
+    x[1] = scan_step(ja.y, jb.y, x[1]);
+    x[2] = scan_step(ja.z, jb.z, x[2]);
+    x[3] = scan_step(ja.w, jb.w, x[3]);
+  }
+#pragma unroll
+  for (int s = T4_S - 1; s >= 0; --s) {
+    const int64_t t = t_base + s;
+    if (t <= t_max) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) x[c] = scan_step(a[s][c], b[s][c], x[c]);
+      const int64_t i = t * A.N + col;
+      __stcs(reinterpret_cast<float4 *>(A.out + i), make_float4(x[0], x[1], x[2], x[3]));
+      if (OP == OP_GAE && A.ret)
+        __stcs(reinterpret_cast<float4 *>(A.ret + i),
+               make_float4(__fadd_rn(x[0], vv[s].x), __fadd_rn(x[1], vv[s].y),
+                           __fadd_rn(x[2], vv[s].z), __fadd_rn(x[3], vv[s].w)));
+    }
+  }
+}
+
+// ---- time-major single-pass scan, warp-owned tiles ------------------------------------------
+// A warp owns a tile of 32 columns x WT_S steps in registers and never meets a block barrier after
+// its loads: the four warps of a CTA take four adjacent column groups of the same time chunk (a time
+// row is fetched in 512-byte pieces at about the same moment) but publish, look back and replay on
+// their own.
+//
+// Carry exchange = decoupled look-back with flag-in-payload words (the protocol NCCL calls LL): every
+// published float travels in an aligned 8-byte word {value bits, launch epoch}.  8-byte accesses are
+// single-copy atomic, so a reader that sees the epoch sees the value: no __threadfence, no release /
+// acquire, no separate flag round trip, no per-launch memset.  A tile publishes its aggregate map
+// (a, b), looks at a window of WT_WIN later chunks in ONE round trip (aggregate and inclusive words of
+// each), composes aggregates up to the nearest chunk whose inclusive value is out, publishes its own
+// inclusive value, and replays its tile from registers.
+constexpr int WT_S = 32;
+constexpr int WT_WARPS = 4;
+constexpr int WT_WIN = 8;
+
+struct WTileWs {
+  unsigned long long *ticket;  // tiles handed out since the workspace was created
+  uint4 *agg;                  // [tiles][32] {a, epoch, b, epoch}
+  uint2 *incl;                 // [tiles][32] {x, epoch}
+};
+
+__device__ __forceinline__ uint4 ld_relaxed_v4(const uint4 *p) {
+  uint4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ uint2 ld_relaxed_v2(const uint2 *p) {
+  uint2 v;
+  asm volatile("ld.relaxed.gpu.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_v4(uint4 *p, uint4 v) {
+  asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y),
+               "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void st_relaxed_v2(uint2 *p, uint2 v) {
+  asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+
+// Everything a warp does with its tile once the loads are in registers.  INTERIOR: the tile lies
+// completely inside [0,T) x [0,N), so no step or column needs masking (the common case; it halves the
+// instruction count of the kernel, which is otherwise issue-bound rather than HBM-bound).
+template <int OP, bool HD, bool INTERIOR>
+__device__ __forceinline__ void wtile_body(const ScanArgs &A, const WTileWs &ws, unsigned int epoch,
+                                           float (&a)[WT_S], float (&v)[WT_S + 1],
+                                           const unsigned char (&db)[WT_S], float lastv, int chunk,
+                                           int wgroup, int n_chunks, int n_wgroups, int lane,
+                                           int64_t col, int64_t colc, bool valid) {
+  constexpr unsigned FULL = 0xffffffffu;
+  const int64_t t_base = (int64_t)chunk * WT_S;
+  const int64_t t_max = A.T - 1;
+  unsigned int dmask = 0u, inmask = 0xffffffffu;
+  if (HD) {
+#pragma unroll
+    for (int s = 0; s < WT_S; ++s) dmask |= (db[s] ? 1u : 0u) << s;
+  }
+  if (!INTERIOR) {
+    inmask = 0u;
+#pragma unroll
+    for (int s = 0; s < WT_S; ++s) inmask |= ((valid && t_base + s <= t_max) ? 1u : 0u) << s;
+  }
+  const float bgain = OP == OP_GAE ? A.gl : A.gamma;
+  if (OP == OP_GAE) {
+#pragma unroll
+    for (int s = 0; s < WT_S; ++s) {
+      const float vn = (!INTERIOR && t_base + s + 1 > t_max) ? lastv : v[s + 1];
+      const float gv = __fmul_rn(A.gamma, vn);
+      const float gvm = ((dmask >> s) & 1u) ? 0.0f : gv;
+      a[s] = __fsub_rn(__fadd_rn(a[s], gvm), v[s]);
+    }
+  }
+  // x_new = a + b * x with b = 0 on a done step, bgain otherwise (or v[s] for the generic scan)
+  auto step = [&](int s, float x) -> float {
+    if (OP == OP_AFFINE) return scan_step(a[s], v[s], x);
+    const float y = scan_step(a[s], bgain, x);
+    return ((dmask >> s) & 1u) ? a[s] : y;
+  };
+  float ca = 0.0f, cb = 1.0f;
+#pragma unroll
+  for (int s = WT_S - 1; s >= 0; --s) {
+    if (INTERIOR || ((inmask >> s) & 1u)) {
+      ca = step(s, ca);
+      if (OP == OP_AFFINE) cb = __fmul_rn(v[s], cb);
+      else cb = ((dmask >> s) & 1u) ? 0.0f : __fmul_rn(bgain, cb);
+    }
+  }
+
+  const size_t tile = (size_t)chunk * n_wgroups + wgroup;
+  if (chunk > 0)
+    st_relaxed_v4(ws.agg + tile * 32 + lane,
+                  make_uint4(__float_as_uint(ca), epoch, __float_as_uint(cb), epoch));
+
+  // ---- look-back, WT_WIN later chunks per round trip --------------------------------------------
+  float pa_ = 0.0f, pb_ = 1.0f, xin = 0.0f;
+  int c = chunk + 1;
+  bool found = false;
+  while (!found) {
+    if (c >= n_chunks) {  // ran off the end of the trajectory: boundary value
+      float q = 0.0f;
+      if (OP != OP_GAE && A.last) q = __ldcg(A.last + colc);
+      xin = scan_step(pa_, pb_, q);
+      break;
+    }
+    uint4 g[WT_WIN];
+    uint2 q[WT_WIN];
+    const int c0 = c;  // window = chunks c0 .. c0 + WT_WIN - 1
+#pragma unroll
+    for (int j = 0; j < WT_WIN; ++j) {
+      const int cj = c0 + j < n_chunks ? c0 + j : n_chunks - 1;
+      const size_t other = ((size_t)cj * n_wgroups + wgroup) * 32 + lane;
+      g[j] = ld_relaxed_v4(ws.agg + other);
+      q[j] = ld_relaxed_v2(ws.incl + other);
+    }
+    bool retry = false;
+#pragma unroll
+    for (int j = 0; j < WT_WIN; ++j) {
+      if (found || retry) continue;
+      if (c0 + j >= n_chunks) {  // window reaches the end: boundary value closes it
+        float qq = 0.0f;
+        if (OP != OP_GAE && A.last) qq = __ldcg(A.last + colc);
+        xin = scan_step(pa_, pb_, qq);
+        found = true;
+      } else if (__all_sync(FULL, q[j].y == epoch)) {
+        xin = scan_step(pa_, pb_, __uint_as_float(q[j].x));
+        found = true;
+      } else if (__all_sync(FULL, g[j].y == epoch && g[j].w == epoch)) {
+        pa_ = scan_step(pa_, pb_, __uint_as_float(g[j].x));  // P o M
+        pb_ = __fmul_rn(pb_, __uint_as_float(g[j].z));
+        ++c;
+      } else {
+        retry = true;  // chunk c has published nothing yet: poll again from c
+      }
+    }
+  }
+  if (chunk > 0)
+    st_relaxed_v2(ws.incl + tile * 32 + lane, make_uint2(__float_as_uint(scan_step(ca, cb, xin)), epoch));
+  if (!INTERIOR && !valid) return;
+  // ---- replay from registers ----------------------------------------------------------------
+  float x = xin;
+  float *po = A.out + t_base * A.N + col;
+  float *pr = (OP == OP_GAE && A.ret) ? A.ret + t_base * A.N + col : nullptr;
+#pragma unroll
+  for (int s = WT_S - 1; s >= 0; --s) {
+    if (INTERIOR || t_base + s <= t_max) {
+      x = step(s, x);
+      __stcs(po + (int64_t)s * A.N, x);
+      if (OP == OP_GAE && pr) __stcs(pr + (int64_t)s * A.N, __fadd_rn(x, v[s]));
+    }
+  }
+}
+
+template <int OP, bool HD>
+__global__ void __launch_bounds__(WT_WARPS * 32, 3)
+    scan_tm_wtile_kernel(const __grid_constant__ ScanArgs A, WTileWs ws, unsigned long long ticket_base,
+                         unsigned int epoch, int n_chunks, int n_wgroups, int n_cgroups) {
+  __shared__ unsigned int s_ticket;
+  __shared__ int s_zero;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    s_ticket = (unsigned int)(atomicAdd(ws.ticket, 1ull) - ticket_base);
+    s_zero = 0;
+  }
+  __syncthreads();
+  const unsigned int ticket = s_ticket;
+  const int chunk = n_chunks - 1 - (int)(ticket / (unsigned)n_cgroups);  // latest chunk first
+  int wgroup = (int)(ticket % (unsigned)n_cgroups) * WT_WARPS + w;
+  const bool warp_on = wgroup < n_wgroups;
+  wgroup = warp_on ? wgroup : n_wgroups - 1;  // idle warps shadow a real tile up to the barrier
+  const int64_t col = (int64_t)wgroup * 32 + lane;
+  const bool valid = warp_on && col < A.N;
+  const int64_t colc = col < A.N ? col : A.N - 1;
+  const int64_t dcol = A.E == 1 ? colc : colc / A.E;
+  const int64_t t_base = (int64_t)chunk * WT_S;
+  const int64_t t_max = A.T - 1;
+
+  // ---- loads: unconditional and all in flight.  Interior tiles use plain strided pointers ------
+  float a[WT_S], v[WT_S + 1];
+  unsigned char db[WT_S];
+  const bool interior = t_base + WT_S <= t_max;  // also covers v[WT_S]
+  if (interior) {
+    const float *pa = A.a + t_base * A.N + colc;
+#pragma unroll
+    for (int s = 0; s < WT_S; ++s) a[s] = __ldcs(pa + (int64_t)s * A.N);
+    if (OP != OP_DR) {
+      const float *pv = A.v + t_base * A.N + colc;
+#pragma unroll
+      for (int s = 0; s <= WT_S; ++s)
+        if (s < WT_S || OP == OP_GAE) v[s] = __ldcs(pv + (int64_t)s * A.N);
+    }
+    if (HD) {
+      const unsigned char *pd = A.done + t_base * A.B + dcol;
+#pragma unroll
+      for (int s = 0; s < WT_S; ++s) db[s] = __ldcs(pd + (int64_t)s * A.B);
+    }
+  } else {
+#pragma unroll
+    for (int s = 0; s < WT_S; ++s) {
+      int64_t t = t_base + s;
+      t = t > t_max ? t_max : t;
+      a[s] = __ldcs(A.a + t * A.N + colc);
+      if (HD) db[s] = __ldcs(A.done + t * A.B + dcol);
+    }
+    if (OP != OP_DR) {
+#pragma unroll
+      for (int s = 0; s <= WT_S; ++s) {
+        int64_t t = t_base + s;
+        t = t > t_max ? t_max : t;
+        if (s < WT_S || OP == OP_GAE) v[s] = __ldcs(A.v + t * A.N + colc);
+      }
+    }
+  }
+  float lastv = 0.0f;  // (the next_value form of GAE is dispatched to another kernel)
+  if (OP == OP_GAE && A.last) lastv = __ldcg(A.last + colc);
+  // Scheduling fence (see scan_tm_tile4_kernel): the barrier pins the loads above, the never-taken
+  // branch on an opaque zero pins their consumers below.
+  __syncthreads();
+  if (*reinterpret_cast<volatile int *>(&s_zero) != 0 || !warp_on) return;
+
+  const bool full_cols = ((int64_t)wgroup + 1) * 32 <= A.N;
+  if (interior && full_cols)
+    wtile_body<OP, HD, true>(A, ws, epoch, a, v, db, lastv, chunk, wgroup, n_chunks, n_wgroups, lane,
+                             col, colc, valid);
+  else
+    wtile_body<OP, HD, false>(A, ws, epoch, a, v, db, lastv, chunk, wgroup, n_chunks, n_wgroups, lane,
+                              col, colc, valid);
+}
+
+// ---- time-major two-launch scan over L2-sized time ranges ----------------------------------
+// No spin-waits.  The trajectory is cut into ranges of RG chunks (a chunk = 32 columns x R2_S steps
+// owned by one warp).  For each range, last first:
+//   scan_tm_agg_kernel    every warp reduces its chunk to an affine map        (reads the inputs)
+//   scan_tm_apply_kernel  every warp re-reads its chunk (L2-resident: the range is sized for that),
+//                         folds the maps of the later chunks of the range, starts from the output
+//                         already written at the first step of the next range, and writes the results
+// so DRAM sees each input once and each output once.
+constexpr int R2_S = 16;
+
+template <int OP, bool HD>
+struct R2Tile {
+  float a[R2_S];
+  float v[R2_S + 1];
+  unsigned char db[R2_S];
+  unsigned int dmask, inmask;
+  float bgain, lastv;
+
+  __device__ __forceinline__ void load(const ScanArgs &A, int64_t t_base, int64_t colc, int64_t dcol,
+                                       bool valid, bool keep_l2) {
+    const int64_t t_max = A.T - 1;
+#pragma unroll
+    for (int s = 0; s < R2_S; ++s) {
+      int64_t t = t_base + s;
+      t = t > t_max ? t_max : t;
+      a[s] = keep_l2 ? __ldcg(A.a + t * A.N + colc) : __ldcs(A.a + t * A.N + colc);
+    }
+    if (OP != OP_DR) {
+#pragma unroll
+      for (int s = 0; s <= R2_S; ++s) {
+        int64_t t = t_base + s;
+        t = t > t_max ? t_max : t;
+        if (s < R2_S || OP == OP_GAE)
+          v[s] = keep_l2 ? __ldcg(A.v + t * A.N + colc) : __ldcs(A.v + t * A.N + colc);
+      }
+    }
+    if (HD) {
+#pragma unroll
+      for (int s = 0; s < R2_S; ++s) {
+        int64_t t = t_base + s;
+        t = t > t_max ? t_max : t;
+        db[s] = keep_l2 ? __ldcg(A.done + t * A.B + dcol) : __ldcs(A.done + t * A.B + dcol);
+      }
+    }
+    lastv = 0.0f;
+    if (OP == OP_GAE && A.last) lastv = __ldcg(A.last + colc);
+  }
+  // call after a block barrier: ptxas otherwise sinks the first consumer between the loads, and the
+  // in-order warp then waits a full memory latency before it issues the remaining loads
+  // `z` is a zero the compiler cannot see (read from shared memory after the barrier): xor-ing it
+  // into every loaded register ties all consumers to a point behind the barrier, i.e. behind the
+  // issue of the last load
+  __device__ __forceinline__ void prepare(const ScanArgs &A, int64_t t_base, bool valid, int z) {
+    const int64_t t_max = A.T - 1;
+#pragma unroll
+    for (int s = 0; s < R2_S; ++s) a[s] = __int_as_float(__float_as_int(a[s]) ^ z);
+    if (OP != OP_DR) {
+#pragma unroll
+      for (int s = 0; s <= R2_S; ++s)
+        if (s < R2_S || OP == OP_GAE) v[s] = __int_as_float(__float_as_int(v[s]) ^ z);
+    }
+    dmask = 0u;
+    if (HD) {
+#pragma unroll
+      for (int s = 0; s < R2_S; ++s) dmask |= (((int)db[s] ^ z) ? 1u : 0u) << s;
+    }
+    inmask = 0u;
+#pragma unroll
+    for (int s = 0; s < R2_S; ++s) inmask |= ((valid && t_base + s <= t_max) ? 1u : 0u) << s;
+    bgain = OP == OP_GAE ? A.gl : A.gamma;
+    if (OP == OP_GAE) {
+#pragma unroll
+      for (int s = 0; s < R2_S; ++s) {
+        const float m = ((dmask >> s) & 1u) ? 0.0f : 1.0f;
+        const float vn = (t_base + s + 1 > t_max) ? lastv : v[s + 1];
+        a[s] = __fsub_rn(__fadd_rn(a[s], __fmul_rn(__fmul_rn(A.gamma, vn), m)), v[s]);
+      }
+    }
+  }
+  __device__ __forceinline__ float acoef(int s) const { return ((inmask >> s) & 1u) ? a[s] : 0.0f; }
+  __device__ __forceinline__ float bcoef(int s) const {
+    if (!((inmask >> s) & 1u)) return 1.0f;
+    if (OP == OP_AFFINE) return v[s];
+    return ((dmask >> s) & 1u) ? __fmul_rn(0.0f, bgain) : __fmul_rn(1.0f, bgain);
+  }
+  __device__ __forceinline__ void composite(float &ca, float &cb) const {
+    ca = 0.0f, cb = 1.0f;
+#pragma unroll
+    for (int s = R2_S - 1; s >= 0; --s) {
+      const float bs = bcoef(s);
+      ca = scan_step(acoef(s), bs, ca);
+      cb = __fmul_rn(bs, cb);
+    }
+  }
+};
+
+// grid = (column groups of 32*warps, chunks of the range); warp -> 32 columns
+template <int OP, bool HD>
+__global__ void __launch_bounds__(256)
+    scan_tm_agg_kernel(const __grid_constant__ ScanArgs A, float2 *__restrict__ agg, int chunk0) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int chunk = chunk0 + blockIdx.y;
+  const int64_t col = ((int64_t)blockIdx.x * 8 + w) * 32 + lane;
+  const bool valid = col < A.N;
+  const int64_t colc = valid ? col : A.N - 1;
+  const int64_t dcol = A.E == 1 ? colc : colc / A.E;
+  __shared__ int s_zero;
+  if (threadIdx.x == 0) s_zero = 0;
+  R2Tile<OP, HD> tile;
+  tile.load(A, (int64_t)chunk * R2_S, colc, dcol, valid, true);
+  __syncthreads();
+  const int z = *reinterpret_cast<volatile int *>(&s_zero);
+  tile.prepare(A, (int64_t)chunk * R2_S, valid, z);
+  float ca, cb;
+  tile.composite(ca, cb);
+  if (valid) agg[(size_t)chunk * A.N + col] = make_float2(ca, cb);
+}
+
+template <int OP, bool HD>
+__global__ void __launch_bounds__(256)
+    scan_tm_apply_kernel(const __grid_constant__ ScanArgs A, const float2 *__restrict__ agg,
+                         int chunk0, int chunk_end, int n_chunks) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int chunk = chunk_end - 1 - (int)blockIdx.y;  // latest chunk first: its inputs were read last
+  const int64_t col = ((int64_t)blockIdx.x * 8 + w) * 32 + lane;
+  const bool valid = col < A.N;
+  const int64_t colc = valid ? col : A.N - 1;
+  const int64_t dcol = A.E == 1 ? colc : colc / A.E;
+  const int64_t t_base = (int64_t)chunk * R2_S;
+  __shared__ int s_zero;
+  if (threadIdx.x == 0) s_zero = 0;
+  R2Tile<OP, HD> tile;
+  tile.load(A, t_base, colc, dcol, valid, false);
+  // carry at the end of the range: boundary value, or the output at the first step of the next range
+  float x;
+  if (chunk_end >= n_chunks) x = scan_init<OP>(A, colc);
+  else x = __ldcg(A.out + (int64_t)chunk_end * R2_S * A.N + colc);
+  // the maps of the later chunks of this range (at most 63), requested with the tile
+  constexpr int MAXG = 16;
+  float2 g[MAXG];
+  const int n_later = chunk_end - 1 - chunk;
+#pragma unroll
+  for (int u = 0; u < MAXG; ++u) {
+    int c = chunk_end - 1 - u;
+    c = c > chunk ? c : chunk + 1 <= chunk_end - 1 ? chunk + 1 : chunk;
+    g[u] = __ldcg(agg + (size_t)c * A.N + colc);
+  }
+  __syncthreads();
+  const int z = *reinterpret_cast<volatile int *>(&s_zero);
+  tile.prepare(A, t_base, valid, z);
+  x = __int_as_float(__float_as_int(x) ^ z);
+#pragma unroll
+  for (int u = 0; u < MAXG; ++u)
+    if (u < n_later)
+      x = scan_step(__int_as_float(__float_as_int(g[u].x) ^ z), __int_as_float(__float_as_int(g[u].y) ^ z), x);
+  for (int c = chunk_end - 1 - MAXG; c > chunk; --c) {  // ranges longer than MAXG chunks (rare)
+    const float2 q = __ldg(agg + (size_t)c * A.N + colc);
+    x = scan_step(q.x, q.y, x);
+  }
+  if (!valid) return;
+  const int64_t t_max = A.T - 1;
+#pragma unroll
+  for (int s = R2_S - 1; s >= 0; --s) {
+    const int64_t t = t_base + s;
+    if (t <= t_max) {
+      x = scan_step(tile.a[s], tile.bcoef(s), x);
+      const int64_t i = t * A.N + col;
+      A.out[i] = x;  // default caching: the first row of a range is read back as the next carry
+      if (OP == OP_GAE && A.ret) __stcs(A.ret + i, __fadd_rn(x, tile.v[s]));
     }
   }
 }
@@ -459,9 +1147,11 @@ __global__ void __launch_bounds__(256) scan_bm_warp_kernel(const __grid_constant
 template <int OP, bool VEC, bool HAS_NV>
 static void launch_bm(const ScanArgs &A, cudaStream_t st) {
   const int64_t blocks = (A.N * 32 + 255) / 256;
-  if (A.T > 512) scan_bm_warp_kernel<OP, VEC, HAS_NV, 4><<<(unsigned)blocks, 256, 0, st>>>(A);
+  if (OP != OP_GAE && A.T >= 2048) scan_bm_warp_kernel<OP, VEC, HAS_NV, 8><<<(unsigned)blocks, 256, 0, st>>>(A);
+  else if (A.T > 512) scan_bm_warp_kernel<OP, VEC, HAS_NV, 4><<<(unsigned)blocks, 256, 0, st>>>(A);
   else scan_bm_warp_kernel<OP, VEC, HAS_NV, 1><<<(unsigned)blocks, 256, 0, st>>>(A);
 }
+
 
 static bool aligned16(const void *p) { return (((uintptr_t)p) & 15) == 0; }
 
@@ -482,13 +1172,8 @@ static int tile_workspace(size_t need, uint8_t **p) {
   return MRL_OK;
 }
 
-template <int OP>
-static int launch_scan(ScanArgs A, int32_t layout, int32_t mode, cudaStream_t st) {
-  if (A.T <= 0 || A.N <= 0) return MRL_OK;
-  if (g_tile_mode < 0) {
-    const char *e = getenv("MRL_TM_KERNEL");
-    g_tile_mode = (e && e[0] == 'c') ? 1 : 0;
-  }
+template <int OP, bool HD>
+static int launch_scan_hd(ScanArgs A, int32_t layout, int32_t mode, cudaStream_t st) {
   if (layout == MRL_TIME_MAJOR) {
     A.st = A.N, A.sc = 1, A.dst = A.B, A.dsc = 1;
     bool chunked;
@@ -496,7 +1181,82 @@ static int launch_scan(ScanArgs A, int32_t layout, int32_t mode, cudaStream_t st
     else if (mode == MRL_SCAN_PARALLEL) chunked = A.T >= 2;
     else chunked = A.T >= 64 && A.N < (int64_t)kNumSM * 1024;
     const int64_t n_chunks = (A.T + TM_TC - 1) / TM_TC;
-    if (chunked && g_tile_mode == 0 && n_chunks <= TM_MAX_CHUNKS) {
+    const bool vec4 = A.E == 1 && A.N % 4 == 0 && aligned16(A.a) && aligned16(A.out) &&
+                      (OP == OP_DR || aligned16(A.v)) && (!A.nv || aligned16(A.nv)) &&
+                      (!A.ret || aligned16(A.ret)) && (!A.last || aligned16(A.last)) &&
+                      (!A.done || (((uintptr_t)A.done) & 3) == 0);
+    if (chunked && g_tile_mode == 6 && !(OP == OP_GAE && A.nv)) {
+      // two launches per L2-sized time range, last range first
+      static const int64_t range_mb = getenv("MRL_TM_RANGE_MB") ? atoll(getenv("MRL_TM_RANGE_MB")) : 24;
+      const int64_t nch = (A.T + R2_S - 1) / R2_S;
+      const int64_t bytes_per_chunk = (int64_t)R2_S * A.N * (OP == OP_DR ? 5 : 9);
+      int64_t rg = (range_mb << 20) / (bytes_per_chunk > 0 ? bytes_per_chunk : 1);
+      if (rg < 1) rg = 1;
+      if (rg > 64) rg = 64;
+      uint8_t *wsp;
+      int rc = tile_workspace((size_t)nch * A.N * sizeof(float2), &wsp);
+      if (rc) return rc;
+      float2 *agg = reinterpret_cast<float2 *>(wsp);
+      const unsigned gx = (unsigned)((A.N + 255) / 256);
+      for (int64_t end = nch; end > 0; end -= rg) {
+        const int64_t begin = end - rg > 0 ? end - rg : 0;
+        dim3 grid(gx, (unsigned)(end - begin));
+        scan_tm_agg_kernel<OP, HD><<<grid, 256, 0, st>>>(A, agg, (int)begin);
+        g_launches.fetch_add(1);
+        scan_tm_apply_kernel<OP, HD><<<grid, 256, 0, st>>>(A, agg, (int)begin, (int)end, (int)nch);
+        if (end - rg > 0) g_launches.fetch_add(1);
+      }
+    } else if (chunked && (g_tile_mode == 5 || g_tile_mode == 0) && !(OP == OP_GAE && A.nv)) {
+      const int64_t nch = (A.T + WT_S - 1) / WT_S;
+      const int64_t n_wgroups = (A.N + 31) / 32;
+      const int64_t n_cgroups = (n_wgroups + WT_WARPS - 1) / WT_WARPS;
+      const size_t tiles = (size_t)nch * n_wgroups;
+      const size_t agg_bytes = tiles * 32 * sizeof(uint4);
+      const size_t need = 256 + agg_bytes + tiles * 32 * sizeof(uint2);
+      // flag-in-payload workspace: zeroed once when (re)allocated, then validated by the launch epoch
+      static uint8_t *ll_ws = nullptr;
+      static size_t ll_bytes = 0;
+      static unsigned long long ll_ticket_base = 0;
+      static unsigned int ll_epoch = 0;
+      if (need > ll_bytes) {
+        if (ll_ws) {
+          MRL_CUDA(cudaStreamSynchronize(st));
+          cudaFree(ll_ws);
+        }
+        ll_ws = nullptr, ll_bytes = 0;
+        MRL_CUDA(cudaMalloc((void **)&ll_ws, need));
+        MRL_CUDA(cudaMemsetAsync(ll_ws, 0, need, st));
+        ll_bytes = need, ll_ticket_base = 0, ll_epoch = 0;
+      }
+      if (++ll_epoch == 0u) {  // epoch wrapped: clear stale words once
+        MRL_CUDA(cudaMemsetAsync(ll_ws + 256, 0, ll_bytes - 256, st));
+        ll_epoch = 1;
+      }
+      WTileWs ws;
+      ws.ticket = reinterpret_cast<unsigned long long *>(ll_ws);
+      ws.agg = reinterpret_cast<uint4 *>(ll_ws + 256);
+      ws.incl = reinterpret_cast<uint2 *>(ll_ws + 256 + agg_bytes);
+      scan_tm_wtile_kernel<OP, HD><<<(unsigned)(nch * n_cgroups), WT_WARPS * 32, 0, st>>>(
+          A, ws, ll_ticket_base, ll_epoch, (int)nch, (int)n_wgroups, (int)n_cgroups);
+      ll_ticket_base += (unsigned long long)(nch * n_cgroups);
+    } else if (chunked && (g_tile_mode == 3 || g_tile_mode == 0) && vec4) {
+      const int64_t n4 = (A.T + T4_TC - 1) / T4_TC;
+      const int64_t n_groups = (A.N + T4_COLS - 1) / T4_COLS;
+      const size_t tiles = (size_t)n4 * n_groups;
+      const size_t flag_bytes = (4 + tiles * 4 + 255) / 256 * 256;
+      const size_t agg_bytes = tiles * T4_COLS * sizeof(float2);
+      uint8_t *wsp;
+      int rc = tile_workspace(flag_bytes + agg_bytes + tiles * T4_COLS * sizeof(float), &wsp);
+      if (rc) return rc;
+      MRL_CUDA(cudaMemsetAsync(wsp, 0, flag_bytes, st));
+      Tile4Ws ws;
+      ws.ticket = reinterpret_cast<unsigned int *>(wsp);
+      ws.flag = ws.ticket + 1;
+      ws.agg = reinterpret_cast<float2 *>(wsp + flag_bytes);
+      ws.incl = reinterpret_cast<float *>(wsp + flag_bytes + agg_bytes);
+      dim3 block(32, T4_W);
+      scan_tm_tile4_kernel<OP, HD><<<(unsigned)tiles, block, 0, st>>>(A, ws, (int)n4, (int)n_groups);
+    } else if (chunked && g_tile_mode <= 1 && n_chunks <= TM_MAX_CHUNKS && g_tile_mode != 2) {
       const int64_t n_groups = (A.N + 31) / 32;
       const size_t tiles = (size_t)n_chunks * n_groups;
       const size_t flag_bytes = (4 + tiles * 4 + 255) / 256 * 256;
@@ -509,23 +1269,23 @@ static int launch_scan(ScanArgs A, int32_t layout, int32_t mode, cudaStream_t st
       ws.flag = ws.ticket + 1;
       ws.agg = reinterpret_cast<float2 *>(wsp + flag_bytes);
       dim3 block(32, TM_W);
-      scan_tm_tile_kernel<OP><<<(unsigned)tiles, block, 0, st>>>(A, ws, (int)n_chunks, (int)n_groups);
+      scan_tm_tile_kernel<OP, HD><<<(unsigned)tiles, block, 0, st>>>(A, ws, (int)n_chunks, (int)n_groups);
     } else if (chunked) {
       int W = 32;
       while (W > 1 && A.T / W < 8) W >>= 1;
       const int64_t chunk = (A.T + W - 1) / W;
       dim3 block(32, W);
       const int64_t blocks = (A.N + 31) / 32;
-      scan_tm_chunked_kernel<OP><<<(unsigned)blocks, block, 0, st>>>(A, chunk);
+      scan_tm_chunked_kernel<OP, HD><<<(unsigned)blocks, block, 0, st>>>(A, chunk);
     } else {
       const int64_t blocks = (A.N + 127) / 128;
-      scan_seq_kernel<OP><<<(unsigned)blocks, 128, 0, st>>>(A);
+      scan_seq_kernel<OP, HD><<<(unsigned)blocks, 128, 0, st>>>(A);
     }
   } else {
     A.st = 1, A.sc = A.T, A.dst = 1, A.dsc = A.T;
     if (mode == MRL_SCAN_SEQUENTIAL) {
       const int64_t blocks = (A.N + 127) / 128;
-      scan_seq_kernel<OP><<<(unsigned)blocks, 128, 0, st>>>(A);
+      scan_seq_kernel<OP, HD><<<(unsigned)blocks, 128, 0, st>>>(A);
     } else {
       const bool vec = (A.T % 4 == 0) && aligned16(A.a) && aligned16(A.out) &&
                        (OP == OP_DR || aligned16(A.v)) && (!A.nv || aligned16(A.nv)) &&
@@ -539,6 +1299,26 @@ static int launch_scan(ScanArgs A, int32_t layout, int32_t mode, cudaStream_t st
   }
   MRL_LAUNCHED();
   return MRL_OK;
+}
+
+template <int OP>
+static int launch_scan(ScanArgs A, int32_t layout, int32_t mode, cudaStream_t st) {
+  if (A.T <= 0 || A.N <= 0) return MRL_OK;
+  if (g_tile_mode < 0) {
+    const char *e = getenv("MRL_TM_KERNEL");
+    // default 0: 128-column tiles when aligned, else 32-column tiles; "t": 32-column tiles only;
+    // "c": two-pass chunked kernel only
+    // "4": 128-column CTA tiles (aligned inputs only)
+    // default / "w": warp-owned tiles with flag-in-payload look-back; "r": two launches per time range
+    g_tile_mode = 0;
+    if (e && e[0] == 'c') g_tile_mode = 2;
+    if (e && e[0] == 't') g_tile_mode = 1;
+    if (e && e[0] == '4') g_tile_mode = 3;
+    if (e && e[0] == 'w') g_tile_mode = 5;
+    if (e && e[0] == 'r') g_tile_mode = 6;
+  }
+  if (OP != OP_AFFINE && A.done) return launch_scan_hd<OP, true>(A, layout, mode, st);
+  return launch_scan_hd<OP, false>(A, layout, mode, st);
 }
 
 // grow-only device scratch for the *_host entry points
