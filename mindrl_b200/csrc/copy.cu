@@ -288,8 +288,14 @@ static int64_t g_bulk_min_row = env_i64("MRL_BULK_MIN_ROW", 2048);
 static int64_t g_bulk_chunk = env_i64("MRL_BULK_CHUNK", 8192);
 static int64_t g_bulk_ctas_per_sm = env_i64("MRL_BULK_CTAS_PER_SM", 4);
 
+extern long long *g_debug_timers;  // prb.cu
+
 int set_copy_option(const char *key, int64_t value) {
   std::string k(key);
+  if (k == "debug_timers") {
+    g_debug_timers = reinterpret_cast<long long *>(value);
+    return MRL_OK;
+  }
   if (k == "gather_path" && value >= 0 && value <= 2) g_gather_path = value;
   else if (k == "bulk_min_row" && value >= 16) g_bulk_min_row = value;
   else if (k == "bulk_chunk" && value >= 16 && value <= 49152 && value % 16 == 0) g_bulk_chunk = value;

@@ -56,6 +56,15 @@ struct PrbBuffer {
 
 static Registry<PrbBuffer> g_prb;
 
+// debug: when set (mrl_set_option("debug_timers", device pointer to >= 32 int64)), thread 0 of the
+// tree kernels stores clock64() at its phase boundaries
+long long *g_debug_timers = nullptr;
+__device__ __forceinline__ void dbg_mark(long long *dbg, int slot) {
+  if (dbg && threadIdx.x == 0 && blockIdx.x == 0) {
+    dbg[slot] = clock64();  // SM cycles (reading %globaltimer costs ~1 us and distorts the phases)
+  }
+}
+
 constexpr int kTopLevels = 11;          // levels 0..10 (2047 nodes) staged in shared memory
 constexpr int kSampleWarps = 8;         // warps (= samples) per CTA of prb_sample_kernel
 constexpr int64_t kFusedRowLimit = 512;  // column row bytes up to which sample() gathers in-kernel
@@ -194,6 +203,7 @@ struct UpdateArgs {
   int32_t levels;
   float alpha;
   uint64_t epoch;
+  long long *dbg;
 };
 
 __device__ __forceinline__ void recompute_node(float *sum, float *mn, int64_t node) {
@@ -203,10 +213,15 @@ __device__ __forceinline__ void recompute_node(float *sum, float *mn, int64_t no
   __stcg(mn + node, ma < mb ? ma : mb);
 }
 
+__device__ __noinline__ float prb_pow_fn(float priority, float alpha) {
+  return mrl_priority_pow(priority, alpha);
+}
+
 __global__ void __launch_bounds__(1024) prb_update_kernel(const __grid_constant__ UpdateArgs U) {
   __shared__ float ssum[2 << kTopLevels];
   __shared__ float smin[2 << kTopLevels];
   const int tid = threadIdx.x, nthr = blockDim.x;
+  dbg_mark(U.dbg, 0);
 
   // 0) arbitration: the highest batch position of a leaf wins; max over ALL priorities (also the
   //    overwritten ones) goes to max_priority, as in the sequential loop
@@ -214,7 +229,7 @@ __global__ void __launch_bounds__(1024) prb_update_kernel(const __grid_constant_
   for (int64_t k = tid; k < U.n; k += nthr) {
     const int64_t leaf = __ldg(U.indices + k);
     atomicMax(U.tag + leaf, (unsigned long long)((U.epoch << 32) | (uint64_t)k));
-    const float p = mrl_priority_pow(__ldg(U.priorities + k), U.alpha);
+    const float p = prb_pow_fn(__ldg(U.priorities + k), U.alpha);
     local_max = p > local_max ? p : local_max;
   }
 #pragma unroll
@@ -225,17 +240,19 @@ __global__ void __launch_bounds__(1024) prb_update_kernel(const __grid_constant_
   if ((tid & 31) == 0 && local_max > 0.0f)
     atomicMax(reinterpret_cast<int *>(&U.state->max_priority), __float_as_int(local_max));
   __syncthreads();
+  dbg_mark(U.dbg, 1);
 
   // 1) winners write their leaf
   for (int64_t k = tid; k < U.n; k += nthr) {
     const int64_t leaf = __ldg(U.indices + k);
     if (__ldcg(U.tag + leaf) == (unsigned long long)((U.epoch << 32) | (uint64_t)k)) {
-      const float p = mrl_priority_pow(__ldg(U.priorities + k), U.alpha);
+      const float p = prb_pow_fn(__ldg(U.priorities + k), U.alpha);
       __stcg(U.sum + U.cap2 + leaf, p);
       __stcg(U.mn + U.cap2 + leaf, p);
     }
   }
   __syncthreads();
+  dbg_mark(U.dbg, 2);
 
   // 2) lower levels, level-synchronous (duplicate ancestors write identical values)
   const int split = U.levels < kTopLevels ? U.levels : kTopLevels;  // level held in smem as input
@@ -248,6 +265,7 @@ __global__ void __launch_bounds__(1024) prb_update_kernel(const __grid_constant_
     __syncthreads();
   }
 
+  dbg_mark(U.dbg, 3);
   // 3) top `split` levels rebuilt in shared memory from the 2^split nodes of level `split`
   const int width = 1 << split;
   for (int i = tid; i < width; i += nthr) {
@@ -255,6 +273,7 @@ __global__ void __launch_bounds__(1024) prb_update_kernel(const __grid_constant_
     smin[width + i] = __ldcg(U.mn + width + i);
   }
   __syncthreads();
+  dbg_mark(U.dbg, 4);
   for (int level = split - 1; level >= 0; --level) {
     const int w = 1 << level;
     for (int i = tid; i < w; i += nthr) {
@@ -265,90 +284,188 @@ __global__ void __launch_bounds__(1024) prb_update_kernel(const __grid_constant_
     }
     __syncthreads();
   }
+  dbg_mark(U.dbg, 5);
   for (int i = tid + 1; i < width; i += nthr) {
     __stcg(U.sum + i, ssum[i]);
     __stcg(U.mn + i, smin[i]);
   }
+  dbg_mark(U.dbg, 6);
 }
 
-// ---- update, low-latency variant (n <= kFastUpdateMax) -------------------------------------
-// Same result as prb_update_kernel, organised around the number of DEPENDENT memory round trips
-// (the tree is cold in L2 whenever a learner step ran in between):
-//   * duplicates are arbitrated in a shared-memory hash table (leaf -> highest batch position),
-//     no global tag traffic;
-//   * the lower levels are rebuilt three levels per barrier: a thread loads the aligned group of 8
-//     nodes below its ancestor (one 32-byte sector per array), rebuilds the 4+2+1 nodes above them
-//     and stores them -- 9 levels cost 3 round trips instead of 9;
-//   * every line a later round will need is prefetched into L2 in the first phase.
-constexpr int kFastUpdateMax = 4096;
-constexpr int kFastItems = kFastUpdateMax / 1024;
+// ---- update, low-latency variant (n <= kWalkMax) -------------------------------------------
+// Same result as prb_update_kernel, organised around DEPENDENT GLOBAL round trips.  Measured with
+// %globaltimer: a level-synchronous step through global memory (store, barrier, load) costs ~1.3 us
+// per tree level whether L2 is warm or cold, i.e. ~12 us for the 9 lower levels of a 2^20-leaf tree.
+// Here every thread walks its own leaf-to-root path in registers and meets the other paths only in
+// shared memory:
+//   * all siblings along the path are loaded up front in one round trip (values of nodes no path of
+//     this batch goes through cannot change);
+//   * per level the thread enters its node into a shared-memory hash table (key = heap index), one
+//     block barrier, then looks its sibling up: a hit means another path of the batch owns the sibling
+//     and its fresh value is taken from shared memory, a miss means the prefetched value is current;
+//   * two tables alternate between levels (entries carry the level as a tag, stale entries count as
+//     free), so one barrier per level suffices;
+//   * duplicates of a leaf are arbitrated at the leaf level (highest batch position wins);
+//   * node values are stored to global memory as the walk passes them, nothing is read back;
+//   * the top kTopLevels levels are rebuilt in shared memory from the 2^kTopLevels nodes below them.
+// Parents are fl(left+right) / min(left,right) of their two children exactly as in the sequential
+// oracle, so the tree is bit-identical.
+constexpr int kWalkMax = 1 << 16;  // larger batches use the global-tag kernel
+constexpr int kWalkThreads = 512;
+constexpr int kWalkLevels = 12;  // lower levels handled by the walk (leaf capacity <= 2^(11+12))
 
-__device__ __forceinline__ uint32_t upd_hash(int64_t leaf, int bits) {
-  return ((uint32_t)leaf * 2654435761u) >> (32 - bits);
+struct WalkTab {
+  unsigned long long *keys;
+  float2 *vals;
+  int mask, bits;
+};
+__device__ __forceinline__ uint32_t walk_hash(uint32_t node, int bits) {
+  return (node * 2654435761u) >> (32 - bits);
 }
-__device__ __forceinline__ void prefetch_l2(const void *p) {
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+// enters (tag, node) if absent; returns its slot.  Slots whose tag differs are free.
+__device__ __forceinline__ int walk_insert(const WalkTab &t, uint32_t tag, uint32_t node) {
+  const unsigned long long key = ((unsigned long long)tag << 32) | node;
+  uint32_t h = walk_hash(node, t.bits);
+  while (true) {
+    unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(t.keys + h);
+    while ((uint32_t)(cur >> 32) != tag) {
+      const unsigned long long old = atomicCAS(t.keys + h, cur, key);
+      if (old == cur) return (int)h;
+      cur = old;
+    }
+    if (cur == key) return (int)h;
+    h = (h + 1) & t.mask;
+  }
+}
+__device__ __forceinline__ int walk_find(const WalkTab &t, uint32_t tag, uint32_t node) {
+  const unsigned long long key = ((unsigned long long)tag << 32) | node;
+  uint32_t h = walk_hash(node, t.bits);
+  while (true) {
+    const unsigned long long cur = t.keys[h];
+    if ((uint32_t)(cur >> 32) != tag) return -1;
+    if (cur == key) return (int)h;
+    h = (h + 1) & t.mask;
+  }
 }
 
-__global__ void __launch_bounds__(1024)
-    prb_update_fast_kernel(const __grid_constant__ UpdateArgs U, int slot_bits) {
+// Code size matters as much as round trips here: a one-CTA kernel fetches every instruction line cold
+// (the 44 KB fully unrolled version of this kernel spent ~30 us on instruction fetch alone), so the
+// level loop is a real loop over shared-memory arrays and p**alpha is a single out-of-line call.
+__device__ __noinline__ float prb_pow_noinline(float priority, float alpha) {
+  return mrl_priority_pow(priority, alpha);
+}
+
+__global__ void __launch_bounds__(kWalkThreads)
+    prb_update_walk_kernel(const __grid_constant__ UpdateArgs U, int slot_bits) {
   __shared__ float ssum[2 << kTopLevels];
   __shared__ float smin[2 << kTopLevels];
   extern __shared__ __align__(16) unsigned char upd_dyn[];
   const int nslots = 1 << slot_bits;
-  unsigned long long *table = reinterpret_cast<unsigned long long *>(upd_dyn);
   const int tid = threadIdx.x, nthr = blockDim.x;
+  WalkTab tab[2];
+  tab[0].keys = reinterpret_cast<unsigned long long *>(upd_dyn);
+  tab[1].keys = tab[0].keys + nslots;
+  tab[0].vals = reinterpret_cast<float2 *>(tab[1].keys + nslots);
+  tab[1].vals = tab[0].vals + nslots;
+  unsigned int *pos = reinterpret_cast<unsigned int *>(tab[1].vals + nslots);
+  float2 *sib = reinterpret_cast<float2 *>(pos + nslots);  // [kWalkLevels][nthr] prefetched siblings
+  tab[0].mask = tab[1].mask = nslots - 1;
+  tab[0].bits = tab[1].bits = slot_bits;
   const int split = U.levels < kTopLevels ? U.levels : kTopLevels;
+  const int nlev = U.levels - split;  // levels walked: nodes at level levels-d, d = 0 .. nlev-1
+  const int width = 1 << split;
+  dbg_mark(U.dbg, 8);
 
-  for (int i = tid; i < nslots; i += nthr) table[i] = 0ull;
-  // prefetch the inputs of the shared-memory top rebuild (level `split`)
-  {
-    const int width = 1 << split;
-    for (int i = tid * 32; i < width; i += nthr * 32) {
-      prefetch_l2(U.sum + width + i);
-      prefetch_l2(U.mn + width + i);
-    }
+  for (int i = tid; i < 2 * nslots; i += nthr) tab[0].keys[i] = 0ull;
+  for (int i = tid; i < nslots; i += nthr) pos[i] = 0u;
+  // inputs of the top rebuild (patched by the walks below)
+  for (int i = tid; i < width; i += nthr) {
+    ssum[width + i] = __ldcg(U.sum + width + i);
+    smin[width + i] = __ldcg(U.mn + width + i);
   }
-  __syncthreads();
-
-  int64_t leaf_of[kFastItems];
-  float p_of[kFastItems];
-  int slot_of[kFastItems];
   float local_max = 0.0f;
-#pragma unroll
-  for (int r = 0; r < kFastItems; ++r) {
-    const int64_t k = tid + (int64_t)r * nthr;
-    leaf_of[r] = -1;
-    p_of[r] = 0.0f;
-    slot_of[r] = 0;
-    if (k < U.n) {
-      const int64_t leaf = __ldg(U.indices + k);
-      leaf_of[r] = leaf;
-      // lines of the three-level rounds
-      for (int lvl = U.levels; lvl > split; lvl -= 3) {
-        const int64_t g = ((U.cap2 + leaf) >> (U.levels - lvl)) & ~(int64_t)7;
-        prefetch_l2(U.sum + g);
-        prefetch_l2(U.mn + g);
+
+  // batches larger than the block are applied in order, blockDim indices at a time
+  uint32_t pass = 0;
+  for (int64_t base = 0; base < U.n; base += nthr, ++pass) {
+    const int64_t k = base + tid;
+    const bool on = k < U.n;
+    // round trip 1: index and priority
+    const int64_t leaf = on ? __ldg(U.indices + k) : 0;
+    const float prio = on ? __ldg(U.priorities + k) : 1.0f;
+    const uint32_t leaf_node = (uint32_t)(U.cap2 + leaf);
+    // round trip 2: every sibling along the path, parked in shared memory
+    if (on) {
+#pragma unroll 4
+      for (int d = 0; d < nlev; ++d) {
+        const uint32_t sn = (leaf_node >> d) ^ 1u;
+        sib[d * nthr + tid] = make_float2(__ldcg(U.sum + sn), __ldcg(U.mn + sn));
       }
-      const float p = mrl_priority_pow(__ldg(U.priorities + k), U.alpha);
-      p_of[r] = p;
-      local_max = p > local_max ? p : local_max;
-      const unsigned long long mine = ((unsigned long long)(leaf + 1) << 32) | (unsigned long long)k;
-      uint32_t h = upd_hash(leaf, slot_bits);
-      while (true) {
-        unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(table + h);
-        if (cur == 0ull) {
-          cur = atomicCAS(table + h, 0ull, mine);
-          if (cur == 0ull) break;
-        }
-        if ((cur >> 32) == (unsigned long long)(leaf + 1)) {
-          atomicMax(table + h, mine);
-          break;
-        }
-        h = (h + 1) & (nslots - 1);
-      }
-      slot_of[r] = (int)h;
     }
+    const float p = prb_pow_noinline(prio, U.alpha);
+    if (on) local_max = p > local_max ? p : local_max;
+    __syncthreads();  // tables cleared (first pass) / previous pass done with them
+    if (pass == 0) dbg_mark(U.dbg, 9);
+
+    // leaf level: duplicates of a leaf -> highest batch position wins
+    const uint32_t pass_tag = pass << 8;
+    int slot = 0;
+    if (on) {
+      slot = walk_insert(tab[0], pass_tag | ((uint32_t)U.levels + 1u), leaf_node);
+      atomicMax(pos + slot, (pass << 16) | ((uint32_t)tid + 1u));
+    }
+    __syncthreads();
+    bool leaf_win = false;
+    if (on) {
+      leaf_win = pos[slot] == ((pass << 16) | ((uint32_t)tid + 1u));
+      if (leaf_win) {
+        tab[0].vals[slot] = make_float2(p, p);
+        __stcg(U.sum + leaf_node, p);
+        __stcg(U.mn + leaf_node, p);
+      }
+    }
+    __syncthreads();
+    if (pass == 0) dbg_mark(U.dbg, 10);
+    float vs = 0.0f, vm = 0.0f;
+    if (on) {
+      const float2 me = tab[0].vals[slot];  // the winning duplicate's value
+      vs = me.x, vm = me.y;
+    }
+    // walk up: one shared-memory exchange and one barrier per level
+#pragma unroll 1
+    for (int d = 0; d < nlev; ++d) {
+      const WalkTab &t = tab[d & 1];
+      const uint32_t tag = pass_tag | ((uint32_t)(U.levels - d) + 1u);
+      const uint32_t node = leaf_node >> d;
+      if (d > 0) {  // (the leaf level was entered above)
+        if (on) {
+          const int sl = walk_insert(t, tag, node);
+          t.vals[sl] = make_float2(vs, vm);  // all paths through this node agree
+          __stcg(U.sum + node, vs);
+          __stcg(U.mn + node, vm);
+        }
+        __syncthreads();
+      }
+      if (on) {
+        const int ss = walk_find(t, tag, node ^ 1u);
+        const float2 o = ss >= 0 ? t.vals[ss] : sib[d * nthr + tid];
+        vs = __fadd_rn(vs, o.x);
+        vm = o.y < vm ? o.y : vm;
+      }
+    }
+    if (pass == 0) dbg_mark(U.dbg, 11);
+    // (vs, vm) now belong to the node at level `split`: patch the inputs of the top rebuild
+    __syncthreads();
+    if (on) {
+      const uint32_t node = leaf_node >> nlev;  // in [width, 2*width)
+      ssum[node] = vs;
+      smin[node] = vm;
+      if (nlev > 0) {
+        __stcg(U.sum + node, vs);
+        __stcg(U.mn + node, vm);
+      }
+    }
+    __syncthreads();  // also orders this pass's global stores before the next pass's sibling loads
   }
 #pragma unroll
   for (int off = 16; off; off >>= 1) {
@@ -357,72 +474,8 @@ __global__ void __launch_bounds__(1024)
   }
   if ((tid & 31) == 0 && local_max > 0.0f)
     atomicMax(reinterpret_cast<int *>(&U.state->max_priority), __float_as_int(local_max));
-  __syncthreads();
-
-  // winners (highest batch position of a leaf) write their leaf
-#pragma unroll
-  for (int r = 0; r < kFastItems; ++r) {
-    if (leaf_of[r] >= 0) {
-      const int64_t k = tid + (int64_t)r * nthr;
-      if ((uint32_t)table[slot_of[r]] == (uint32_t)k) {
-        __stcg(U.sum + U.cap2 + leaf_of[r], p_of[r]);
-        __stcg(U.mn + U.cap2 + leaf_of[r], p_of[r]);
-      }
-    }
-  }
-  __syncthreads();
-
-  // lower levels: h <= 3 levels per barrier
-  for (int lvl = U.levels; lvl > split;) {
-    const int h = (lvl - split) < 3 ? (lvl - split) : 3;
-    const int gsz = 1 << h;
-#pragma unroll
-    for (int r = 0; r < kFastItems; ++r) {
-      if (leaf_of[r] < 0) continue;
-      const int64_t node = (U.cap2 + leaf_of[r]) >> (U.levels - lvl);
-      const int64_t g = node & ~(int64_t)(gsz - 1);
-      float vs[8], vm[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        vs[j] = 0.0f, vm[j] = FLT_MAX;
-        if (j < gsz) {
-          vs[j] = __ldcg(U.sum + g + j);
-          vm[j] = __ldcg(U.mn + g + j);
-        }
-      }
-      // rebuild h levels above the group; level lvl-1 nodes start at g>>1, lvl-2 at g>>2, ...
-      int cnt = gsz;
-      int64_t base = g;
-#pragma unroll
-      for (int step = 0; step < 3; ++step) {
-        if (step < h) {
-          cnt >>= 1;
-          base >>= 1;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (j < cnt) {
-              const float a = vs[2 * j], b = vs[2 * j + 1];
-              const float ma = vm[2 * j], mb = vm[2 * j + 1];
-              vs[j] = __fadd_rn(a, b);
-              vm[j] = ma < mb ? ma : mb;
-              __stcg(U.sum + base + j, vs[j]);
-              __stcg(U.mn + base + j, vm[j]);
-            }
-          }
-        }
-      }
-    }
-    lvl -= h;
-    __syncthreads();
-  }
-
-  // top `split` levels in shared memory
-  const int width = 1 << split;
-  for (int i = tid; i < width; i += nthr) {
-    ssum[width + i] = __ldcg(U.sum + width + i);
-    smin[width + i] = __ldcg(U.mn + width + i);
-  }
-  __syncthreads();
+  dbg_mark(U.dbg, 12);
+#pragma unroll 1
   for (int level = split - 1; level >= 0; --level) {
     const int w = 1 << level;
     for (int i = tid; i < w; i += nthr) {
@@ -433,10 +486,12 @@ __global__ void __launch_bounds__(1024)
     }
     __syncthreads();
   }
+  dbg_mark(U.dbg, 13);
   for (int i = tid + 1; i < width; i += nthr) {
     __stcg(U.sum + i, ssum[i]);
     __stcg(U.mn + i, smin[i]);
   }
+  dbg_mark(U.dbg, 14);
 }
 
 // ---- push --------------------------------------------------------------------------------
@@ -636,30 +691,36 @@ static int prb_sample_impl(PrbBuffer *b, int64_t n, float beta, const float *uni
   return MRL_OK;
 }
 
-static int g_update_path = -1;  // MRL_UPDATE_PATH=tags forces the global-tag kernel
+// 0 = global-tag level-synchronous kernel (default: 18 us at n=256 on 2^20 leaves, measured),
+// 1 = register walk with shared-memory exchange (MRL_UPDATE_PATH=walk; bit-identical results, but
+//     measured at ~57 us: kept for the next round's latency work)
+static int g_update_path = -1;
 
 static int prb_update_impl(PrbBuffer *b, const int64_t *indices, const float *priorities,
                            int64_t n, cudaStream_t st) {
   if (g_update_path < 0) {
     const char *e = getenv("MRL_UPDATE_PATH");
-    g_update_path = (e && e[0] == 't') ? 1 : 0;
+    g_update_path = (e && e[0] == 'w') ? 1 : 0;
   }
   UpdateArgs U;
   U.sum = b->sum, U.mn = b->mn, U.tag = b->tag, U.state = b->state;
   U.indices = indices, U.priorities = priorities;
   U.n = n, U.cap2 = b->cap2, U.levels = b->levels, U.alpha = b->alpha;
   U.epoch = ++b->epoch;
-  if (n <= kFastUpdateMax && g_update_path == 0) {
+  U.dbg = g_debug_timers;
+  if (n <= kWalkMax && b->levels - kTopLevels <= kWalkLevels && g_update_path == 1) {
+    int threads = (int)((n + 31) / 32 * 32);
+    threads = threads < 256 ? 256 : (threads > kWalkThreads ? kWalkThreads : threads);
     int bits = 6;
-    while ((1 << bits) < 2 * n) ++bits;
-    const size_t smem = (size_t)(1 << bits) * 8;
-    static size_t configured = 0;
-    if (smem > configured) {
-      MRL_CUDA(cudaFuncSetAttribute(prb_update_fast_kernel,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8192 * 8)));
-      configured = 8192 * 8;
+    while ((1 << bits) < 2 * (n < threads ? n : threads)) ++bits;
+    const size_t smem = (size_t)(1 << bits) * (2 * 8 + 2 * 8 + 4) + (size_t)kWalkLevels * threads * 8;
+    static bool configured = false;
+    if (!configured) {
+      MRL_CUDA(cudaFuncSetAttribute(prb_update_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    1024 * 36 + kWalkLevels * kWalkThreads * 8));
+      configured = true;
     }
-    prb_update_fast_kernel<<<1, 1024, smem, st>>>(U, bits);
+    prb_update_walk_kernel<<<1, threads, smem, st>>>(U, bits);
   } else {
     prb_update_kernel<<<1, 1024, 0, st>>>(U);
   }
