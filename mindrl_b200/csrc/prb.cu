@@ -35,7 +35,8 @@ namespace mrl {
 
 struct PrbState {
   float max_priority;
-  float pad[3];
+  unsigned int done_ctas;  // subtree update: CTAs that have finished their lower levels
+  float pad[2];
 };
 
 struct PrbBuffer {
@@ -77,7 +78,10 @@ __global__ void __launch_bounds__(256)
     mn[i] = FLT_MAX;
     if (i < cap2) tag[i] = 0ull;
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) state->max_priority = 1.0f;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    state->max_priority = 1.0f;
+    state->done_ctas = 0u;
+  }
 }
 
 // ---- sample ------------------------------------------------------------------------------
@@ -494,6 +498,168 @@ __global__ void __launch_bounds__(kWalkThreads)
   dbg_mark(U.dbg, 14);
 }
 
+// ---- update, subtree-partitioned over many SMs ------------------------------------------------
+// Measured (scratch/lat_test2.cu): a level of the one-CTA kernel costs 0.5 us with 32 indices and
+// 1.0 / 3.3 us with 256 / 1024 -- one SM's path to L2 serialises the scattered 32-byte requests.  So
+// the batch is spread over kSubCtas CTAs by ownership of the subtrees below level kTopLevels: the
+// lower levels of different subtrees never meet, every CTA scans the index list, keeps the entries
+// that fall into its subtrees, loads all siblings of its paths in one round trip and walks the paths
+// up in registers, exchanging values between paths that merge through a small shared-memory list
+// (typically 2..32 entries per CTA: a linear scan).  The last CTA to finish (atomic ticket after a
+// __threadfence) rebuilds the top levels in shared memory.  Parents are fl(left+right)/min of their
+// children exactly as in the sequential oracle; duplicates of a leaf resolve to the highest batch
+// position; max_priority takes every processed priority.
+constexpr int kSubCtas = 128;
+constexpr int kSubThreads = 512;
+constexpr int kSubMaxLocal = kSubThreads;  // indices scanned per pass = most entries a CTA can keep
+
+__global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __grid_constant__ UpdateArgs U) {
+  __shared__ float ssum[2 << kTopLevels];
+  __shared__ float smin[2 << kTopLevels];
+  __shared__ int s_k[kSubMaxLocal];        // batch position of each local entry
+  __shared__ uint32_t s_node[kSubMaxLocal];
+  __shared__ float2 s_val[kSubMaxLocal];
+  __shared__ int s_cnt;
+  __shared__ unsigned int s_last;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int split = U.levels < kTopLevels ? U.levels : kTopLevels;
+  const int nlev = U.levels - split;
+  const int width = 1 << split;
+  const int per_cta = (width + (int)gridDim.x - 1) / (int)gridDim.x;  // level-`split` nodes per CTA
+  const int own_lo = (int)blockIdx.x * per_cta, own_hi = own_lo + per_cta;
+  float local_max = 0.0f;
+
+  // passes of blockDim indices: the local list always fits and batch order is kept across passes
+  for (int64_t base = 0; base < U.n; base += kSubMaxLocal) {
+    const int64_t end = base + kSubMaxLocal < U.n ? base + kSubMaxLocal : U.n;
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    for (int64_t k = base + tid; k < end; k += nthr) {
+      const int64_t leaf = __ldg(U.indices + k);
+      const int top = (int)(leaf >> nlev);  // index of the level-`split` ancestor within its level
+      if (top >= own_lo && top < own_hi) s_k[atomicAdd(&s_cnt, 1)] = (int)(k - base);
+    }
+    __syncthreads();
+    const int m = s_cnt;  // <= kSubMaxLocal == blockDim: one thread per local entry
+    {
+      const int j0 = 0;
+      const int j = tid;
+      const bool on = j < m;
+      const int64_t k = on ? base + s_k[j] : 0;
+      const int64_t leaf = on ? __ldg(U.indices + k) : 0;
+      const uint32_t leaf_node = (uint32_t)(U.cap2 + leaf);
+      float p = 0.0f;
+      float sib_s[kWalkLevels], sib_m[kWalkLevels];
+      if (on) {
+#pragma unroll
+        for (int d = 0; d < kWalkLevels; ++d) {
+          sib_s[d] = 0.0f, sib_m[d] = FLT_MAX;
+          if (d < nlev) {
+            const uint32_t sn = (leaf_node >> d) ^ 1u;
+            sib_s[d] = __ldcg(U.sum + sn);
+            sib_m[d] = __ldcg(U.mn + sn);
+          }
+        }
+        p = prb_pow_fn(__ldg(U.priorities + k), U.alpha);
+        local_max = p > local_max ? p : local_max;
+      }
+      // leaf level: among local entries of the same leaf the highest batch position provides the value
+      if (on) {
+        s_node[j] = leaf_node;
+        s_val[j] = make_float2(p, p);
+      }
+      __syncthreads();
+      float vs = p, vm = p;
+      if (on) {
+        int best = s_k[j];
+        int best_i = j;
+        for (int i = j0; i < m && i < j0 + nthr; ++i)
+          if (s_node[i] == leaf_node && s_k[i] > best) best = s_k[i], best_i = i;
+        const float2 w = s_val[best_i];
+        vs = w.x, vm = w.y;
+        if (best_i == j) {
+          __stcg(U.sum + leaf_node, p);
+          __stcg(U.mn + leaf_node, p);
+        }
+      }
+      __syncthreads();
+      if (on) s_val[j] = make_float2(vs, vm);  // every entry of a leaf now carries the winner's value
+      __syncthreads();
+      // walk up; paths that merge exchange values through the shared list
+#pragma unroll
+      for (int d = 0; d < kWalkLevels; ++d) {
+        if (d < nlev) {
+          const uint32_t node = leaf_node >> d;
+          if (d > 0) {
+            if (on) {
+              s_node[j] = node;
+              s_val[j] = make_float2(vs, vm);
+              __stcg(U.sum + node, vs);
+              __stcg(U.mn + node, vm);
+            }
+            __syncthreads();
+          }
+          if (on) {
+            float os = sib_s[d], om = sib_m[d];
+            const uint32_t want = node ^ 1u;
+            for (int i = j0; i < m && i < j0 + nthr; ++i)
+              if (s_node[i] == want) {
+                const float2 o = s_val[i];
+                os = o.x, om = o.y;
+                break;
+              }
+            vs = __fadd_rn(vs, os);
+            vm = om < vm ? om : vm;
+          }
+          __syncthreads();
+        }
+      }
+      if (on && nlev > 0) {
+        const uint32_t node = leaf_node >> nlev;
+        __stcg(U.sum + node, vs);
+        __stcg(U.mn + node, vm);
+      }
+      __syncthreads();  // this group's stores precede the next group's sibling loads (same CTA)
+    }
+  }
+#pragma unroll
+  for (int off = 16; off; off >>= 1) {
+    const float o = __shfl_xor_sync(0xffffffffu, local_max, off);
+    local_max = o > local_max ? o : local_max;
+  }
+  if ((tid & 31) == 0 && local_max > 0.0f)
+    atomicMax(reinterpret_cast<int *>(&U.state->max_priority), __float_as_int(local_max));
+
+  // ---- the last CTA to get here rebuilds the top levels ------------------------------------------
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(&U.state->done_ctas, 1u) == gridDim.x - 1 ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int i = tid; i < width; i += nthr) {
+    ssum[width + i] = __ldcg(U.sum + width + i);
+    smin[width + i] = __ldcg(U.mn + width + i);
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int level = split - 1; level >= 0; --level) {
+    const int w = 1 << level;
+    for (int i = tid; i < w; i += nthr) {
+      const int node = w + i;
+      ssum[node] = __fadd_rn(ssum[2 * node], ssum[2 * node + 1]);
+      const float ma = smin[2 * node], mb = smin[2 * node + 1];
+      smin[node] = ma < mb ? ma : mb;
+    }
+    __syncthreads();
+  }
+  for (int i = tid + 1; i < width; i += nthr) {
+    __stcg(U.sum + i, ssum[i]);
+    __stcg(U.mn + i, smin[i]);
+  }
+  if (tid == 0) U.state->done_ctas = 0u;  // ready for the next launch (stream-ordered)
+}
+
 // ---- push --------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32)
     prb_push_kernel(float *sum, float *mn, const PrbState *state, int64_t cap2, int32_t levels,
@@ -691,16 +857,16 @@ static int prb_sample_impl(PrbBuffer *b, int64_t n, float beta, const float *uni
   return MRL_OK;
 }
 
-// 0 = global-tag level-synchronous kernel (default: 18 us at n=256 on 2^20 leaves, measured),
-// 1 = register walk with shared-memory exchange (MRL_UPDATE_PATH=walk; bit-identical results, but
-//     measured at ~57 us: kept for the next round's latency work)
+// 0 = subtree-partitioned kernel over 128 CTAs (default),
+// 1 = one-CTA register walk with shared-memory hash exchange (MRL_UPDATE_PATH=walk; measured ~57 us),
+// 2 = one-CTA global-tag level-synchronous kernel (MRL_UPDATE_PATH=tags; measured 18 us at n=256)
 static int g_update_path = -1;
 
 static int prb_update_impl(PrbBuffer *b, const int64_t *indices, const float *priorities,
                            int64_t n, cudaStream_t st) {
   if (g_update_path < 0) {
     const char *e = getenv("MRL_UPDATE_PATH");
-    g_update_path = (e && e[0] == 'w') ? 1 : 0;
+    g_update_path = (e && e[0] == 'w') ? 1 : ((e && e[0] == 't') ? 2 : 0);
   }
   UpdateArgs U;
   U.sum = b->sum, U.mn = b->mn, U.tag = b->tag, U.state = b->state;
@@ -721,6 +887,9 @@ static int prb_update_impl(PrbBuffer *b, const int64_t *indices, const float *pr
       configured = true;
     }
     prb_update_walk_kernel<<<1, threads, smem, st>>>(U, bits);
+  } else if (g_update_path == 0 && b->levels - kTopLevels <= kWalkLevels && b->levels > kTopLevels &&
+             n < (1LL << 31)) {
+    prb_update_sub_kernel<<<kSubCtas, kSubThreads, 0, st>>>(U);
   } else {
     prb_update_kernel<<<1, 1024, 0, st>>>(U);
   }
