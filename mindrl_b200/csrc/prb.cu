@@ -84,6 +84,15 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// global-timer variant (ns) for marks taken by different CTAs
+__device__ __forceinline__ void dbg_mark_gt(long long *dbg, int slot) {
+  if (dbg && threadIdx.x == 0) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    dbg[slot] = t;
+  }
+}
+
 // ---- sample ------------------------------------------------------------------------------
 struct SampleArgs {
   const float *sum;
@@ -97,44 +106,42 @@ struct SampleArgs {
   float beta;
   uint64_t seed, ctr;
   uint32_t gather_mask;  // columns whose rows this kernel copies itself (narrow rows)
+  long long *dbg;
 };
 
 __global__ void __launch_bounds__(kSampleWarps * 32)
     prb_sample_kernel(const __grid_constant__ SampleArgs S, const __grid_constant__ ColTable tab) {
-  __shared__ float top[1 << kTopLevels];
-  const int top_levels = S.levels < kTopLevels ? S.levels : kTopLevels;  // levels fully in smem
-  // nodes [1, 2^(top_levels+1)) cover levels 0..top_levels, but only keep what fits: levels
-  // 0..top_levels-1 plus (when levels < kTopLevels) the leaf level is read from global.
-  const int staged = 1 << top_levels;  // nodes 1 .. staged-1  => levels 0 .. top_levels-1
-  for (int i = threadIdx.x; i < staged; i += blockDim.x) top[i] = i ? __ldcg(S.sum + i) : 0.0f;
-  __syncthreads();
-
+  dbg_mark(S.dbg, 0);
   const int lane = threadIdx.x & 31;
   const int64_t i = (int64_t)blockIdx.x * kSampleWarps + (threadIdx.x >> 5);
   if (i >= S.n) return;
   constexpr unsigned FULL = 0xffffffffu;
 
-  const float root_sum = staged > 1 ? top[1] : __ldcg(S.sum + 1);
-  const float seg = __fdiv_rn(root_sum, (float)S.n);
+  // everything that does not depend on the descent is requested first
+  const float root_sum = __ldcg(S.sum + 1);
+  float w_min = __ldcg(S.mn + 1);
   const float u = S.uniforms ? __ldg(S.uniforms + i) : mrl_uniform01(S.seed, S.ctr + (uint64_t)i);
-  float mass = __fmul_rn(__fadd_rn(u, (float)i), seg);
-
-  // levels whose children are staged: node at level l has children at level l+1 <= top_levels-1
-  int64_t node = 1;
-  int level = 0;
-  for (; level + 1 < top_levels; ++level) {
-    const float left = top[2 * node];
-    if (mass <= left) {
-      node = 2 * node;
-    } else {
-      mass = __fsub_rn(mass, left);
-      node = 2 * node + 1;
+  float w_sum = root_sum, w_size = (float)S.size;
+  if (S.gstats) {
+    w_sum = 0.0f, w_min = FLT_MAX, w_size = 0.0f;
+    for (int r = 0; r < S.world; ++r) {
+      w_sum = __fadd_rn(w_sum, __ldg(S.gstats + 4 * r));
+      const float m = __ldg(S.gstats + 4 * r + 1);
+      w_min = m < w_min ? m : w_min;
+      w_size = __fadd_rn(w_size, __ldg(S.gstats + 4 * r + 2));
     }
   }
-  // warp hops: h <= 5 levels per 128-byte load
-  float leaf_p = 0.0f;
-  int remaining = S.levels - level;
-  if (remaining == 0) leaf_p = __ldcg(S.sum + node);  // capacity 1
+  const float seg = __fdiv_rn(root_sum, (float)S.n);
+  float mass = __fmul_rn(__fadd_rn(u, (float)i), seg);
+  dbg_mark(S.dbg, 1);
+
+  // Warp hops from the root, h <= 5 levels per coalesced 128-byte load.  (Staging the top 11 levels
+  // in shared memory first was measured slower: 3.3 us for the staging alone against ~0.4 us per hop;
+  // the top lines are shared by all warps and stay in L1/L2 anyway.)
+  int64_t node = 1;
+  float leaf_p = root_sum;  // capacity 1: the root is the leaf
+  int remaining = S.levels;
+#pragma unroll 1
   while (remaining > 0) {
     const int h = remaining < 5 ? remaining : 5;
     const int64_t base = node << h;
@@ -158,34 +165,34 @@ __global__ void __launch_bounds__(kSampleWarps * 32)
     if (remaining == 0) leaf_p = __shfl_sync(FULL, p[0], off);
   }
   const int64_t leaf = node - S.cap2;
+  const int64_t slot = leaf < S.capacity ? leaf : S.capacity - 1;
+  dbg_mark(S.dbg, 3);
 
-  if (lane == 0) {
-    float w_sum = root_sum, w_min = __ldcg(S.mn + 1), w_size = (float)S.size;
-    if (S.gstats) {
-      w_sum = 0.0f, w_min = FLT_MAX, w_size = 0.0f;
-      for (int r = 0; r < S.world; ++r) {
-        w_sum = __fadd_rn(w_sum, __ldg(S.gstats + 4 * r));
-        const float m = __ldg(S.gstats + 4 * r + 1);
-        w_min = m < w_min ? m : w_min;
-        w_size = __fadd_rn(w_size, __ldg(S.gstats + 4 * r + 2));
-      }
-    }
-    const float max_w = mrl_is_weight(w_min, w_sum, w_size, S.beta);
-    S.indices[i] = leaf;
-    S.weights[i] = __fdiv_rn(mrl_is_weight(leaf_p, w_sum, w_size, S.beta), max_w);
+  // start pulling the row in while the weights are computed
+  if (S.gather_mask && lane < tab.ncols && ((S.gather_mask >> lane) & 1u)) {
+    const uint8_t *src = tab.col[lane] + slot * tab.row_bytes[lane];
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(src));
   }
+  // lanes 0 and 1 evaluate the two powers side by side: (p/sum*size)^-beta and (min/sum*size)^-beta
+  {
+    const float x = lane == 0 ? leaf_p : w_min;
+    float r = 0.0f;
+    if (lane < 2) r = mrl_is_weight(x, w_sum, w_size, S.beta);
+    const float max_w = __shfl_sync(FULL, r, 1);
+    if (lane == 0) {
+      S.indices[i] = leaf;
+      S.weights[i] = __fdiv_rn(r, max_w);
+    }
+  }
+  dbg_mark(S.dbg, 4);
   if (S.gather_mask) {
-    const int64_t slot = leaf < S.capacity ? leaf : S.capacity - 1;
     for (int c = 0; c < tab.ncols; ++c) {
       if (!((S.gather_mask >> c) & 1u)) continue;
       const int64_t rb = tab.row_bytes[c];
       const uint8_t *src = tab.col[c] + slot * rb;
       uint8_t *dst = tab.io[c] + i * rb;
       const int v = tab.vec[c];
-      if (v == 16) {
-        for (int64_t o = lane * 16; o < rb; o += 512)
-          *reinterpret_cast<uint4 *>(dst + o) = *reinterpret_cast<const uint4 *>(src + o);
-      } else if (v >= 4) {
+      if (v >= 4) {
         for (int64_t o = lane * 4; o < rb; o += 128)
           *reinterpret_cast<uint32_t *>(dst + o) = *reinterpret_cast<const uint32_t *>(src + o);
       } else {
@@ -193,8 +200,8 @@ __global__ void __launch_bounds__(kSampleWarps * 32)
       }
     }
   }
+  dbg_mark(S.dbg, 5);
 }
-
 // ---- update ------------------------------------------------------------------------------
 struct UpdateArgs {
   float *sum;
@@ -528,6 +535,7 @@ __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __gri
   const int per_cta = (width + (int)gridDim.x - 1) / (int)gridDim.x;  // level-`split` nodes per CTA
   const int own_lo = (int)blockIdx.x * per_cta, own_hi = own_lo + per_cta;
   float local_max = 0.0f;
+  if (blockIdx.x == 0) dbg_mark_gt(U.dbg, 8);
 
   // passes of blockDim indices: the local list always fits and batch order is kept across passes
   for (int64_t base = 0; base < U.n; base += kSubMaxLocal) {
@@ -541,6 +549,7 @@ __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __gri
     }
     __syncthreads();
     const int m = s_cnt;  // <= kSubMaxLocal == blockDim: one thread per local entry
+    if (blockIdx.x == 0 && base == 0) dbg_mark_gt(U.dbg, 9);
     {
       const int j0 = 0;
       const int j = tid;
@@ -585,6 +594,7 @@ __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __gri
       __syncthreads();
       if (on) s_val[j] = make_float2(vs, vm);  // every entry of a leaf now carries the winner's value
       __syncthreads();
+      if (blockIdx.x == 0 && base == 0) dbg_mark_gt(U.dbg, 10);
       // walk up; paths that merge exchange values through the shared list
 #pragma unroll
       for (int d = 0; d < kWalkLevels; ++d) {
@@ -630,18 +640,22 @@ __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __gri
   if ((tid & 31) == 0 && local_max > 0.0f)
     atomicMax(reinterpret_cast<int *>(&U.state->max_priority), __float_as_int(local_max));
 
+  if (blockIdx.x == 0) dbg_mark_gt(U.dbg, 11);
   // ---- the last CTA to get here rebuilds the top levels ------------------------------------------
   __threadfence();
   __syncthreads();
   if (tid == 0) s_last = atomicAdd(&U.state->done_ctas, 1u) == gridDim.x - 1 ? 1u : 0u;
   __syncthreads();
+  if (blockIdx.x == 0) dbg_mark_gt(U.dbg, 12);
   if (!s_last) return;
+  dbg_mark_gt(U.dbg, 13);
   __threadfence();
   for (int i = tid; i < width; i += nthr) {
     ssum[width + i] = __ldcg(U.sum + width + i);
     smin[width + i] = __ldcg(U.mn + width + i);
   }
   __syncthreads();
+  dbg_mark_gt(U.dbg, 14);
 #pragma unroll 1
   for (int level = split - 1; level >= 0; --level) {
     const int w = 1 << level;
@@ -653,10 +667,12 @@ __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __gri
     }
     __syncthreads();
   }
+  dbg_mark_gt(U.dbg, 15);
   for (int i = tid + 1; i < width; i += nthr) {
     __stcg(U.sum + i, ssum[i]);
     __stcg(U.mn + i, smin[i]);
   }
+  dbg_mark_gt(U.dbg, 16);
   if (tid == 0) U.state->done_ctas = 0u;  // ready for the next launch (stream-ordered)
 }
 
@@ -847,6 +863,7 @@ static int prb_sample_impl(PrbBuffer *b, int64_t n, float beta, const float *uni
       else wide |= 1u << c;
     }
   S.gather_mask = fused;
+  S.dbg = g_debug_timers;
   ColTable tab;
   fill_table(tab, b, out_cols);
   const int64_t blocks = (n + kSampleWarps - 1) / kSampleWarps;

@@ -30,12 +30,24 @@ for cold in (True, False):
     for i in range(12):
         if cold:
             flush.fill_(i); fsrc.sum()
-        _ffi.check(L.mrl_prb_sample(h.value, batch, 0.4, None, idx.data_ptr(), w.data_ptr(), tab, 0))
+        which = os.environ.get("WHICH", "update")
         dbg.zero_()
+        if which == "sample":
+            _ffi.set_option("debug_timers", dbg.data_ptr())
+        else:
+            _ffi.set_option("debug_timers", 0)
+        _ffi.check(L.mrl_prb_sample(h.value, batch, 0.4, None, idx.data_ptr(), w.data_ptr(), tab, 0))
+        if which == "sample":
+            torch.cuda.synchronize()
+            snap = dbg.cpu().numpy().copy()
+            _ffi.set_option("debug_timers", 0)
+        else:
+            dbg.zero_()
+            _ffi.set_option("debug_timers", dbg.data_ptr())
         _ffi.check(L.mrl_prb_update(h.value, idx.data_ptr(), prio[i % 8].data_ptr(), batch, 0))
         torch.cuda.synchronize()
-        acc.append(dbg.cpu().numpy().copy())
+        acc.append(snap if which == "sample" else dbg.cpu().numpy().copy())
     a = np.stack(acc[2:])
     slots = [k for k in range(32) if a[:, k].min() > 0]
     base = a[:, slots[0]]
-    print("cold" if cold else "warm", os.environ.get("MRL_UPDATE_PATH", "fast"), {k: round(float(np.median(a[:, k] - base)) / 1965, 2) for k in slots})
+    print("cold" if cold else "warm", os.environ.get("MRL_UPDATE_PATH", "fast"), {k: round(float(np.median(a[:, k] - base)) / (1965 if os.environ.get('WHICH','update')=='sample' else 1000), 2) for k in slots})
