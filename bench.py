@@ -117,6 +117,8 @@ class Ctx:
         self.local_rank = int(os.environ.get("LOCAL_RANK", 0))
         if self.world > 1:
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            # keep stdout to the one JSON line (NCCL prints its version banner there at VERSION/INFO)
+            os.environ["NCCL_DEBUG"] = os.environ.get("MRL_NCCL_DEBUG", "WARN")
         torch.cuda.set_device(self.local_rank)
         if self.world > 1:
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
@@ -239,9 +241,21 @@ def bench_per(ctx, name, rows, batch, steps, warmup, primary):
     sharded = ctx.world > 1
     stats = torch.empty(4, dtype=torch.float32, device="cuda")
     gstats = torch.empty((ctx.world, 4), dtype=torch.float32, device="cuda")
+    p2p = sharded and os.environ.get("MRL_SHARD_EXCHANGE", "p2p") == "p2p" and ctx.world <= 32
+    if p2p:  # peer mailboxes: the sample kernel exchanges the root statistics itself
+        buf = C.create_string_buffer(64)
+        ffi.check(L.mrl_prb_shard_init(h, ctx.rank, ctx.world, buf))
+        parts = [None] * ctx.world
+        ctx.dist.all_gather_object(parts, buf.raw)
+        allh = b"".join(parts)
+        ffi.check(L.mrl_prb_shard_connect(h, C.create_string_buffer(allh, len(allh))))
+        ctx.dist.barrier()
 
     def step(i):
-        if sharded:  # root stats all-gather (16 B/rank over NVLink), then local strata
+        if p2p:
+            ffi.check(L.mrl_prb_sample_sharded_p2p(h, batch, BETA, None, idx.data_ptr(), w.data_ptr(),
+                                                   out_tab, st))
+        elif sharded:  # root stats all-gather (16 B/rank over NVLink), then local strata
             ffi.check(L.mrl_prb_root_stats(h, stats.data_ptr(), st))
             ctx.dist.all_gather_into_tensor(gstats, stats)
             ffi.check(L.mrl_prb_sample_sharded(h, batch, BETA, None, gstats.data_ptr(), ctx.world,
@@ -301,10 +315,14 @@ def bench_per(ctx, name, rows, batch, steps, warmup, primary):
     h_prio_ptr = [h_prio[i].data_ptr() for i in range(pool)]
 
     def step_host(i):
-        if sharded:
+        if sharded and not p2p:
             ffi.check(L.mrl_prb_root_stats(h, stats.data_ptr(), st))
             ctx.dist.all_gather_into_tensor(gstats, stats)
-        ffi.check(L.mrl_prb_sample_host(h, batch, BETA, None, h_idx.data_ptr(), h_w.data_ptr(), h_tab, st))
+        if p2p:
+            ffi.check(L.mrl_prb_sample_sharded_p2p_host(h, batch, BETA, None, h_idx.data_ptr(),
+                                                        h_w.data_ptr(), h_tab, st))
+        else:
+            ffi.check(L.mrl_prb_sample_host(h, batch, BETA, None, h_idx.data_ptr(), h_w.data_ptr(), h_tab, st))
         ffi.check(L.mrl_prb_update_host(h, h_idx.data_ptr(), h_prio_ptr[i % pool], batch, st))
 
     esteps = max(10, min(steps, 200 if R > 512 else 1000))
@@ -449,7 +467,7 @@ def host_info():
     return info
 
 
-def run_reference(args):
+def run_reference(args, emit):
     """the reference arm: the reference's sequential CPU algorithm (oracle port) on the host"""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
@@ -486,10 +504,20 @@ def run_reference(args):
                          "host": host_info()},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
+    # the driver reads ONE JSON line from stdout: native libraries (NCCL's version banner) write to
+    # fd 1 too, so everything but that line is sent to stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(os.dup(2), "w")
+
+    def emit(obj):
+        real_stdout.write(json.dumps(obj) + "\n")
+        real_stdout.flush()
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)
@@ -500,7 +528,7 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, emit)
         return
 
     ctx = Ctx(args)
@@ -554,7 +582,8 @@ def main():
             "config": {"workload": primary["workload"], "per_rank": True,
                        "l2": "flushed before every timed iteration (256 MiB written, then 256 MiB read; untimed); "
                              "step time = sum of per-iteration CUDA-event durations on the launching stream",
-                       "sharding": ("replicated per-rank sub-buffers; root stats all-gathered (NCCL) per sample"
+                       "sharding": ("per-rank sub-buffers (1M rows each); root statistics exchanged inside the sample "
+                                    "kernel by peer stores over NVLink (MRL_SHARD_EXCHANGE=nccl: NCCL all-gather)"
                                     if ctx.world > 1 else "single GPU")},
             "clocks": ctx.clocks.summary(),
             "e2e": primary["e2e"], "gpu_launches": primary.get("gpu_launches"),
@@ -562,7 +591,7 @@ def main():
             "algorithmic_bytes_per_sample": primary.get("algorithmic_bytes_per_sample"),
             "also": also,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if ctx.world > 1:
         ctx.dist.barrier()
         ctx.dist.destroy_process_group()

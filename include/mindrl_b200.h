@@ -173,6 +173,23 @@ int mrl_prb_sample_sharded(int64_t handle, int64_t n, float beta, const float *u
                            const float *gstats, int32_t world, int64_t *indices, float *weights,
                            void *const *out_cols, void *stream);
 
+/* Fused exchange for ranks on ONE node (one process per GPU): the root statistics travel as peer
+ * stores over NVLink issued by the sample kernel itself, overlapped with the tree descent; no NCCL
+ * call, no extra launch.
+ *   1. mrl_prb_shard_init   allocates this rank's mailbox, returns its 64-byte CUDA IPC handle
+ *   2. ranks all-gather the handles (any transport) into world*64 bytes, rank order
+ *   3. mrl_prb_shard_connect maps the peers' mailboxes
+ *   4. mrl_prb_sample_sharded_p2p: same results as mrl_prb_root_stats + all-gather +
+ *      mrl_prb_sample_sharded.  Collective: every rank must call it the same number of times. */
+int mrl_prb_shard_init(int64_t handle, int32_t rank, int32_t world, void *ipc_handle_out);
+int mrl_prb_shard_connect(int64_t handle, const void *all_ipc_handles);
+int mrl_prb_sample_sharded_p2p(int64_t handle, int64_t n, float beta, const float *uniforms,
+                               int64_t *indices, float *weights, void *const *out_cols,
+                               void *stream);
+int mrl_prb_sample_sharded_p2p_host(int64_t handle, int64_t n, float beta, const float *uniforms,
+                                    int64_t *indices, float *weights, void *const *out_cols,
+                                    void *stream);
+
 /* ---- reverse scans ----------------------------------------------------- */
 /* DiscountedReturn (discounted_return.py:84-92):
  *   last <- reward[t] + ((1 - done[t]) * gamma) * last ; out[t] <- last,  t = T-1..0

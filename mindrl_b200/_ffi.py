@@ -64,6 +64,10 @@ SIGNATURES = {
     "mrl_prb_columns": [i64, vp],
     "mrl_prb_root_stats": [i64, vp, vp],
     "mrl_prb_sample_sharded": [i64, i64, f32, vp, vp, i32, vp, vp, vp, vp],
+    "mrl_prb_shard_init": [i64, i32, i32, vp],
+    "mrl_prb_shard_connect": [i64, vp],
+    "mrl_prb_sample_sharded_p2p": [i64, i64, f32, vp, vp, vp, vp, vp],
+    "mrl_prb_sample_sharded_p2p_host": [i64, i64, f32, vp, vp, vp, vp, vp],
     "mrl_discounted_return": [vp, vp, vp, vp, i64, i64, i64, f32, i32, i32, vp],
     "mrl_discounted_return_host": [vp, vp, vp, vp, i64, i64, i64, f32, i32, i32, vp],
     "mrl_gae": [vp, vp, vp, vp, vp, vp, vp, i64, i64, f32, f32, i32, i32, vp],

@@ -48,10 +48,12 @@ class PriorityReplayBuffer:
         return self._handle_arr
 
     # -- PriorityReplayBufferSample (:92-106) ------------------------------------------------
-    def sample(self, beta, uniforms=None, gstats=None):
+    def sample(self, beta, uniforms=None, gstats=None, p2p=False):
         """-> (indices int64[B], weights float32[B], *columns).
         uniforms: optional B draws in [0,1) to use instead of the buffer's own generator.
-        gstats: optional [world,4] device array of all ranks' root stats (sharded buffer)."""
+        gstats: optional [world,4] device array of all ranks' root stats (sharded buffer).
+        p2p: sharded buffer with connected peer mailboxes (shard_init/shard_connect): the root stats
+        are exchanged inside the sample kernel; collective over the ranks."""
         n = self._sample_size
         L = _ffi.lib()
         st = K.current_stream()
@@ -69,7 +71,10 @@ class PriorityReplayBuffer:
                     _ffi.check(L.mrl_memcpy_h2d(keep.data_ptr(), h.ctypes.data, h.nbytes, st))
                     _ffi.check(L.mrl_stream_sync(st))
                 u_ptr = keep.data_ptr()
-            if gstats is None:
+            if p2p:
+                _ffi.check(L.mrl_prb_sample_sharded_p2p(self._handle, n, float(beta), u_ptr,
+                                                        idx.data_ptr(), w.data_ptr(), tab, st))
+            elif gstats is None:
                 _ffi.check(L.mrl_prb_sample(self._handle, n, float(beta), u_ptr, idx.data_ptr(),
                                             w.data_ptr(), tab, st))
             else:
@@ -145,6 +150,17 @@ class PriorityReplayBuffer:
         _ffi.check(_ffi.lib().mrl_prb_tree_dump(self._handle, s.ctypes.data, m.ctypes.data,
                                                 K.current_stream()))
         return s, m
+
+    def shard_init(self, rank, world):
+        """allocates this rank's peer mailbox; returns its 64-byte CUDA IPC handle"""
+        buf = C.create_string_buffer(64)
+        _ffi.check(_ffi.lib().mrl_prb_shard_init(self._handle, int(rank), int(world), buf))
+        return buf.raw
+
+    def shard_connect(self, all_handles):
+        """maps every rank's mailbox; all_handles = world*64 bytes in rank order"""
+        buf = C.create_string_buffer(bytes(all_handles), len(all_handles))
+        _ffi.check(_ffi.lib().mrl_prb_shard_connect(self._handle, buf))
 
     def root_stats(self):
         """device array {root_sum, root_min, size, max_priority} for the sharded exchange"""

@@ -43,7 +43,10 @@ class ShardedPriorityReplayBuffer:
     """`local` is this rank's buffer: mindrl_b200.core.PriorityReplayBuffer on a GPU box.  It
     must provide root_stats(), sample(beta, uniforms=, gstats=), update_priorities(), insert()."""
 
-    def __init__(self, local, local_capacity, group=None):
+    def __init__(self, local, local_capacity, group=None, exchange="auto"):
+        """exchange: 'p2p' = peer-memory mailboxes written by the sample kernel itself (ranks on one
+        node), 'nccl' = all-gather of the 16-byte root statistics, 'auto' = p2p when the local buffer
+        supports it."""
         if dist is None or not dist.is_initialized():
             raise RuntimeError("torch.distributed must be initialised (one process per GPU)")
         self.local = local
@@ -51,6 +54,15 @@ class ShardedPriorityReplayBuffer:
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
+        self.p2p = False
+        if exchange in ("auto", "p2p") and hasattr(local, "shard_init") and self.world <= 32:
+            mine = local.shard_init(self.rank, self.world)
+            parts = [None] * self.world
+            dist.all_gather_object(parts, mine, group=group)
+            local.shard_connect(b"".join(parts))
+            self.p2p = True
+        elif exchange == "p2p":
+            raise RuntimeError("peer-memory exchange is not available for this buffer")
 
     def insert(self, *transition):
         return self.local.insert(*transition)
@@ -66,8 +78,10 @@ class ShardedPriorityReplayBuffer:
         return torch.stack(parts, 0).contiguous()
 
     def sample(self, beta, uniforms=None):
-        g = self.global_stats()
-        out = self.local.sample(beta, uniforms=uniforms, gstats=g)
+        if self.p2p:
+            out = self.local.sample(beta, uniforms=uniforms, p2p=True)
+        else:
+            out = self.local.sample(beta, uniforms=uniforms, gstats=self.global_stats())
         idx = to_global(out[0], self.rank, self.local_capacity)
         return (idx,) + tuple(out[1:])
 

@@ -39,6 +39,18 @@ struct PrbState {
   float pad[2];
 };
 
+// peer-memory mailbox of the sharded buffer: every rank owns [2][world][4] flag-in-payload words
+// {value bits, epoch}; ranks write their root statistics straight into every peer's mailbox (NVLink
+// peer stores issued by the sample kernel itself) and poll their own copy
+constexpr int kMaxWorld = 32;
+struct ShardLink {
+  int rank = -1, world = 0;
+  uint2 *mailbox = nullptr;     // this rank's mailbox (cudaMalloc, exported through CUDA IPC)
+  uint2 *peer[kMaxWorld] = {};  // mapped mailboxes of all ranks (peer[rank] == mailbox)
+  uint2 **peer_dev = nullptr;   // the same table in device memory
+  uint32_t epoch = 0;           // sharded sample calls so far (identical on every rank)
+};
+
 struct PrbBuffer {
   int64_t capacity = 0, cap2 = 1;
   int32_t levels = 0;  // log2(cap2)
@@ -53,6 +65,7 @@ struct PrbBuffer {
   uint64_t seed = 0, ctr = 0, epoch = 0;
   bool small_rows = true;  // gather fused into the sample kernel
   Staging stage;
+  ShardLink link;
 };
 
 static Registry<PrbBuffer> g_prb;
@@ -107,6 +120,10 @@ struct SampleArgs {
   uint64_t seed, ctr;
   uint32_t gather_mask;  // columns whose rows this kernel copies itself (narrow rows)
   long long *dbg;
+  uint2 *const *peers;  // sharded, peer-memory exchange: mailboxes of all ranks (else NULL)
+  const uint2 *mailbox;
+  int32_t rank;
+  uint32_t epoch;
 };
 
 __global__ void __launch_bounds__(kSampleWarps * 32)
@@ -120,6 +137,17 @@ __global__ void __launch_bounds__(kSampleWarps * 32)
   // everything that does not depend on the descent is requested first
   const float root_sum = __ldcg(S.sum + 1);
   float w_min = __ldcg(S.mn + 1);
+  if (S.peers && blockIdx.x == 0 && threadIdx.x < S.world) {
+    // Fused exchange, part 1: this rank's root statistics go straight into every rank's mailbox
+    // (peer stores over NVLink).  The words are self-validating {value, epoch}: no fence, no flag.
+    uint2 *dst = S.peers[threadIdx.x] + ((size_t)(S.epoch & 1u) * S.world + S.rank) * 4;
+    const float vals[3] = {root_sum, w_min, (float)S.size};
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+      asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1,%2};" ::"l"(dst + q),
+                   "r"(__float_as_uint(vals[q])), "r"(S.epoch)
+                   : "memory");
+  }
   const float u = S.uniforms ? __ldg(S.uniforms + i) : mrl_uniform01(S.seed, S.ctr + (uint64_t)i);
   float w_sum = root_sum, w_size = (float)S.size;
   if (S.gstats) {
@@ -172,6 +200,28 @@ __global__ void __launch_bounds__(kSampleWarps * 32)
   if (S.gather_mask && lane < tab.ncols && ((S.gather_mask >> lane) & 1u)) {
     const uint8_t *src = tab.col[lane] + slot * tab.row_bytes[lane];
     asm volatile("prefetch.global.L1 [%0];" ::"l"(src));
+  }
+  if (S.peers) {
+    // Fused exchange, part 2: by now the descent has hidden the NVLink latency; lane r polls rank r's
+    // words in the local mailbox, then the totals are formed in rank order (as the oracle does).
+    float ps = 0.0f, pm = FLT_MAX, pz = 0.0f;
+    if (lane < S.world) {
+      const uint2 *src = S.mailbox + ((size_t)(S.epoch & 1u) * S.world + lane) * 4;
+      uint2 a, b, c;
+      do {
+        asm volatile("ld.relaxed.sys.global.v2.u32 {%0,%1}, [%2];" : "=r"(a.x), "=r"(a.y) : "l"(src) : "memory");
+        asm volatile("ld.relaxed.sys.global.v2.u32 {%0,%1}, [%2];" : "=r"(b.x), "=r"(b.y) : "l"(src + 1) : "memory");
+        asm volatile("ld.relaxed.sys.global.v2.u32 {%0,%1}, [%2];" : "=r"(c.x), "=r"(c.y) : "l"(src + 2) : "memory");
+      } while (a.y != S.epoch || b.y != S.epoch || c.y != S.epoch);
+      ps = __uint_as_float(a.x), pm = __uint_as_float(b.x), pz = __uint_as_float(c.x);
+    }
+    w_sum = 0.0f, w_min = FLT_MAX, w_size = 0.0f;
+    for (int r = 0; r < S.world; ++r) {
+      w_sum = __fadd_rn(w_sum, __shfl_sync(FULL, ps, r));
+      const float m = __shfl_sync(FULL, pm, r);
+      w_min = m < w_min ? m : w_min;
+      w_size = __fadd_rn(w_size, __shfl_sync(FULL, pz, r));
+    }
   }
   // lanes 0 and 1 evaluate the two powers side by side: (p/sum*size)^-beta and (min/sum*size)^-beta
   {
@@ -848,8 +898,16 @@ static int prb_push_batch_impl(PrbBuffer *b, int64_t nrows, void *const *src, cu
 
 static int prb_sample_impl(PrbBuffer *b, int64_t n, float beta, const float *uniforms,
                            const float *gstats, int32_t world, int64_t *indices, float *weights,
-                           void *const *out_cols, cudaStream_t st) {
+                           void *const *out_cols, cudaStream_t st, bool p2p = false) {
   SampleArgs S;
+  S.peers = nullptr, S.mailbox = nullptr, S.rank = 0, S.epoch = 0;
+  if (p2p) {
+    S.peers = b->link.peer_dev;
+    S.mailbox = b->link.mailbox;
+    S.rank = b->link.rank;
+    S.epoch = ++b->link.epoch;
+    world = b->link.world;
+  }
   S.sum = b->sum, S.mn = b->mn, S.uniforms = uniforms, S.gstats = gstats;
   S.indices = indices, S.weights = weights;
   S.n = n, S.cap2 = b->cap2, S.capacity = b->capacity, S.size = b->size;
@@ -925,7 +983,17 @@ using namespace mrl;
     return MRL_ERR_HANDLE;                                                 \
   }
 
+static void link_free(PrbBuffer *b) {
+  ShardLink &k = b->link;
+  for (int r = 0; r < k.world; ++r)
+    if (k.peer[r] && r != k.rank) cudaIpcCloseMemHandle(k.peer[r]);
+  if (k.peer_dev) cudaFree(k.peer_dev);
+  if (k.mailbox) cudaFree(k.mailbox);
+  k = ShardLink();
+}
+
 static void prb_free(PrbBuffer *b) {
+  link_free(b);
   for (int c = 0; c < b->ncols; ++c)
     if (b->cols[c]) cudaFree(b->cols[c]);
   if (b->sum) cudaFree(b->sum);
@@ -1063,11 +1131,9 @@ extern "C" int mrl_prb_sample_sharded(int64_t handle, int64_t n, float beta, con
                          as_stream(stream));
 }
 
-extern "C" int mrl_prb_sample_host(int64_t handle, int64_t n, float beta, const float *uniforms,
-                                   int64_t *indices, float *weights, void *const *out_cols,
-                                   void *stream) {
-  PRB_GET(b, handle);
-  MRL_REQUIRE(n >= 1 && indices && weights, "mrl_prb_sample_host: need n >= 1, indices and weights");
+static int prb_sample_host_impl(PrbBuffer *b, int64_t n, float beta, const float *uniforms,
+                                int64_t *indices, float *weights, void *const *out_cols,
+                                void *stream, bool p2p) {
   cudaStream_t st = as_stream(stream);
   // device arena: [indices | weights | uniforms | col0 | col1 ...]
   size_t off[MRL_MAX_COLS + 4];
@@ -1088,7 +1154,7 @@ extern "C" int mrl_prb_sample_host(int64_t handle, int64_t n, float beta, const 
   void *out_dev[MRL_MAX_COLS];
   for (int c = 0; c < b->ncols; ++c) out_dev[c] = d + off[c];
   rc = prb_sample_impl(b, n, beta, uniforms ? (const float *)(d + o_u) : nullptr, nullptr, 0,
-                       (int64_t *)(d + o_idx), (float *)(d + o_w), out_cols ? out_dev : nullptr, st);
+                       (int64_t *)(d + o_idx), (float *)(d + o_w), out_cols ? out_dev : nullptr, st, p2p);
   if (rc) return rc;
   if (total <= (1u << 16)) {
     MRL_CUDA(cudaMemcpyAsync(b->stage.host, d, total, cudaMemcpyDeviceToHost, st));
@@ -1109,6 +1175,23 @@ extern "C" int mrl_prb_sample_host(int64_t handle, int64_t n, float beta, const 
     memcpy(weights, b->stage.host + o_w, (size_t)n * 4);
   }
   return MRL_OK;
+}
+
+extern "C" int mrl_prb_sample_host(int64_t handle, int64_t n, float beta, const float *uniforms,
+                                   int64_t *indices, float *weights, void *const *out_cols,
+                                   void *stream) {
+  PRB_GET(b, handle);
+  MRL_REQUIRE(n >= 1 && indices && weights, "mrl_prb_sample_host: need n >= 1, indices and weights");
+  return prb_sample_host_impl(b, n, beta, uniforms, indices, weights, out_cols, stream, false);
+}
+
+extern "C" int mrl_prb_sample_sharded_p2p_host(int64_t handle, int64_t n, float beta,
+                                               const float *uniforms, int64_t *indices,
+                                               float *weights, void *const *out_cols, void *stream) {
+  PRB_GET(b, handle);
+  MRL_REQUIRE(n >= 1 && indices && weights, "mrl_prb_sample_sharded_p2p_host: need n >= 1, indices and weights");
+  MRL_REQUIRE(b->link.peer_dev, "mrl_prb_sample_sharded_p2p_host: mailboxes are not connected");
+  return prb_sample_host_impl(b, n, beta, uniforms, indices, weights, out_cols, stream, true);
 }
 
 extern "C" int mrl_prb_update(int64_t handle, const int64_t *indices, const float *priorities,
@@ -1180,4 +1263,53 @@ extern "C" int mrl_prb_root_stats(int64_t handle, float *stats4, void *stream) {
   prb_stats_kernel<<<1, 1, 0, as_stream(stream)>>>(b->sum, b->mn, b->state, (float)b->size, stats4);
   MRL_LAUNCHED();
   return MRL_OK;
+}
+
+extern "C" int mrl_prb_shard_init(int64_t handle, int32_t rank, int32_t world, void *ipc_handle_out) {
+  PRB_GET(b, handle);
+  MRL_REQUIRE(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world && ipc_handle_out,
+              "mrl_prb_shard_init: need 0 <= rank < world <= %d", kMaxWorld);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes in the ABI");
+  link_free(b);
+  ShardLink &k = b->link;
+  k.rank = rank, k.world = world;
+  const size_t bytes = sizeof(uint2) * 2 * (size_t)world * 4;
+  MRL_CUDA(cudaMalloc((void **)&k.mailbox, bytes));
+  MRL_CUDA(cudaMemset(k.mailbox, 0, bytes));  // epoch 0 never matches a call (epochs start at 1)
+  MRL_CUDA(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  MRL_CUDA(cudaIpcGetMemHandle(&h, k.mailbox));
+  memcpy(ipc_handle_out, &h, sizeof(h));
+  return MRL_OK;
+}
+
+extern "C" int mrl_prb_shard_connect(int64_t handle, const void *all_ipc_handles) {
+  PRB_GET(b, handle);
+  ShardLink &k = b->link;
+  MRL_REQUIRE(k.world >= 1 && k.mailbox && all_ipc_handles, "mrl_prb_shard_connect: call mrl_prb_shard_init first");
+  for (int r = 0; r < k.world; ++r) {
+    if (r == k.rank) {
+      k.peer[r] = k.mailbox;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char *)all_ipc_handles + 64 * (size_t)r, sizeof(h));
+    void *p = nullptr;
+    MRL_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    k.peer[r] = (uint2 *)p;
+  }
+  MRL_CUDA(cudaMalloc((void **)&k.peer_dev, sizeof(uint2 *) * kMaxWorld));
+  MRL_CUDA(cudaMemcpy(k.peer_dev, k.peer, sizeof(uint2 *) * kMaxWorld, cudaMemcpyHostToDevice));
+  k.epoch = 0;
+  return MRL_OK;
+}
+
+extern "C" int mrl_prb_sample_sharded_p2p(int64_t handle, int64_t n, float beta, const float *uniforms,
+                                          int64_t *indices, float *weights, void *const *out_cols,
+                                          void *stream) {
+  PRB_GET(b, handle);
+  MRL_REQUIRE(n >= 1 && indices && weights, "mrl_prb_sample_sharded_p2p: need n >= 1, indices and weights");
+  MRL_REQUIRE(b->link.peer_dev, "mrl_prb_sample_sharded_p2p: mailboxes are not connected");
+  return prb_sample_impl(b, n, beta, uniforms, nullptr, 0, indices, weights, out_cols,
+                         as_stream(stream), true);
 }
