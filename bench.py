@@ -283,16 +283,19 @@ def bench_per(ctx, name, rows, batch, steps, warmup, primary):
         "prb_sample_kernel(descent+weights)": {"ms": t_sample / ksteps, "bytes": (4 * L_1M + 16) * batch},
         "prb_update_kernel": {"ms": t_update / ksteps, "bytes": (24 * L_1M + 20) * batch},
     }
-    if R > 512:  # wide rows: the gather is its own kernel; time it through a uniform-buffer view
+    if R > 512:  # wide columns are gathered by their own kernel: time it through a uniform-buffer view
+        wide = [c for c, r in enumerate(rows) if r > 512]
         uh = C.c_int64(-1)
-        rb = np.asarray(rows, dtype=np.int64)
-        ffi.check(L.mrl_urb_create(cap, len(rows), rb.ctypes.data, cols, 0, C.byref(uh)))
+        rb = np.asarray([rows[c] for c in wide], dtype=np.int64)
+        wcols = ffi.ptr_table([cols[c] for c in wide])
+        ffi.check(L.mrl_urb_create(cap, len(wide), rb.ctypes.data, wcols, 0, C.byref(uh)))
+        wide_tab = ffi.ptr_table([outs[c].data_ptr() for c in wide])
 
         def only_gather(i):
-            ffi.check(L.mrl_urb_gather(uh.value, idx.data_ptr(), batch, out_tab, st))
+            ffi.check(L.mrl_urb_gather(uh.value, idx.data_ptr(), batch, wide_tab, st))
 
         t_gather, _ = ctx.timed(only_gather, ksteps, 3)
-        kern["gather_bulk_kernel(+small columns)"] = {"ms": t_gather / ksteps, "bytes": 2 * R * batch}
+        kern["gather_bulk_kernel"] = {"ms": t_gather / ksteps, "bytes": 2 * sum(rows[c] for c in wide) * batch}
         ffi.check(L.mrl_urb_destroy(uh.value))
     else:
         kern["prb_sample_kernel(descent+weights)"]["bytes"] += 0

@@ -569,39 +569,129 @@ __global__ void __launch_bounds__(kWalkThreads)
 constexpr int kSubCtas = 128;
 constexpr int kSubThreads = 512;
 constexpr int kSubMaxLocal = kSubThreads;  // indices scanned per pass = most entries a CTA can keep
+constexpr int kSubDenseAt = 128;            // a share larger than this is rebuilt subtree by subtree
 
 __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __grid_constant__ UpdateArgs U) {
   __shared__ float ssum[2 << kTopLevels];
   __shared__ float smin[2 << kTopLevels];
-  __shared__ int s_k[kSubMaxLocal];        // batch position of each local entry
-  __shared__ uint32_t s_node[kSubMaxLocal];
-  __shared__ float2 s_val[kSubMaxLocal];
+  __shared__ int s_raw[4 * kSubMaxLocal];  // sparse: entry lists; dense: per-leaf winner table
   __shared__ int s_cnt;
+  __shared__ unsigned int s_dirty;  // bit j: owned subtree blockIdx.x + j*gridDim.x has an entry
   __shared__ unsigned int s_last;
+  int *s_k = s_raw;                                                 // batch position of each entry
+  uint32_t *s_node = reinterpret_cast<uint32_t *>(s_raw + kSubMaxLocal);
+  float2 *s_val = reinterpret_cast<float2 *>(s_raw + 2 * kSubMaxLocal);
   const int tid = threadIdx.x, nthr = blockDim.x;
+  constexpr int G = kSubCtas;  // == gridDim.x (a power of two: the ownership tests are masks)
   const int split = U.levels < kTopLevels ? U.levels : kTopLevels;
   const int nlev = U.levels - split;
   const int width = 1 << split;
-  const int per_cta = (width + (int)gridDim.x - 1) / (int)gridDim.x;  // level-`split` nodes per CTA
-  const int own_lo = (int)blockIdx.x * per_cta, own_hi = own_lo + per_cta;
-  float local_max = 0.0f;
   if (blockIdx.x == 0) dbg_mark_gt(U.dbg, 8);
 
-  // passes of blockDim indices: the local list always fits and batch order is kept across passes
-  for (int64_t base = 0; base < U.n; base += kSubMaxLocal) {
-    const int64_t end = base + kSubMaxLocal < U.n ? base + kSubMaxLocal : U.n;
-    if (tid == 0) s_cnt = 0;
-    __syncthreads();
-    for (int64_t k = base + tid; k < end; k += nthr) {
-      const int64_t leaf = __ldg(U.indices + k);
-      const int top = (int)(leaf >> nlev);  // index of the level-`split` ancestor within its level
-      if (top >= own_lo && top < own_hi) s_k[atomicAdd(&s_cnt, 1)] = (int)(k - base);
+  // max_priority takes every processed priority (also those a later duplicate overwrites): each CTA
+  // covers its slice of the batch
+  float local_max = 0.0f;
+  {
+    const int64_t per = (U.n + G - 1) / G;
+    const int64_t lo = per * blockIdx.x, hi = lo + per < U.n ? lo + per : U.n;
+    for (int64_t k = lo + tid; k < hi; k += nthr) {
+      const float p = prb_pow_fn(__ldg(U.priorities + k), U.alpha);
+      local_max = p > local_max ? p : local_max;
     }
-    __syncthreads();
-    const int m = s_cnt;  // <= kSubMaxLocal == blockDim: one thread per local entry
-    if (blockIdx.x == 0 && base == 0) dbg_mark_gt(U.dbg, 9);
-    {
-      const int j0 = 0;
+  }
+
+  // this CTA owns the subtrees (level-`split` nodes) congruent to blockIdx.x mod gridDim.x: a
+  // contiguous run of leaves is spread over many CTAs
+  if (tid == 0) s_cnt = 0, s_dirty = 0u;
+  __syncthreads();
+  {
+    int mine = 0;
+    unsigned int dirty = 0u;
+    for (int64_t k = tid; k < U.n; k += nthr) {
+      const int top = (int)(__ldg(U.indices + k) >> nlev);
+      if (top % G == (int)blockIdx.x) {
+        ++mine;
+        dirty |= 1u << ((top / G) & 31);
+      }
+    }
+    if (mine) {
+      atomicAdd(&s_cnt, mine);
+      atomicOr(&s_dirty, dirty);
+    }
+  }
+  __syncthreads();
+  const int total_mine = s_cnt;
+  const unsigned int dirty_mask = s_dirty;
+  __syncthreads();
+  if (blockIdx.x == 0) dbg_mark_gt(U.dbg, 9);
+
+  const int S = 1 << nlev;  // leaves per subtree
+  const bool dense = total_mine > kSubDenseAt && 2 * S <= (2 << kTopLevels) && S <= 4 * kSubMaxLocal &&
+                     (width + G - 1) / G <= 32;
+  if (dense) {
+    // ---- dense share: rebuild every dirty subtree completely in shared memory -------------------
+    // (coalesced loads of all its leaves instead of scattered sibling loads; cost independent of how
+    // many of its leaves the batch touches)
+    int *win = s_raw;  // per leaf of the subtree: highest batch position + 1
+    for (int jsub = 0; jsub * G + (int)blockIdx.x < width; ++jsub) {
+      if (!((dirty_mask >> (jsub & 31)) & 1u)) continue;
+      const int sub = jsub * G + (int)blockIdx.x;
+      const int64_t leaf0 = (int64_t)sub << nlev;
+      for (int i = tid; i < S; i += nthr) win[i] = 0;
+      __syncthreads();
+      for (int64_t k = tid; k < U.n; k += nthr) {
+        const int64_t leaf = __ldg(U.indices + k);
+        if ((leaf >> nlev) == sub) atomicMax(&win[leaf - leaf0], (int)k + 1);
+      }
+      __syncthreads();
+      for (int i = tid; i < S; i += nthr) {
+        const int wk = win[i];
+        float vs, vm;
+        if (wk) {
+          vs = vm = prb_pow_fn(__ldg(U.priorities + (wk - 1)), U.alpha);
+          __stcg(U.sum + U.cap2 + leaf0 + i, vs);
+          __stcg(U.mn + U.cap2 + leaf0 + i, vm);
+        } else {
+          vs = __ldcg(U.sum + U.cap2 + leaf0 + i);
+          vm = __ldcg(U.mn + U.cap2 + leaf0 + i);
+        }
+        ssum[S + i] = vs;
+        smin[S + i] = vm;
+      }
+      __syncthreads();
+#pragma unroll 1
+      for (int level = nlev - 1; level >= 0; --level) {
+        const int w = 1 << level;
+        for (int i = tid; i < w; i += nthr) {
+          const int node = w + i;
+          ssum[node] = __fadd_rn(ssum[2 * node], ssum[2 * node + 1]);
+          const float ma = smin[2 * node], mb = smin[2 * node + 1];
+          smin[node] = ma < mb ? ma : mb;
+        }
+        __syncthreads();
+      }
+      for (int jn = tid + 1; jn < S; jn += nthr) {  // local heap node -> global heap node
+        const int l = 31 - __clz(jn);
+        const int64_t g = ((int64_t)(width + sub) << l) + (jn - (1 << l));
+        __stcg(U.sum + g, ssum[jn]);
+        __stcg(U.mn + g, smin[jn]);
+      }
+      __syncthreads();
+    }
+  } else if (total_mine > 0) {
+    // ---- sparse share: one thread per entry walks its path in registers ---------------------------
+    // single pass when the share fits the list, else passes of blockDim indices (batch order kept)
+    const int64_t span = total_mine <= kSubMaxLocal ? U.n : kSubMaxLocal;
+    for (int64_t base = 0; base < U.n; base += span) {
+      const int64_t end = base + span < U.n ? base + span : U.n;
+      if (tid == 0) s_cnt = 0;
+      __syncthreads();
+      for (int64_t k = base + tid; k < end; k += nthr) {
+        const int top = (int)(__ldg(U.indices + k) >> nlev);
+        if (top % G == (int)blockIdx.x) s_k[atomicAdd(&s_cnt, 1)] = (int)(k - base);
+      }
+      __syncthreads();
+      const int m = s_cnt;  // <= kSubMaxLocal == blockDim: one thread per local entry
       const int j = tid;
       const bool on = j < m;
       const int64_t k = on ? base + s_k[j] : 0;
@@ -620,9 +710,8 @@ __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __gri
           }
         }
         p = prb_pow_fn(__ldg(U.priorities + k), U.alpha);
-        local_max = p > local_max ? p : local_max;
       }
-      // leaf level: among local entries of the same leaf the highest batch position provides the value
+      // leaf level: among entries of the same leaf the highest batch position provides the value
       if (on) {
         s_node[j] = leaf_node;
         s_val[j] = make_float2(p, p);
@@ -632,7 +721,7 @@ __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __gri
       if (on) {
         int best = s_k[j];
         int best_i = j;
-        for (int i = j0; i < m && i < j0 + nthr; ++i)
+        for (int i = 0; i < m; ++i)
           if (s_node[i] == leaf_node && s_k[i] > best) best = s_k[i], best_i = i;
         const float2 w = s_val[best_i];
         vs = w.x, vm = w.y;
@@ -662,7 +751,7 @@ __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __gri
           if (on) {
             float os = sib_s[d], om = sib_m[d];
             const uint32_t want = node ^ 1u;
-            for (int i = j0; i < m && i < j0 + nthr; ++i)
+            for (int i = 0; i < m; ++i)
               if (s_node[i] == want) {
                 const float2 o = s_val[i];
                 os = o.x, om = o.y;
@@ -679,7 +768,7 @@ __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __gri
         __stcg(U.sum + node, vs);
         __stcg(U.mn + node, vm);
       }
-      __syncthreads();  // this group's stores precede the next group's sibling loads (same CTA)
+      __syncthreads();  // this pass's stores precede the next pass's sibling loads (same CTA)
     }
   }
 #pragma unroll

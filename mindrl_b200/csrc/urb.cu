@@ -68,6 +68,28 @@ __global__ void __launch_bounds__(256)
   if (j < n) slots[j] = mrl_uniform_below(seed, ctr + (uint64_t)j, count);
 }
 
+// BufferSample for narrow rows in ONE launch: warp j draws its slot and copies the row of every column
+__global__ void __launch_bounds__(256)
+    urb_sample_fused_kernel(const __grid_constant__ ColTable tab, int64_t *slots_out, int64_t n,
+                            uint64_t seed, uint64_t ctr, int64_t count) {
+  const int lane = threadIdx.x & 31;
+  const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (j >= n) return;
+  const int64_t slot = mrl_uniform_below(seed, ctr + (uint64_t)j, count);
+  if (slots_out && lane == 0) slots_out[j] = slot;
+  for (int c = 0; c < tab.ncols; ++c) {
+    const int64_t rb = tab.row_bytes[c];
+    const uint8_t *src = tab.col[c] + slot * rb;
+    uint8_t *dst = tab.io[c] + j * rb;
+    if (tab.vec[c] >= 4) {
+      for (int64_t o = lane * 4; o < rb; o += 128)
+        *reinterpret_cast<uint32_t *>(dst + o) = *reinterpret_cast<const uint32_t *>(src + o);
+    } else {
+      for (int64_t o = lane; o < rb; o += 32) dst[o] = src[o];
+    }
+  }
+}
+
 static int urb_append_impl(UrbBuffer *b, int64_t nrows, void *const *src, cudaStream_t st) {
   const int64_t cap = b->capacity;
   int64_t pos;
@@ -119,6 +141,17 @@ static int urb_sample_impl(UrbBuffer *b, int64_t n, int64_t *slots_out, void *co
   if ((b->head > 0 && n > b->capacity) || (b->head == 0 && n > b->count)) {
     set_error("The batch size %lld is larger than total buffer size %d", (long long)n, b->count);
     return MRL_ERR_STATE;
+  }
+  ColTable ftab;
+  fill_table(ftab, b->ncols, b->cols, b->row_bytes, out);
+  bool narrow = true;
+  for (int c = 0; c < b->ncols; ++c) narrow = narrow && b->row_bytes[c] <= 512;
+  if (narrow) {
+    urb_sample_fused_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(ftab, slots_out, n, b->seed,
+                                                                          b->ctr, b->count);
+    MRL_LAUNCHED();
+    b->ctr += (uint64_t)n;
+    return MRL_OK;
   }
   int64_t *slots = slots_out;
   if (!slots) {
