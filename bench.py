@@ -43,6 +43,15 @@ C3_ROWS = [28224, 4, 4, 1, 28224]        # R = 56457 (obs, action, reward, done,
 L_1M = 20
 
 
+def ncu_traffic(key):
+    """per-launch DRAM bytes of a kernel from the committed ncu capture (profiles/r1_traffic.json)"""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        return t[key]["dram_traffic_bytes"]
+    except Exception:
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -301,8 +310,11 @@ def bench_per(ctx, name, rows, batch, steps, warmup, primary):
         kern["prb_sample_kernel(descent+weights)"]["bytes"] += 0
     dom = max(kern, key=lambda k: kern[k]["ms"])
     ach = kern[dom]["bytes"] / (kern[dom]["ms"] * 1e-3) / 1e9
+    tkey = ("c3:" if R > 512 else "c2:") + {"prb_sample_kernel(descent+weights)": "prb_sample_kernel",
+                                             "prb_update_kernel": "prb_update_sub_kernel",
+                                             "gather_bulk_kernel": "gather_bulk_kernel<4>"}.get(dom, dom)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm, "unit": "GB/s",
-                "frac": ach / hbm, "traffic": None, "peak_source": peak_src,
+                "frac": ach / hbm, "traffic": ncu_traffic(tkey), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": kern[dom]["bytes"],
                 "kernel_ms": {k: v["ms"] for k, v in kern.items()},
                 "note": ("tree kernels are dependent-load latency bound (L2/HBM round trips), "
@@ -389,8 +401,9 @@ def bench_gae(ctx, steps, warmup):
     run("discounted_return_time_major", dr_tm, 9, 4 * B)
     run("discounted_return_batch_major", dr_bm, 9, 4 * B)
     main = out["gae_time_major[T,B]"]
-    roofline = {"bound": "hbm", "kernel": "scan_tm_chunked_kernel<GAE>", "achieved": main["GBps"],
-                "peak": hbm, "unit": "GB/s", "frac": main["frac"], "traffic": None,
+    roofline = {"bound": "hbm", "kernel": "scan_tm_wtile_kernel<GAE>", "achieved": main["GBps"],
+                "peak": hbm, "unit": "GB/s", "frac": main["frac"],
+                "traffic": ncu_traffic("c4:scan_tm_wtile_kernel<1, 1>"),
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": 17 * n + 4 * B}
     # e2e: host arrays in, host arrays out
     hr, hv = pinned(ctx, (T, B), torch.float32), pinned(ctx, (T + 1, B), torch.float32)
@@ -406,6 +419,9 @@ def bench_gae(ctx, steps, warmup):
     e_ms = ctx.timed_host(gae_host, esteps, 2)
     e2e = {"value": n * esteps / (e_ms * 1e-3), "unit": "elements/s", "h2d_bytes_per_step": 9 * n + 4 * B,
            "d2h_bytes_per_step": 8 * n, "steps": esteps, "ms_per_step": e_ms / esteps}
+    bm = out["gae_batch_major[B,T]"]
+    roofline["batch_major_kernel"] = {"kernel": "scan_bm_warp_kernel<GAE>", "achieved": bm["GBps"], "frac": bm["frac"],
+                                      "traffic": ncu_traffic("c4:scan_bm_warp_kernel<1, 1, 0, 4>")}
     return {"workload": "C4 GAE 4096 envs x 2048 steps fp32 gamma=0.99 lambda=0.95 done~Bernoulli(1/200)",
             "metric": "gae_elements_per_s", "value": main["elems_per_s"], "unit": "elements/s",
             "ms_per_step": main["ms"], "steps": steps, "roofline": roofline, "e2e": e2e,
@@ -592,6 +608,7 @@ def main():
             "e2e": primary["e2e"], "gpu_launches": primary.get("gpu_launches"),
             "roofline": primary["roofline"], "cpu_baseline": primary.get("cpu_baseline"),
             "algorithmic_bytes_per_sample": primary.get("algorithmic_bytes_per_sample"),
+            "variants": primary.get("variants"),
             "also": also,
         }
         emit(line)
