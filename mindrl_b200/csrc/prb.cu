@@ -583,41 +583,30 @@ __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __gri
   float2 *s_val = reinterpret_cast<float2 *>(s_raw + 2 * kSubMaxLocal);
   const int tid = threadIdx.x, nthr = blockDim.x;
   constexpr int G = kSubCtas;  // == gridDim.x (a power of two: the ownership tests are masks)
+  // max_priority takes every processed priority (also those a later duplicate overwrites); every
+  // entry is owned by exactly one CTA, which evaluates p**alpha for it anyway
+  float local_max = 0.0f;
   const int split = U.levels < kTopLevels ? U.levels : kTopLevels;
   const int nlev = U.levels - split;
   const int width = 1 << split;
   if (blockIdx.x == 0) dbg_mark_gt(U.dbg, 8);
-
-  // max_priority takes every processed priority (also those a later duplicate overwrites): each CTA
-  // covers its slice of the batch
-  float local_max = 0.0f;
-  {
-    const int64_t per = (U.n + G - 1) / G;
-    const int64_t lo = per * blockIdx.x, hi = lo + per < U.n ? lo + per : U.n;
-    for (int64_t k = lo + tid; k < hi; k += nthr) {
-      const float p = prb_pow_fn(__ldg(U.priorities + k), U.alpha);
-      local_max = p > local_max ? p : local_max;
-    }
-  }
 
   // this CTA owns the subtrees (level-`split` nodes) congruent to blockIdx.x mod gridDim.x: a
   // contiguous run of leaves is spread over many CTAs
   if (tid == 0) s_cnt = 0, s_dirty = 0u;
   __syncthreads();
   {
-    int mine = 0;
+    // one scan: count this CTA's share, note its dirty subtrees, and optimistically build the entry list
     unsigned int dirty = 0u;
     for (int64_t k = tid; k < U.n; k += nthr) {
       const int top = (int)(__ldg(U.indices + k) >> nlev);
-      if (top % G == (int)blockIdx.x) {
-        ++mine;
+      if ((top & (G - 1)) == (int)blockIdx.x) {
         dirty |= 1u << ((top / G) & 31);
+        const int pos = atomicAdd(&s_cnt, 1);
+        if (pos < kSubMaxLocal) s_k[pos] = (int)k;
       }
     }
-    if (mine) {
-      atomicAdd(&s_cnt, mine);
-      atomicOr(&s_dirty, dirty);
-    }
+    if (dirty) atomicOr(&s_dirty, dirty);
   }
   __syncthreads();
   const int total_mine = s_cnt;
@@ -641,7 +630,11 @@ __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __gri
       __syncthreads();
       for (int64_t k = tid; k < U.n; k += nthr) {
         const int64_t leaf = __ldg(U.indices + k);
-        if ((leaf >> nlev) == sub) atomicMax(&win[leaf - leaf0], (int)k + 1);
+        if ((leaf >> nlev) == sub) {
+          atomicMax(&win[leaf - leaf0], (int)k + 1);
+          const float p = prb_pow_fn(__ldg(U.priorities + k), U.alpha);
+          local_max = p > local_max ? p : local_max;
+        }
       }
       __syncthreads();
       for (int i = tid; i < S; i += nthr) {
@@ -681,16 +674,19 @@ __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __gri
   } else if (total_mine > 0) {
     // ---- sparse share: one thread per entry walks its path in registers ---------------------------
     // single pass when the share fits the list, else passes of blockDim indices (batch order kept)
-    const int64_t span = total_mine <= kSubMaxLocal ? U.n : kSubMaxLocal;
+    const bool one_pass = total_mine <= kSubMaxLocal;  // the list built by the scan above is complete
+    const int64_t span = one_pass ? U.n : kSubMaxLocal;
     for (int64_t base = 0; base < U.n; base += span) {
       const int64_t end = base + span < U.n ? base + span : U.n;
-      if (tid == 0) s_cnt = 0;
-      __syncthreads();
-      for (int64_t k = base + tid; k < end; k += nthr) {
-        const int top = (int)(__ldg(U.indices + k) >> nlev);
-        if (top % G == (int)blockIdx.x) s_k[atomicAdd(&s_cnt, 1)] = (int)(k - base);
+      if (!one_pass) {
+        if (tid == 0) s_cnt = 0;
+        __syncthreads();
+        for (int64_t k = base + tid; k < end; k += nthr) {
+          const int top = (int)(__ldg(U.indices + k) >> nlev);
+          if ((top & (G - 1)) == (int)blockIdx.x) s_k[atomicAdd(&s_cnt, 1)] = (int)(k - base);
+        }
+        __syncthreads();
       }
-      __syncthreads();
       const int m = s_cnt;  // <= kSubMaxLocal == blockDim: one thread per local entry
       const int j = tid;
       const bool on = j < m;
@@ -710,6 +706,7 @@ __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __gri
           }
         }
         p = prb_pow_fn(__ldg(U.priorities + k), U.alpha);
+        local_max = p > local_max ? p : local_max;
       }
       // leaf level: among entries of the same leaf the highest batch position provides the value
       if (on) {
@@ -1241,19 +1238,26 @@ static int prb_sample_host_impl(PrbBuffer *b, int64_t n, float beta, const float
     MRL_CUDA(cudaMemcpyAsync(d + o_u, b->stage.host + o_u, (size_t)n * 4, cudaMemcpyHostToDevice, st));
   }
   void *out_dev[MRL_MAX_COLS];
+  if (total <= (1u << 16)) {
+    // small result: the kernel writes straight into the pinned staging buffer (it is mapped into the
+    // device address space), so there is no device-to-host copy to launch -- only the stream wait
+    uint8_t *hz = b->stage.host;
+    for (int c = 0; c < b->ncols; ++c) out_dev[c] = hz + off[c];
+    rc = prb_sample_impl(b, n, beta, uniforms ? (const float *)(d + o_u) : nullptr, nullptr, 0,
+                         (int64_t *)(hz + o_idx), (float *)(hz + o_w), out_cols ? out_dev : nullptr, st, p2p);
+    if (rc) return rc;
+    MRL_CUDA(cudaStreamSynchronize(st));
+    memcpy(indices, hz + o_idx, (size_t)n * 8);
+    memcpy(weights, hz + o_w, (size_t)n * 4);
+    if (out_cols)
+      for (int c = 0; c < b->ncols; ++c) memcpy(out_cols[c], hz + off[c], (size_t)n * b->row_bytes[c]);
+    return MRL_OK;
+  }
   for (int c = 0; c < b->ncols; ++c) out_dev[c] = d + off[c];
   rc = prb_sample_impl(b, n, beta, uniforms ? (const float *)(d + o_u) : nullptr, nullptr, 0,
                        (int64_t *)(d + o_idx), (float *)(d + o_w), out_cols ? out_dev : nullptr, st, p2p);
   if (rc) return rc;
-  if (total <= (1u << 16)) {
-    MRL_CUDA(cudaMemcpyAsync(b->stage.host, d, total, cudaMemcpyDeviceToHost, st));
-    MRL_CUDA(cudaStreamSynchronize(st));
-    memcpy(indices, b->stage.host + o_idx, (size_t)n * 8);
-    memcpy(weights, b->stage.host + o_w, (size_t)n * 4);
-    if (out_cols)
-      for (int c = 0; c < b->ncols; ++c)
-        memcpy(out_cols[c], b->stage.host + off[c], (size_t)n * b->row_bytes[c]);
-  } else {
+  {
     MRL_CUDA(cudaMemcpyAsync(b->stage.host, d, o_u, cudaMemcpyDeviceToHost, st));
     if (out_cols)
       for (int c = 0; c < b->ncols; ++c)

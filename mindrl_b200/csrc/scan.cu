@@ -8,10 +8,11 @@
 //   scan_seq_kernel         thread per column, t = T-1..0, 8 rows of loads in flight per thread.
 //                           Same operation order as the reference loop => bit-identical to the
 //                           oracle.  Coalesced for time-major data.
-//   scan_tm_chunked_kernel  time-major: CTA = 32 columns x W time-chunks.  Pass 1 reduces each chunk
-//                           to an affine map, the maps are combined through shared memory, pass 2
-//                           replays the chunk from its carry (second read hits L2).  Gives T-parallel
-//                           work when B alone cannot fill 148 SMs (4096 envs = 128 warps).
+//   scan_tm_wtile_kernel    time-major, default: a warp owns 32 columns x 32 steps in registers; tiles
+//                           are handed out latest-chunk-first by a ticket; the carry comes from a
+//                           decoupled look-back over flag-in-payload words.  One read, one write.
+//   scan_tm_tile4_kernel    time-major, 128-column CTA tiles (aligned inputs, next_value form of GAE)
+//   scan_tm_chunked_kernel  time-major two-pass fallback (unaligned next_value form)
 //   scan_bm_warp_kernel     batch-major: warp per environment, 128 steps per tile (float4 per lane),
 //                           per-lane composite + 5-step shuffle suffix scan of affine maps; a done flag
 //                           makes b = 0, which cuts the segment inside the same scan.
@@ -177,162 +178,10 @@ __global__ void __launch_bounds__(1024)
   scan_walk<OP, HD, 8>(A, col, lastv, t_lo, t_hi, x);
 }
 
-// ---- time-major single-pass tile scan -----------------------------------------------------
-// CTA = 32 columns x (TM_W warps x TM_S steps) = one [128 x 32] tile held in registers.  Tiles are
-// handed out by a ticket counter in dependency order (latest time chunk first).  Each CTA reduces
-// its tile to one affine map per column and publishes it (aggregate + release flag); a CTA then
-// folds the aggregates of all later time chunks of its column group into its carry -- aggregates do
-// not depend on any carry, so there is no serial chain across CTAs -- and replays its tile from
-// registers.  One global read and one global write per element.
-constexpr int TM_W = 8;    // warps per CTA
-constexpr int TM_S = 16;   // steps per thread
-constexpr int TM_TC = TM_W * TM_S;
-constexpr int TM_MAX_CHUNKS = 64;  // time chunks folded directly; longer T uses the chunked kernel
-
-struct TileWs {
-  unsigned int *ticket;  // 1 counter
-  unsigned int *flag;    // [n_chunks * n_groups]
-  float2 *agg;           // [n_chunks * n_groups][32]
-};
-
-template <int OP, bool HD>
-__global__ void __launch_bounds__(TM_W * 32)
-    scan_tm_tile_kernel(const __grid_constant__ ScanArgs A, TileWs ws, int n_chunks, int n_groups) {
-  __shared__ float sA[TM_W][32];
-  __shared__ float sB[TM_W][32];
-  __shared__ float s_ext[32];
-  __shared__ unsigned int s_ticket;
-  const int lane = threadIdx.x, w = threadIdx.y;
-  if (lane == 0 && w == 0) s_ticket = atomicAdd(ws.ticket, 1u);
-  __syncthreads();
-  const unsigned int ticket = s_ticket;
-  const int chunk = n_chunks - 1 - (int)(ticket / (unsigned)n_groups);  // latest chunk first
-  const int group = (int)(ticket % (unsigned)n_groups);
-  const int64_t col = (int64_t)group * 32 + lane;
-  const bool valid = col < A.N;
-  const int64_t colc = valid ? col : A.N - 1;  // clamped: loads stay legal, results unused
-  const int64_t t_base = (int64_t)chunk * TM_TC + (int64_t)w * TM_S;
-  const int64_t t_max = A.T - 1;
-  const float lastv = scan_lastv<OP>(A, colc);
-
-  float a[TM_S], b[TM_S], aux[TM_S];
-  if (OP == OP_GAE && !A.nv) {
-    // V[t+1] of step s is V[t] of step s+1: TM_S+1 loads instead of 2*TM_S
-    float vv[TM_S + 1], rr[TM_S], mm[TM_S];
-#pragma unroll
-    for (int s = 0; s <= TM_S; ++s) {
-      int64_t t = t_base + s;
-      t = t > t_max ? t_max : t;
-      vv[s] = __ldg(A.v + t * A.st + colc);
-    }
-#pragma unroll
-    for (int s = 0; s < TM_S; ++s) {
-      int64_t t = t_base + s;
-      t = t > t_max ? t_max : t;
-      rr[s] = __ldg(A.a + t * A.st + colc);
-      mm[s] = 1.0f;
-      if (HD) mm[s] = __fsub_rn(1.0f, __ldg(A.done + t * A.dst + colc) ? 1.0f : 0.0f);
-    }
-#pragma unroll
-    for (int s = 0; s < TM_S; ++s) {
-      const int64_t t = t_base + s;
-      const float vn = (t + 1 > t_max) ? lastv : vv[s + 1];
-      const float gvm = __fmul_rn(__fmul_rn(A.gamma, vn), mm[s]);
-      const bool in = valid && t <= t_max;
-      a[s] = in ? __fsub_rn(__fadd_rn(rr[s], gvm), vv[s]) : 0.0f;
-      b[s] = in ? __fmul_rn(A.gl, mm[s]) : 1.0f;
-      aux[s] = vv[s];
-    }
-  } else {
-#pragma unroll
-    for (int s = 0; s < TM_S; ++s) {
-      int64_t t = t_base + s;
-      t = t > t_max ? t_max : t;
-      scan_load<OP, HD>(A, t, colc, lastv, a[s], b[s], aux[s]);
-    }
-#pragma unroll
-    for (int s = 0; s < TM_S; ++s) {
-      const bool in = valid && (t_base + s) <= t_max;
-      a[s] = in ? a[s] : 0.0f;
-      b[s] = in ? b[s] : 1.0f;
-    }
-  }
-  float ca = 0.0f, cb = 1.0f;  // x[t_base] = ca + cb * x[t_base + TM_S]
-#pragma unroll
-  for (int s = TM_S - 1; s >= 0; --s) {
-    ca = scan_step(a[s], b[s], ca);
-    cb = __fmul_rn(b[s], cb);
-  }
-  sA[w][lane] = ca;
-  sB[w][lane] = cb;
-  __syncthreads();
-
-  const int tile = chunk * n_groups + group;
-  if (w == 0) {
-    // publish this tile's aggregate: x[tile start] = ta + tb * x[tile end]
-    float ta = 0.0f, tb = 1.0f;
-#pragma unroll
-    for (int j = TM_W - 1; j >= 0; --j) {
-      ta = scan_step(sA[j][lane], sB[j][lane], ta);
-      tb = __fmul_rn(sB[j][lane], tb);
-    }
-    if (chunk > 0) {
-      __stcg(&ws.agg[(size_t)tile * 32 + lane], make_float2(ta, tb));
-      __threadfence();
-      __syncwarp();
-      if (lane == 0) {
-        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ws.flag + tile), "r"(1u) : "memory");
-      }
-    }
-    // carry from all later chunks of this column group: the flags are polled lane-parallel and the
-    // aggregates fetched in independent batches, so the wait is one round trip, not one per chunk
-    const int n_later = n_chunks - 1 - chunk;
-    for (int j0 = 0; j0 < n_later; j0 += 32) {
-      const int j = j0 + lane;
-      if (j < n_later) {
-        const unsigned int *fp = ws.flag + (size_t)(chunk + 1 + j) * n_groups + group;
-        unsigned int f;
-        do {
-          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(fp) : "memory");
-        } while (f == 0u);
-      }
-    }
-    __syncwarp();
-    float x = valid ? scan_init<OP>(A, col) : 0.0f;
-    for (int c0 = n_chunks - 1; c0 > chunk; c0 -= 8) {
-      float2 g[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        int c = c0 - u;
-        const bool in = c > chunk;
-        c = in ? c : chunk + 1;
-        const float2 q = __ldcg(&ws.agg[((size_t)c * n_groups + group) * 32 + lane]);
-        g[u] = in ? q : make_float2(0.0f, 1.0f);
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) x = scan_step(g[u].x, g[u].y, x);
-    }
-    s_ext[lane] = x;
-  }
-  __syncthreads();
-  if (!valid) return;
-  float x = s_ext[lane];
-  for (int j = TM_W - 1; j > w; --j) x = scan_step(sA[j][lane], sB[j][lane], x);
-#pragma unroll
-  for (int s = TM_S - 1; s >= 0; --s) {
-    const int64_t t = t_base + s;
-    if (t <= t_max) {
-      x = scan_step(a[s], b[s], x);
-      scan_store<OP>(A, t, col, x, aux[s]);
-    }
-  }
-}
-
 // ---- time-major single-pass tile scan, 512-byte rows ---------------------------------------
-// Same scheme as scan_tm_tile_kernel, but a lane owns 4 adjacent columns (one 16-byte load per
-// array and step), so every warp-level access is a contiguous 512-byte piece of a time row instead
-// of 128 bytes: the 32-column variant leaves DRAM pages after 128 bytes and reaches only ~1/4 of
-// the bandwidth.  Tile = 128 columns x (T4_W warps x T4_S steps).  The carry comes from a decoupled
+// CTA = 128 columns x (T4_W warps x T4_S steps) held in registers; a lane owns 4 adjacent columns (one
+// 16-byte load per array and step).  Tiles are handed out by a ticket counter in dependency order
+// (latest time chunk first).  The carry comes from a decoupled
 // look-back: every tile publishes its aggregate (flag 1) and later its inclusive value at the tile
 // start (flag 2); a tile walks towards later chunks, composing aggregates until it meets an
 // inclusive value.
@@ -815,179 +664,6 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 3)
                               col, colc, valid);
 }
 
-// ---- time-major two-launch scan over L2-sized time ranges ----------------------------------
-// No spin-waits.  The trajectory is cut into ranges of RG chunks (a chunk = 32 columns x R2_S steps
-// owned by one warp).  For each range, last first:
-//   scan_tm_agg_kernel    every warp reduces its chunk to an affine map        (reads the inputs)
-//   scan_tm_apply_kernel  every warp re-reads its chunk (L2-resident: the range is sized for that),
-//                         folds the maps of the later chunks of the range, starts from the output
-//                         already written at the first step of the next range, and writes the results
-// so DRAM sees each input once and each output once.
-constexpr int R2_S = 16;
-
-template <int OP, bool HD>
-struct R2Tile {
-  float a[R2_S];
-  float v[R2_S + 1];
-  unsigned char db[R2_S];
-  unsigned int dmask, inmask;
-  float bgain, lastv;
-
-  __device__ __forceinline__ void load(const ScanArgs &A, int64_t t_base, int64_t colc, int64_t dcol,
-                                       bool valid, bool keep_l2) {
-    const int64_t t_max = A.T - 1;
-#pragma unroll
-    for (int s = 0; s < R2_S; ++s) {
-      int64_t t = t_base + s;
-      t = t > t_max ? t_max : t;
-      a[s] = keep_l2 ? __ldcg(A.a + t * A.N + colc) : __ldcs(A.a + t * A.N + colc);
-    }
-    if (OP != OP_DR) {
-#pragma unroll
-      for (int s = 0; s <= R2_S; ++s) {
-        int64_t t = t_base + s;
-        t = t > t_max ? t_max : t;
-        if (s < R2_S || OP == OP_GAE)
-          v[s] = keep_l2 ? __ldcg(A.v + t * A.N + colc) : __ldcs(A.v + t * A.N + colc);
-      }
-    }
-    if (HD) {
-#pragma unroll
-      for (int s = 0; s < R2_S; ++s) {
-        int64_t t = t_base + s;
-        t = t > t_max ? t_max : t;
-        db[s] = keep_l2 ? __ldcg(A.done + t * A.B + dcol) : __ldcs(A.done + t * A.B + dcol);
-      }
-    }
-    lastv = 0.0f;
-    if (OP == OP_GAE && A.last) lastv = __ldcg(A.last + colc);
-  }
-  // call after a block barrier: ptxas otherwise sinks the first consumer between the loads, and the
-  // in-order warp then waits a full memory latency before it issues the remaining loads
-  // `z` is a zero the compiler cannot see (read from shared memory after the barrier): xor-ing it
-  // into every loaded register ties all consumers to a point behind the barrier, i.e. behind the
-  // issue of the last load
-  __device__ __forceinline__ void prepare(const ScanArgs &A, int64_t t_base, bool valid, int z) {
-    const int64_t t_max = A.T - 1;
-#pragma unroll
-    for (int s = 0; s < R2_S; ++s) a[s] = __int_as_float(__float_as_int(a[s]) ^ z);
-    if (OP != OP_DR) {
-#pragma unroll
-      for (int s = 0; s <= R2_S; ++s)
-        if (s < R2_S || OP == OP_GAE) v[s] = __int_as_float(__float_as_int(v[s]) ^ z);
-    }
-    dmask = 0u;
-    if (HD) {
-#pragma unroll
-      for (int s = 0; s < R2_S; ++s) dmask |= (((int)db[s] ^ z) ? 1u : 0u) << s;
-    }
-    inmask = 0u;
-#pragma unroll
-    for (int s = 0; s < R2_S; ++s) inmask |= ((valid && t_base + s <= t_max) ? 1u : 0u) << s;
-    bgain = OP == OP_GAE ? A.gl : A.gamma;
-    if (OP == OP_GAE) {
-#pragma unroll
-      for (int s = 0; s < R2_S; ++s) {
-        const float m = ((dmask >> s) & 1u) ? 0.0f : 1.0f;
-        const float vn = (t_base + s + 1 > t_max) ? lastv : v[s + 1];
-        a[s] = __fsub_rn(__fadd_rn(a[s], __fmul_rn(__fmul_rn(A.gamma, vn), m)), v[s]);
-      }
-    }
-  }
-  __device__ __forceinline__ float acoef(int s) const { return ((inmask >> s) & 1u) ? a[s] : 0.0f; }
-  __device__ __forceinline__ float bcoef(int s) const {
-    if (!((inmask >> s) & 1u)) return 1.0f;
-    if (OP == OP_AFFINE) return v[s];
-    return ((dmask >> s) & 1u) ? __fmul_rn(0.0f, bgain) : __fmul_rn(1.0f, bgain);
-  }
-  __device__ __forceinline__ void composite(float &ca, float &cb) const {
-    ca = 0.0f, cb = 1.0f;
-#pragma unroll
-    for (int s = R2_S - 1; s >= 0; --s) {
-      const float bs = bcoef(s);
-      ca = scan_step(acoef(s), bs, ca);
-      cb = __fmul_rn(bs, cb);
-    }
-  }
-};
-
-// grid = (column groups of 32*warps, chunks of the range); warp -> 32 columns
-template <int OP, bool HD>
-__global__ void __launch_bounds__(256)
-    scan_tm_agg_kernel(const __grid_constant__ ScanArgs A, float2 *__restrict__ agg, int chunk0) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int chunk = chunk0 + blockIdx.y;
-  const int64_t col = ((int64_t)blockIdx.x * 8 + w) * 32 + lane;
-  const bool valid = col < A.N;
-  const int64_t colc = valid ? col : A.N - 1;
-  const int64_t dcol = A.E == 1 ? colc : colc / A.E;
-  __shared__ int s_zero;
-  if (threadIdx.x == 0) s_zero = 0;
-  R2Tile<OP, HD> tile;
-  tile.load(A, (int64_t)chunk * R2_S, colc, dcol, valid, true);
-  __syncthreads();
-  const int z = *reinterpret_cast<volatile int *>(&s_zero);
-  tile.prepare(A, (int64_t)chunk * R2_S, valid, z);
-  float ca, cb;
-  tile.composite(ca, cb);
-  if (valid) agg[(size_t)chunk * A.N + col] = make_float2(ca, cb);
-}
-
-template <int OP, bool HD>
-__global__ void __launch_bounds__(256)
-    scan_tm_apply_kernel(const __grid_constant__ ScanArgs A, const float2 *__restrict__ agg,
-                         int chunk0, int chunk_end, int n_chunks) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int chunk = chunk_end - 1 - (int)blockIdx.y;  // latest chunk first: its inputs were read last
-  const int64_t col = ((int64_t)blockIdx.x * 8 + w) * 32 + lane;
-  const bool valid = col < A.N;
-  const int64_t colc = valid ? col : A.N - 1;
-  const int64_t dcol = A.E == 1 ? colc : colc / A.E;
-  const int64_t t_base = (int64_t)chunk * R2_S;
-  __shared__ int s_zero;
-  if (threadIdx.x == 0) s_zero = 0;
-  R2Tile<OP, HD> tile;
-  tile.load(A, t_base, colc, dcol, valid, false);
-  // carry at the end of the range: boundary value, or the output at the first step of the next range
-  float x;
-  if (chunk_end >= n_chunks) x = scan_init<OP>(A, colc);
-  else x = __ldcg(A.out + (int64_t)chunk_end * R2_S * A.N + colc);
-  // the maps of the later chunks of this range (at most 63), requested with the tile
-  constexpr int MAXG = 16;
-  float2 g[MAXG];
-  const int n_later = chunk_end - 1 - chunk;
-#pragma unroll
-  for (int u = 0; u < MAXG; ++u) {
-    int c = chunk_end - 1 - u;
-    c = c > chunk ? c : chunk + 1 <= chunk_end - 1 ? chunk + 1 : chunk;
-    g[u] = __ldcg(agg + (size_t)c * A.N + colc);
-  }
-  __syncthreads();
-  const int z = *reinterpret_cast<volatile int *>(&s_zero);
-  tile.prepare(A, t_base, valid, z);
-  x = __int_as_float(__float_as_int(x) ^ z);
-#pragma unroll
-  for (int u = 0; u < MAXG; ++u)
-    if (u < n_later)
-      x = scan_step(__int_as_float(__float_as_int(g[u].x) ^ z), __int_as_float(__float_as_int(g[u].y) ^ z), x);
-  for (int c = chunk_end - 1 - MAXG; c > chunk; --c) {  // ranges longer than MAXG chunks (rare)
-    const float2 q = __ldg(agg + (size_t)c * A.N + colc);
-    x = scan_step(q.x, q.y, x);
-  }
-  if (!valid) return;
-  const int64_t t_max = A.T - 1;
-#pragma unroll
-  for (int s = R2_S - 1; s >= 0; --s) {
-    const int64_t t = t_base + s;
-    if (t <= t_max) {
-      x = scan_step(tile.a[s], tile.bcoef(s), x);
-      const int64_t i = t * A.N + col;
-      A.out[i] = x;  // default caching: the first row of a range is read back as the next carry
-      if (OP == OP_GAE && A.ret) __stcs(A.ret + i, __fadd_rn(x, tile.v[s]));
-    }
-  }
-}
-
 // ---- batch-major warp scan ----------------------------------------------------------------
 // A tile is Q sub-tiles of 128 steps.  Every load instruction of a sub-tile is one fully coalesced
 // 512-byte warp access (lane l owns steps 4l..4l+3 of the sub-tile); all Q sub-tiles of the NEXT tile
@@ -1180,33 +856,11 @@ static int launch_scan_hd(ScanArgs A, int32_t layout, int32_t mode, cudaStream_t
     if (mode == MRL_SCAN_SEQUENTIAL) chunked = false;
     else if (mode == MRL_SCAN_PARALLEL) chunked = A.T >= 2;
     else chunked = A.T >= 64 && A.N < (int64_t)kNumSM * 1024;
-    const int64_t n_chunks = (A.T + TM_TC - 1) / TM_TC;
     const bool vec4 = A.E == 1 && A.N % 4 == 0 && aligned16(A.a) && aligned16(A.out) &&
                       (OP == OP_DR || aligned16(A.v)) && (!A.nv || aligned16(A.nv)) &&
                       (!A.ret || aligned16(A.ret)) && (!A.last || aligned16(A.last)) &&
                       (!A.done || (((uintptr_t)A.done) & 3) == 0);
-    if (chunked && g_tile_mode == 6 && !(OP == OP_GAE && A.nv)) {
-      // two launches per L2-sized time range, last range first
-      static const int64_t range_mb = getenv("MRL_TM_RANGE_MB") ? atoll(getenv("MRL_TM_RANGE_MB")) : 24;
-      const int64_t nch = (A.T + R2_S - 1) / R2_S;
-      const int64_t bytes_per_chunk = (int64_t)R2_S * A.N * (OP == OP_DR ? 5 : 9);
-      int64_t rg = (range_mb << 20) / (bytes_per_chunk > 0 ? bytes_per_chunk : 1);
-      if (rg < 1) rg = 1;
-      if (rg > 64) rg = 64;
-      uint8_t *wsp;
-      int rc = tile_workspace((size_t)nch * A.N * sizeof(float2), &wsp);
-      if (rc) return rc;
-      float2 *agg = reinterpret_cast<float2 *>(wsp);
-      const unsigned gx = (unsigned)((A.N + 255) / 256);
-      for (int64_t end = nch; end > 0; end -= rg) {
-        const int64_t begin = end - rg > 0 ? end - rg : 0;
-        dim3 grid(gx, (unsigned)(end - begin));
-        scan_tm_agg_kernel<OP, HD><<<grid, 256, 0, st>>>(A, agg, (int)begin);
-        g_launches.fetch_add(1);
-        scan_tm_apply_kernel<OP, HD><<<grid, 256, 0, st>>>(A, agg, (int)begin, (int)end, (int)nch);
-        if (end - rg > 0) g_launches.fetch_add(1);
-      }
-    } else if (chunked && (g_tile_mode == 5 || g_tile_mode == 0) && !(OP == OP_GAE && A.nv)) {
+    if (chunked && (g_tile_mode == 5 || g_tile_mode == 0) && !(OP == OP_GAE && A.nv)) {
       const int64_t nch = (A.T + WT_S - 1) / WT_S;
       const int64_t n_wgroups = (A.N + 31) / 32;
       const int64_t n_cgroups = (n_wgroups + WT_WARPS - 1) / WT_WARPS;
@@ -1256,20 +910,6 @@ static int launch_scan_hd(ScanArgs A, int32_t layout, int32_t mode, cudaStream_t
       ws.incl = reinterpret_cast<float *>(wsp + flag_bytes + agg_bytes);
       dim3 block(32, T4_W);
       scan_tm_tile4_kernel<OP, HD><<<(unsigned)tiles, block, 0, st>>>(A, ws, (int)n4, (int)n_groups);
-    } else if (chunked && g_tile_mode <= 1 && n_chunks <= TM_MAX_CHUNKS && g_tile_mode != 2) {
-      const int64_t n_groups = (A.N + 31) / 32;
-      const size_t tiles = (size_t)n_chunks * n_groups;
-      const size_t flag_bytes = (4 + tiles * 4 + 255) / 256 * 256;
-      uint8_t *wsp;
-      int rc = tile_workspace(flag_bytes + tiles * 32 * sizeof(float2), &wsp);
-      if (rc) return rc;
-      MRL_CUDA(cudaMemsetAsync(wsp, 0, flag_bytes, st));
-      TileWs ws;
-      ws.ticket = reinterpret_cast<unsigned int *>(wsp);
-      ws.flag = ws.ticket + 1;
-      ws.agg = reinterpret_cast<float2 *>(wsp + flag_bytes);
-      dim3 block(32, TM_W);
-      scan_tm_tile_kernel<OP, HD><<<(unsigned)tiles, block, 0, st>>>(A, ws, (int)n_chunks, (int)n_groups);
     } else if (chunked) {
       int W = 32;
       while (W > 1 && A.T / W < 8) W >>= 1;
@@ -1309,13 +949,12 @@ static int launch_scan(ScanArgs A, int32_t layout, int32_t mode, cudaStream_t st
     // default 0: 128-column tiles when aligned, else 32-column tiles; "t": 32-column tiles only;
     // "c": two-pass chunked kernel only
     // "4": 128-column CTA tiles (aligned inputs only)
-    // default / "w": warp-owned tiles with flag-in-payload look-back; "r": two launches per time range
+    // default / "w": warp-owned tiles with flag-in-payload look-back; "4": 128-column CTA tiles
+    // (aligned inputs; also serves the next_value form of GAE); "c": two-pass chunked kernel
     g_tile_mode = 0;
     if (e && e[0] == 'c') g_tile_mode = 2;
-    if (e && e[0] == 't') g_tile_mode = 1;
     if (e && e[0] == '4') g_tile_mode = 3;
     if (e && e[0] == 'w') g_tile_mode = 5;
-    if (e && e[0] == 'r') g_tile_mode = 6;
   }
   if (OP != OP_AFFINE && A.done) return launch_scan_hd<OP, true>(A, layout, mode, st);
   return launch_scan_hd<OP, false>(A, layout, mode, st);

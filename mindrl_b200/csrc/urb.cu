@@ -326,18 +326,24 @@ extern "C" int mrl_urb_sample_host(int64_t handle, int64_t n, int64_t *slots_out
   rc = b->stage.ensure(off[b->ncols + 1]);
   if (rc) return rc;
   void *out_dev[MRL_MAX_COLS];
+  const size_t total = off[b->ncols + 1];
+  if (total <= (1u << 16)) {
+    // small result: the kernels write straight into the pinned (device-mapped) staging buffer
+    uint8_t *hz = b->stage.host;
+    for (int c = 0; c < b->ncols; ++c) out_dev[c] = hz + off[c];
+    rc = urb_sample_impl(b, n, (int64_t *)(hz + off[b->ncols]), out_dev, st);
+    if (rc) return rc;
+    MRL_CUDA(cudaStreamSynchronize(st));
+    for (int c = 0; c < b->ncols; ++c)
+      memcpy(out_cols[c], hz + off[c], (size_t)n * b->row_bytes[c]);
+    if (slots_out) memcpy(slots_out, hz + off[b->ncols], (size_t)n * 8);
+    return MRL_OK;
+  }
   for (int c = 0; c < b->ncols; ++c) out_dev[c] = b->stage.dev + off[c];
   int64_t *slots_dev = (int64_t *)(b->stage.dev + off[b->ncols]);
   rc = urb_sample_impl(b, n, slots_dev, out_dev, st);
   if (rc) return rc;
-  const size_t total = off[b->ncols + 1];
-  if (total <= (1u << 16)) {  // one small D2H, then scatter on the host
-    MRL_CUDA(cudaMemcpyAsync(b->stage.host, b->stage.dev, total, cudaMemcpyDeviceToHost, st));
-    MRL_CUDA(cudaStreamSynchronize(st));
-    for (int c = 0; c < b->ncols; ++c)
-      memcpy(out_cols[c], b->stage.host + off[c], (size_t)n * b->row_bytes[c]);
-    if (slots_out) memcpy(slots_out, b->stage.host + off[b->ncols], (size_t)n * 8);
-  } else {
+  {
     for (int c = 0; c < b->ncols; ++c)
       MRL_CUDA(cudaMemcpyAsync(out_cols[c], b->stage.dev + off[c], (size_t)n * b->row_bytes[c],
                                cudaMemcpyDeviceToHost, st));
