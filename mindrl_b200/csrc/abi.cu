@@ -15,6 +15,17 @@ void set_error(const char *fmt, ...) {
   va_end(ap);
 }
 
+int stream_wait_spin(cudaStream_t st) {
+  static thread_local cudaEvent_t ev = nullptr;
+  if (!ev) MRL_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  MRL_CUDA(cudaEventRecord(ev, st));
+  cudaError_t e;
+  while ((e = cudaEventQuery(ev)) == cudaErrorNotReady) {
+  }
+  MRL_CUDA(e);
+  return MRL_OK;
+}
+
 }  // namespace mrl
 
 using namespace mrl;
@@ -76,7 +87,4 @@ extern "C" int mrl_memset(void *dst, int value, size_t bytes, void *stream) {
   if (bytes) MRL_CUDA(cudaMemsetAsync(dst, value, bytes, as_stream(stream)));
   return MRL_OK;
 }
-extern "C" int mrl_stream_sync(void *stream) {
-  MRL_CUDA(cudaStreamSynchronize(as_stream(stream)));
-  return MRL_OK;
-}
+extern "C" int mrl_stream_sync(void *stream) { return stream_wait_spin(as_stream(stream)); }

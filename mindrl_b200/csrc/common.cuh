@@ -104,6 +104,11 @@ struct Staging {
 };
 
 // gathers the columns selected by col_mask (bit c = column c)
+// waits for `st` by polling an event: the blocking cudaStreamSynchronize adds several microseconds of
+// wake-up latency, which is most of a small *_host call
+int stream_wait_spin(cudaStream_t st);
+
+// gathers the columns selected by col_mask (bit c = column c)
 int gather_rows(const ColTable &tab, const int64_t *slots, int64_t n, int64_t capacity,
                 cudaStream_t st, uint32_t col_mask = 0xffffffffu);
 int copy_segments(const ColTable &tab, int64_t dst_row, int64_t src_row, int64_t nrows,

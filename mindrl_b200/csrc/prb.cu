@@ -1246,7 +1246,8 @@ static int prb_sample_host_impl(PrbBuffer *b, int64_t n, float beta, const float
     rc = prb_sample_impl(b, n, beta, uniforms ? (const float *)(d + o_u) : nullptr, nullptr, 0,
                          (int64_t *)(hz + o_idx), (float *)(hz + o_w), out_cols ? out_dev : nullptr, st, p2p);
     if (rc) return rc;
-    MRL_CUDA(cudaStreamSynchronize(st));
+    rc = stream_wait_spin(st);
+    if (rc) return rc;
     memcpy(indices, hz + o_idx, (size_t)n * 8);
     memcpy(weights, hz + o_w, (size_t)n * 4);
     if (out_cols)

@@ -589,7 +589,7 @@ __device__ __forceinline__ void wtile_body(const ScanArgs &A, const WTileWs &ws,
 }
 
 template <int OP, bool HD>
-__global__ void __launch_bounds__(WT_WARPS * 32, 3)
+__global__ void __launch_bounds__(WT_WARPS * 32, OP == OP_GAE ? 3 : 4)
     scan_tm_wtile_kernel(const __grid_constant__ ScanArgs A, WTileWs ws, unsigned long long ticket_base,
                          unsigned int epoch, int n_chunks, int n_wgroups, int n_cgroups) {
   __shared__ unsigned int s_ticket;

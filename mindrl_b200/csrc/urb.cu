@@ -333,7 +333,8 @@ extern "C" int mrl_urb_sample_host(int64_t handle, int64_t n, int64_t *slots_out
     for (int c = 0; c < b->ncols; ++c) out_dev[c] = hz + off[c];
     rc = urb_sample_impl(b, n, (int64_t *)(hz + off[b->ncols]), out_dev, st);
     if (rc) return rc;
-    MRL_CUDA(cudaStreamSynchronize(st));
+    rc = stream_wait_spin(st);
+    if (rc) return rc;
     for (int c = 0; c < b->ncols; ++c)
       memcpy(out_cols[c], hz + off[c], (size_t)n * b->row_bytes[c]);
     if (slots_out) memcpy(slots_out, hz + off[b->ncols], (size_t)n * 8);

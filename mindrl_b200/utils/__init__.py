@@ -1,3 +1,4 @@
 from .discounted_return import DiscountedReturn, affine_scan, discounted_reward, gae
+from .vtrace import get_vs_and_advantages
 
-__all__ = ["DiscountedReturn", "discounted_reward", "gae", "affine_scan"]
+__all__ = ["DiscountedReturn", "discounted_reward", "gae", "affine_scan", "get_vs_and_advantages"]

@@ -141,7 +141,51 @@ def make_ppo():
     print("wrote", OUT_PPO, os.path.getsize(OUT_PPO), "bytes")
 
 
+VTRACE_REF = "/root/reference/mindspore_rl/algorithm/impala/vtrace.py"
+OUT_VTRACE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "vtrace_ref.npz")
+
+
+def make_vtrace():
+    """runs the reference's get_vs_and_advantages (vtrace.py:48-108) on the numpy stand-in"""
+    install_shim()
+    ms = sys.modules["mindspore"]
+    ops = sys.modules["mindspore.ops"]
+    w = lambda a: np.asarray(a).view(Tensor)  # noqa: E731
+    ops.exp = lambda x: w(np.exp(np.asarray(x, dtype=np.float32)))
+    ops.minimum = lambda a, b: w(np.minimum(np.asarray(a), np.asarray(b)))
+    ops.concat = lambda xs, axis=0: w(np.concatenate([np.asarray(x) for x in xs], axis=axis))
+    ops.expand_dims = lambda x, axis: w(np.expand_dims(np.asarray(x), axis))
+    ops.zeros_like = lambda x: w(np.zeros_like(np.asarray(x)))
+    ops.stack = lambda xs: w(np.stack([np.asarray(x) for x in xs]))
+    ops.flip = lambda x, dims: w(np.flip(np.asarray(x), axis=tuple(dims)))
+    ops.stop_gradient = lambda x: x
+    ops.transpose = lambda x, perm: w(np.transpose(np.asarray(x), perm))
+    ms.ops = ops
+    spec = importlib.util.spec_from_file_location("ref_vtrace", VTRACE_REF)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rng = np.random.default_rng(11)
+    cases = {}
+    for name, (T, B) in [("a", (5, 3)), ("b", (20, 16)), ("c", (100, 8)), ("d", (1, 4))]:
+        log_rhos = (rng.normal(size=(T, B)) * 0.5).astype(np.float32)
+        discounts = np.full((T, B), 0.99, np.float32)
+        rewards = rng.normal(size=(T, B)).astype(np.float32)
+        values = rng.normal(size=(T, B)).astype(np.float32)
+        boot = rng.normal(size=(B,)).astype(np.float32)
+        masks = (rng.random((T, B)) > 0.1).astype(np.float32)
+        vs, pg = mod.get_vs_and_advantages(Tensor(log_rhos), Tensor(discounts), Tensor(rewards), Tensor(values),
+                                           Tensor(boot), 1.0, 1.0, 1.0, Tensor(masks))
+        for k, v in dict(log_rhos=log_rhos, discounts=discounts, rewards=rewards, values=values, boot=boot,
+                         masks=masks, vs=np.asarray(vs).view(np.ndarray).astype(np.float32),
+                         pg=np.asarray(pg).view(np.ndarray).astype(np.float32)).items():
+            cases[f"{name}/{k}"] = v
+        assert np.asarray(vs).dtype == np.float32
+    np.savez_compressed(OUT_VTRACE, **cases)
+    print("wrote", OUT_VTRACE, os.path.getsize(OUT_VTRACE), "bytes")
+
+
 def main():
+    make_vtrace()
     make_ppo()
     DR = load_reference()
     rng = np.random.default_rng(20261019)

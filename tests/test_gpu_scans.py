@@ -177,6 +177,17 @@ def test_affine_scan_vtrace_form():
         exact(M.affine_scan(dev(a), dev(b), dev(xl), layout=layout, mode="sequential"), ref)
 
 
+def test_vtrace_golden(golden_dir):
+    """get_vs_and_advantages against vectors produced by the reference's own vtrace.py"""
+    g = np.load(os.path.join(golden_dir, "vtrace_ref.npz"))
+    for n in sorted({k.split("/")[0] for k in g.files}):
+        args = [dev(g[f"{n}/{k}"]) for k in ("log_rhos", "discounts", "rewards", "values", "boot")]
+        for mode in ("auto", "sequential"):
+            vs, pg = M.get_vs_and_advantages(*args, 1.0, 1.0, 1.0, dev(g[f"{n}/masks"]), mode=mode)
+            close(vs, g[f"{n}/vs"])   # exp() of the carrier differs from numpy's in the last ulp
+            close(pg, g[f"{n}/pg"])
+
+
 def test_full_size_c4_against_oracle_and_float64():
     """BASELINE config 4: 4096 envs x 2048 steps, gamma .99 lambda .95, random done flags"""
     rng = np.random.default_rng(4)

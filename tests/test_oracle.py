@@ -99,6 +99,19 @@ def test_affine_scan_is_vtrace_recurrence():
     assert np.allclose(out, ref, rtol=1e-6, atol=1e-6)
 
 
+def test_vtrace_golden_through_oracle_scan(golden_dir):
+    """vtrace.py:84-99 run by the reference's own code: the recurrence is the oracle's affine scan"""
+    g = np.load(os.path.join(golden_dir, "vtrace_ref.npz"))
+    for n in sorted({k.split("/")[0] for k in g.files}):
+        lr, disc, r, v, boot, m = (g[f"{n}/{k}"] for k in ("log_rhos", "discounts", "rewards", "values", "boot", "masks"))
+        rhos = np.minimum(np.exp(lr), np.float32(1.0))
+        cs = np.minimum(rhos, np.float32(1.0))
+        v1 = np.concatenate([v[1:], boot[None]], 0)
+        deltas = rhos * (r + disc * v1 - v)
+        acc = O.affine_scan(deltas, disc * cs * m, None, layout=0)
+        assert np.array_equal((acc + v).view(np.uint32), g[f"{n}/vs"].view(np.uint32)), n
+
+
 # ---- arithmetic --------------------------------------------------------------------------
 def test_detpow_equals_correctly_rounded_pow():
     rng = np.random.default_rng(3)
