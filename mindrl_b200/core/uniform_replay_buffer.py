@@ -121,6 +121,25 @@ class UniformReplayBuffer:
         """count >= capacity as a bool array of shape (1,) (:162-172)"""
         return np.asarray([self.count >= self._capacity])
 
+    # -- checkpointing (not in the reference, which never saves its buffers: SURVEY.md section 5) ---
+    def state_dict(self):
+        """host copy of the columns and the cursor pair"""
+        cols = []
+        for b in self.buffer:
+            cols.append(b.cpu().numpy() if K.is_torch(b) else b.numpy())
+        c, h = self._state()
+        return {"columns": cols, "count": c, "head": h}
+
+    def load_state_dict(self, state):
+        st = K.current_stream()
+        for b, src, dt in zip(self.buffer, state["columns"], self._spec.dtypes):
+            a = np.ascontiguousarray(src, dtype=dt)
+            if a.nbytes != K.nbytes_of(b):
+                raise ValueError("checkpoint column does not match this buffer")
+            _ffi.check(_ffi.lib().mrl_memcpy_h2d(b.data_ptr(), a.ctypes.data, a.nbytes, st))
+        _ffi.check(_ffi.lib().mrl_stream_sync(st))
+        _ffi.check(_ffi.lib().mrl_urb_set_state(self._handle, int(state["count"]), int(state["head"])))
+
     def destroy(self):
         if getattr(self, "_handle", -1) != -1:
             _ffi.lib().mrl_urb_destroy(self._handle)

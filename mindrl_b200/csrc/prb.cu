@@ -786,29 +786,78 @@ __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __gri
   if (!s_last) return;
   dbg_mark_gt(U.dbg, 13);
   __threadfence();
-  for (int i = tid; i < width; i += nthr) {
-    ssum[width + i] = __ldcg(U.sum + width + i);
-    smin[width + i] = __ldcg(U.mn + width + i);
-  }
-  __syncthreads();
-  dbg_mark_gt(U.dbg, 14);
-#pragma unroll 1
-  for (int level = split - 1; level >= 0; --level) {
-    const int w = 1 << level;
-    for (int i = tid; i < w; i += nthr) {
-      const int node = w + i;
-      ssum[node] = __fadd_rn(ssum[2 * node], ssum[2 * node + 1]);
-      const float ma = smin[2 * node], mb = smin[2 * node + 1];
-      smin[node] = ma < mb ? ma : mb;
+  if (width == 4 * kSubThreads && nthr == kSubThreads) {
+    // 2048 level-11 nodes, 4 per thread: two levels in registers, five by warp shuffles, the last
+    // four by one warp -- one block barrier instead of eleven, no shared-memory tree
+    const float4 a = __ldcg(reinterpret_cast<const float4 *>(U.sum + width) + tid);
+    const float4 m = __ldcg(reinterpret_cast<const float4 *>(U.mn + width) + tid);
+    dbg_mark_gt(U.dbg, 14);
+    const float s0 = __fadd_rn(a.x, a.y), s1 = __fadd_rn(a.z, a.w);
+    const float m0 = m.x < m.y ? m.x : m.y, m1 = m.z < m.w ? m.z : m.w;
+    __stcg(reinterpret_cast<float2 *>(U.sum + width / 2) + tid, make_float2(s0, s1));
+    __stcg(reinterpret_cast<float2 *>(U.mn + width / 2) + tid, make_float2(m0, m1));
+    float xs = __fadd_rn(s0, s1), xm = m0 < m1 ? m0 : m1;  // node width/4 + tid
+    int node = width / 4 + tid;
+    __stcg(U.sum + node, xs);
+    __stcg(U.mn + node, xm);
+    const int lane = tid & 31;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const float os = __shfl_xor_sync(0xffffffffu, xs, 1 << k);
+      const float om = __shfl_xor_sync(0xffffffffu, xm, 1 << k);
+      // left child is the lane with the lower index: keep fl(left + right)
+      xs = (lane >> k) & 1 ? __fadd_rn(os, xs) : __fadd_rn(xs, os);
+      xm = om < xm ? om : xm;
+      node >>= 1;
+      if ((lane & ((2 << k) - 1)) == 0) {
+        __stcg(U.sum + node, xs);
+        __stcg(U.mn + node, xm);
+      }
+    }
+    // warp roots = the 16 nodes of level 4
+    float *r_s = ssum, *r_m = smin;
+    if (lane == 0) r_s[tid >> 5] = xs, r_m[tid >> 5] = xm;
+    __syncthreads();
+    if (tid < 32) {
+      xs = tid < 16 ? r_s[tid] : 0.0f;
+      xm = tid < 16 ? r_m[tid] : FLT_MAX;
+      node = 16 + tid;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float os = __shfl_xor_sync(0xffffffffu, xs, 1 << k);
+        const float om = __shfl_xor_sync(0xffffffffu, xm, 1 << k);
+        xs = (tid >> k) & 1 ? __fadd_rn(os, xs) : __fadd_rn(xs, os);
+        xm = om < xm ? om : xm;
+        node >>= 1;
+        if (tid < 16 && (tid & ((2 << k) - 1)) == 0) {
+          __stcg(U.sum + node, xs);
+          __stcg(U.mn + node, xm);
+        }
+      }
+    }
+    dbg_mark_gt(U.dbg, 16);
+  } else {
+    for (int i = tid; i < width; i += nthr) {
+      ssum[width + i] = __ldcg(U.sum + width + i);
+      smin[width + i] = __ldcg(U.mn + width + i);
     }
     __syncthreads();
+#pragma unroll 1
+    for (int level = split - 1; level >= 0; --level) {
+      const int w = 1 << level;
+      for (int i = tid; i < w; i += nthr) {
+        const int nd = w + i;
+        ssum[nd] = __fadd_rn(ssum[2 * nd], ssum[2 * nd + 1]);
+        const float ma = smin[2 * nd], mb = smin[2 * nd + 1];
+        smin[nd] = ma < mb ? ma : mb;
+      }
+      __syncthreads();
+    }
+    for (int i = tid + 1; i < width; i += nthr) {
+      __stcg(U.sum + i, ssum[i]);
+      __stcg(U.mn + i, smin[i]);
+    }
   }
-  dbg_mark_gt(U.dbg, 15);
-  for (int i = tid + 1; i < width; i += nthr) {
-    __stcg(U.sum + i, ssum[i]);
-    __stcg(U.mn + i, smin[i]);
-  }
-  dbg_mark_gt(U.dbg, 16);
   if (tid == 0) U.state->done_ctas = 0u;  // ready for the next launch (stream-ordered)
 }
 

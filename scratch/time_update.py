@@ -3,7 +3,7 @@ import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mindrl_b200 import _ffi
 L = _ffi.lib()
-cap, batch = 1_000_000, 256
+cap, batch = 1_000_000, int(os.environ.get("BATCH", 256))
 rows = [16, 4, 4, 16]
 rb = np.asarray(rows, dtype=np.int64)
 h = C.c_int64(-1)

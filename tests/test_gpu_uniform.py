@@ -148,3 +148,30 @@ def test_launch_counter_moves():
     g.insert([dev(np.ones((5, 1), np.float32))])
     g.sample()
     assert _ffi.launch_count() >= before + 2
+
+
+def test_n_step_buffer_and_checkpoint():
+    """NStepBuffer (utils/n_step_buffer.py:54-103) over get_item, and state_dict round trip"""
+    shapes, types = [(4,), (1,)], [np.float32, np.int32]
+    nb = M.NStepBuffer(shapes, types, td_step=3, buffer_size=50)
+    check, _ = nb.get_data()
+    assert not check
+    for i in range(7):
+        nb.push([dev(np.full(4, i, np.float32)), dev(np.array([i], np.int32))])
+    check, cols = nb.get_data()
+    assert check
+    assert np.array_equal(cols[1].cpu().numpy()[:3, 0], [4, 5, 6])
+    assert np.array_equal(cols[0].cpu().numpy()[:3, 0], [4.0, 5.0, 6.0])
+    assert nb.clear() is True and nb.buffer.count == 0
+    g = M.UniformReplayBuffer(4, 20, shapes, types, seed=2)
+    rng = np.random.default_rng(3)
+    g.insert([dev(rng.normal(size=(27, 4)).astype(np.float32)), dev(np.arange(27, dtype=np.int32)[:, None])])
+    sd = g.state_dict()
+    h = M.UniformReplayBuffer(4, 20, shapes, types, seed=2)
+    h.load_state_dict(sd)
+    assert (h.count, h.head) == (g.count, g.head)
+    for a, b in zip(g.buffer, h.buffer):
+        assert torch.equal(a, b)
+    for i in (0, 5, -1):
+        for a, b in zip(g.get_item(i), h.get_item(i)):
+            assert torch.equal(a, b)
