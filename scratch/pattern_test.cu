@@ -28,6 +28,20 @@ __global__ void __launch_bounds__(256) row_copy(const float4* __restrict__ in, f
 #pragma unroll
   for (int s = 0; s < S; ++s) { v[s].x += 1.f; __stcs(out + (t_base + s) * N4 + col4, v[s]); }
 }
+// scalar variant: a warp owns 32 columns (one float per lane) x S rows, like scan_tm_wtile_kernel
+template <int S>
+__global__ void __launch_bounds__(128) wtile_copy(const float* __restrict__ in, float* __restrict__ out, int T, int N, int n_wgroups) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int tile = blockIdx.x;                       // CTA = 4 adjacent column groups of one chunk
+  int chunk = tile / (n_wgroups / 4), cg = tile % (n_wgroups / 4);
+  long col = ((long)cg * 4 + w) * 32 + lane;
+  long t_base = (long)chunk * S;
+  float v[S];
+#pragma unroll
+  for (int s = 0; s < S; ++s) v[s] = __ldcs(in + (t_base + s) * N + col);
+#pragma unroll
+  for (int s = 0; s < S; ++s) __stcs(out + (t_base + s) * N + col, v[s] + 1.f);
+}
 __global__ void __launch_bounds__(256) flat_copy(const float4* __restrict__ in, float4* __restrict__ out, long n4) {
   long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   float4 v[8];
@@ -59,6 +73,8 @@ int main() {
   run("row 1024col x 8 rows (256 thr)", [&](int k) { row_copy<8><<<(T / 8) * (N / 1024), 256>>>(in[k], out[k], T, N4, N / 1024); });
   run("row 1024col x 16 rows (256 thr)", [&](int k) { row_copy<16><<<(T / 16) * (N / 1024), 256>>>(in[k], out[k], T, N4, N / 1024); });
   run("row 512col x 8 rows (128 thr)", [&](int k) { row_copy<8><<<(T / 8) * (N / 512), 128>>>(in[k], out[k], T, N4, N / 512); });
+  run("wtile 32col x 32 rows scalar (128 thr)", [&](int k) { wtile_copy<32><<<(T / 32) * (N / 128), 128>>>((const float*)in[k], (float*)out[k], T, N, N / 32); });
+  run("wtile 32col x 16 rows scalar (128 thr)", [&](int k) { wtile_copy<16><<<(T / 16) * (N / 128), 128>>>((const float*)in[k], (float*)out[k], T, N, N / 32); });
   run("flat 4KB per warp", [&](int k) { flat_copy<<<(unsigned)((size_t)T * N / 4 / 8 / 256), 256>>>(in[k], out[k], (long)T * N4); });
   return 0;
 }
