@@ -403,9 +403,9 @@ def bench_gae(ctx, steps, warmup):
     run("discounted_return_time_major", dr_tm, 9, 4 * B)
     run("discounted_return_batch_major", dr_bm, 9, 4 * B)
     main = out["gae_time_major[T,B]"]
-    roofline = {"bound": "hbm", "kernel": "scan_tm_wtile_kernel<GAE>", "achieved": main["GBps"],
+    roofline = {"bound": "hbm", "kernel": "scan_tm_pipe_kernel<GAE>", "achieved": main["GBps"],
                 "peak": hbm, "unit": "GB/s", "frac": main["frac"],
-                "traffic": ncu_traffic("c4:scan_tm_wtile_kernel<1, 1>"),
+                "traffic": ncu_traffic("c4:scan_tm_pipe_kernel<1, 1>"),
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": 17 * n + 4 * B}
     # e2e: host arrays in, host arrays out
     hr, hv = pinned(ctx, (T, B), torch.float32), pinned(ctx, (T + 1, B), torch.float32)
