@@ -576,15 +576,18 @@ __device__ __forceinline__ void wtile_body(const ScanArgs &A, const WTileWs &ws,
   if (!INTERIOR && !valid) return;
   // ---- replay from registers ----------------------------------------------------------------
   float x = xin;
-  float *po = A.out + t_base * A.N + col;
-  float *pr = (OP == OP_GAE && A.ret) ? A.ret + t_base * A.N + col : nullptr;
+  // stepping pointers: one 64-bit add per store instead of a 64-bit multiply-add
+  float *po = A.out + (t_base + WT_S - 1) * A.N + col;
+  const int64_t dret = (OP == OP_GAE && A.ret) ? A.ret - A.out : 0;
+  const bool want_ret = OP == OP_GAE && A.ret != nullptr;
 #pragma unroll
   for (int s = WT_S - 1; s >= 0; --s) {
     if (INTERIOR || t_base + s <= t_max) {
       x = step(s, x);
-      __stcs(po + (int64_t)s * A.N, x);
-      if (OP == OP_GAE && pr) __stcs(pr + (int64_t)s * A.N, __fadd_rn(x, v[s]));
+      __stcs(po, x);
+      if (want_ret) __stcs(po + dret, __fadd_rn(x, v[s]));
     }
+    po -= A.N;
   }
 }
 
