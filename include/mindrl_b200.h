@@ -163,6 +163,14 @@ int mrl_prb_max_priority(int64_t handle, float *max_priority, void *stream);
 int mrl_prb_tree_dump(int64_t handle, float *sum_nodes, float *min_nodes, void *stream);
 /* device pointers of the ring columns (capacity rows each) */
 int mrl_prb_columns(int64_t handle, void **col_ptrs_out);
+/* checkpoint support (the reference never saves its buffers): the scalar state
+ * {size, head, rng counter, max_priority} and the 2*leaf_capacity node arrays.  Host pointers;
+ * both calls synchronise `stream`.  Columns are copied by the caller through mrl_prb_columns. */
+int mrl_prb_get_state(int64_t handle, int64_t *size, int64_t *head, uint64_t *rng_counter,
+                      float *max_priority, void *stream);
+int mrl_prb_set_state(int64_t handle, int64_t size, int64_t head, uint64_t rng_counter,
+                      float max_priority, const float *sum_nodes, const float *min_nodes,
+                      void *stream);
 /* sharded buffer (one sub-buffer + tree per rank):
  *   mrl_prb_root_stats writes {root_sum, root_min, (float)size, max_priority} to stats4 (device);
  *   ranks all-gather those 16 bytes (NCCL) into gstats[world][4];
@@ -216,6 +224,11 @@ int mrl_gae(const float *reward, const float *value, const float *next_value,
 int mrl_gae_host(const float *reward, const float *value, const float *next_value,
                  const float *last_value, const uint8_t *done, float *adv, float *ret, int64_t T,
                  int64_t B, float gamma, float lambda, int32_t layout, int32_t mode, void *stream);
+/* advantage normalisation that follows GAE in PPO / A2C (ppo.py:361-368):
+ *   out = (x - mean(x)) / (sqrt(var(x)) + eps), mean and population variance over all n elements,
+ * accumulated in float64 in a fixed order (deterministic).  out may alias x. */
+int mrl_normalize(const float *x, float *out, int64_t n, float eps, void *stream);
+
 /* generic first-order reverse recurrence x[t] = a[t] + b[t] * x[t+1], x[T] = x_last (NULL = 0):
  * V-trace (vtrace.py:88-93, b = discount*c*mask) and TD(lambda) (coma.py:489-501). */
 int mrl_affine_scan(const float *a, const float *b, const float *x_last, float *out, int64_t T,

@@ -62,6 +62,8 @@ SIGNATURES = {
     "mrl_prb_max_priority": [i64, vp, vp],
     "mrl_prb_tree_dump": [i64, vp, vp, vp],
     "mrl_prb_columns": [i64, vp],
+    "mrl_prb_get_state": [i64, vp, vp, vp, vp, vp],
+    "mrl_prb_set_state": [i64, i64, i64, u64, f32, vp, vp, vp],
     "mrl_prb_root_stats": [i64, vp, vp],
     "mrl_prb_sample_sharded": [i64, i64, f32, vp, vp, i32, vp, vp, vp, vp],
     "mrl_prb_shard_init": [i64, i32, i32, vp],
@@ -72,6 +74,7 @@ SIGNATURES = {
     "mrl_discounted_return_host": [vp, vp, vp, vp, i64, i64, i64, f32, i32, i32, vp],
     "mrl_gae": [vp, vp, vp, vp, vp, vp, vp, i64, i64, f32, f32, i32, i32, vp],
     "mrl_gae_host": [vp, vp, vp, vp, vp, vp, vp, i64, i64, f32, f32, i32, i32, vp],
+    "mrl_normalize": [vp, vp, i64, f32, vp],
     "mrl_affine_scan": [vp, vp, vp, vp, i64, i64, i32, i32, vp],
 }
 _RESTYPES = {"mrl_last_error": C.c_char_p, "mrl_launch_count": i64}

@@ -151,6 +151,43 @@ class PriorityReplayBuffer:
                                                 K.current_stream()))
         return s, m
 
+    # -- checkpointing (not in the reference, which never saves its buffers) ----------------------
+    def state_dict(self):
+        """host copy of the ring columns, the tree and the scalar state"""
+        L = _ffi.lib()
+        st = K.current_stream()
+        ptrs = (C.c_void_p * self._spec.ncols)()
+        _ffi.check(L.mrl_prb_columns(self._handle, ptrs))
+        cols = []
+        for p, shape, dt, rb in zip(ptrs, self._spec.shapes, self._spec.dtypes, self._spec.row_bytes):
+            a = np.empty((self._capacity,) + shape, dtype=dt)
+            _ffi.check(L.mrl_memcpy_d2h(a.ctypes.data, p, self._capacity * rb, st))
+            cols.append(a)
+        size, head, ctr, maxp = C.c_int64(), C.c_int64(), C.c_uint64(), C.c_float()
+        _ffi.check(L.mrl_prb_get_state(self._handle, C.byref(size), C.byref(head), C.byref(ctr),
+                                       C.byref(maxp), st))
+        s, m = self.tree()
+        return {"columns": cols, "sum": s, "min": m, "size": size.value, "head": head.value,
+                "rng_counter": ctr.value, "max_priority": maxp.value}
+
+    def load_state_dict(self, state):
+        L = _ffi.lib()
+        st = K.current_stream()
+        ptrs = (C.c_void_p * self._spec.ncols)()
+        _ffi.check(L.mrl_prb_columns(self._handle, ptrs))
+        for p, src, dt, rb in zip(ptrs, state["columns"], self._spec.dtypes, self._spec.row_bytes):
+            a = np.ascontiguousarray(src, dtype=dt)
+            if a.nbytes != self._capacity * rb:
+                raise ValueError("checkpoint column does not match this buffer")
+            _ffi.check(L.mrl_memcpy_h2d(p, a.ctypes.data, a.nbytes, st))
+        s = np.ascontiguousarray(state["sum"], dtype=np.float32)
+        m = np.ascontiguousarray(state["min"], dtype=np.float32)
+        if s.size != 2 * self.info()[2] or m.size != s.size:
+            raise ValueError("checkpoint tree does not match this buffer")
+        _ffi.check(L.mrl_prb_set_state(self._handle, int(state["size"]), int(state["head"]),
+                                       int(state["rng_counter"]), float(state["max_priority"]),
+                                       s.ctypes.data, m.ctypes.data, st))
+
     def shard_init(self, rank, world):
         """allocates this rank's peer mailbox; returns its 64-byte CUDA IPC handle"""
         buf = C.create_string_buffer(64)

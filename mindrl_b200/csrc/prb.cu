@@ -1456,3 +1456,31 @@ extern "C" int mrl_prb_sample_sharded_p2p(int64_t handle, int64_t n, float beta,
   return prb_sample_impl(b, n, beta, uniforms, nullptr, 0, indices, weights, out_cols,
                          as_stream(stream), true);
 }
+
+extern "C" int mrl_prb_get_state(int64_t handle, int64_t *size, int64_t *head, uint64_t *rng_counter,
+                                 float *max_priority, void *stream) {
+  PRB_GET(b, handle);
+  if (size) *size = b->size;
+  if (head) *head = b->head;
+  if (rng_counter) *rng_counter = b->ctr;
+  if (max_priority) return mrl_prb_max_priority(handle, max_priority, stream);
+  return MRL_OK;
+}
+
+extern "C" int mrl_prb_set_state(int64_t handle, int64_t size, int64_t head, uint64_t rng_counter,
+                                 float max_priority, const float *sum_nodes, const float *min_nodes,
+                                 void *stream) {
+  PRB_GET(b, handle);
+  MRL_REQUIRE(size >= 0 && size <= b->capacity && head >= -1 && head < b->capacity && sum_nodes && min_nodes,
+              "mrl_prb_set_state: state does not fit this buffer");
+  cudaStream_t st = as_stream(stream);
+  const size_t bytes = sizeof(float) * 2 * (size_t)b->cap2;
+  MRL_CUDA(cudaMemcpyAsync(b->sum, sum_nodes, bytes, cudaMemcpyHostToDevice, st));
+  MRL_CUDA(cudaMemcpyAsync(b->mn, min_nodes, bytes, cudaMemcpyHostToDevice, st));
+  MRL_CUDA(cudaMemcpyAsync(&b->state->max_priority, &max_priority, sizeof(float), cudaMemcpyHostToDevice, st));
+  MRL_CUDA(cudaStreamSynchronize(st));
+  b->size = size;
+  b->head = head;
+  b->ctr = rng_counter;
+  return MRL_OK;
+}

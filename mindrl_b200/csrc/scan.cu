@@ -1093,6 +1093,72 @@ static int launch_scan(ScanArgs A, int32_t layout, int32_t mode, cudaStream_t st
   return launch_scan_hd<OP, false>(A, layout, mode, st);
 }
 
+// ---- advantage normalisation ----------------------------------------------------------------
+// pass 1: one float64 partial (sum, sum of squares) per CTA; pass 2: every CTA folds the partials in the
+// same fixed order (deterministic), then scales its share.  Replaces moments() + elementwise ops of
+// ppo.py:361-368.
+constexpr int NORM_CTAS = kNumSM * 4;
+
+__global__ void __launch_bounds__(256)
+    norm_partial_kernel(const float *__restrict__ x, int64_t n, double2 *__restrict__ part) {
+  __shared__ double ss[8], sq[8];
+  double s = 0.0, q = 0.0;
+  const int64_t n4 = n / 4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const bool al = (((uintptr_t)x) & 15) == 0;
+  if (al) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+      const float4 v = __ldg(reinterpret_cast<const float4 *>(x) + i);
+      s += (double)v.x + (double)v.y + (double)v.z + (double)v.w;
+      q += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+    }
+  }
+  for (int64_t i = (al ? n4 * 4 : 0) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double v = __ldg(x + i);
+    s += v;
+    q += v * v;
+  }
+#pragma unroll
+  for (int off = 16; off; off >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, off);
+    q += __shfl_xor_sync(0xffffffffu, q, off);
+  }
+  if ((threadIdx.x & 31) == 0) ss[threadIdx.x >> 5] = s, sq[threadIdx.x >> 5] = q;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int w = 0; w < 8; ++w) a += ss[w], b += sq[w];
+    part[blockIdx.x] = make_double2(a, b);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    norm_apply_kernel(const float *__restrict__ x, float *__restrict__ out, int64_t n, float eps,
+                      const double2 *__restrict__ part, int nparts) {
+  __shared__ float s_mean, s_inv;
+  if (threadIdx.x < 32) {
+    double a = 0.0, b = 0.0;
+    for (int i = threadIdx.x; i < nparts; i += 32) a += part[i].x, b += part[i].y;
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, off);
+      b += __shfl_xor_sync(0xffffffffu, b, off);
+    }
+    if (threadIdx.x == 0) {
+      const double mean = a / (double)n;
+      double var = b / (double)n - mean * mean;
+      var = var > 0.0 ? var : 0.0;
+      s_mean = (float)mean;
+      s_inv = 1.0f / (sqrtf((float)var) + eps);
+    }
+  }
+  __syncthreads();
+  const float mean = s_mean, inv = s_inv;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = __fmul_rn(__fsub_rn(__ldg(x + i), mean), inv);
+}
+
 // grow-only device scratch for the *_host entry points
 static uint8_t *g_scratch = nullptr;
 static size_t g_scratch_bytes = 0;
@@ -1155,6 +1221,21 @@ extern "C" int mrl_affine_scan(const float *a, const float *b, const float *x_la
   A.a = a, A.v = b, A.last = x_last, A.out = out;
   A.T = T, A.B = B, A.E = 1, A.N = B;
   return launch_scan<OP_AFFINE>(A, layout, mode, as_stream(stream));
+}
+
+extern "C" int mrl_normalize(const float *x, float *out, int64_t n, float eps, void *stream) {
+  MRL_REQUIRE(n >= 0 && (n == 0 || (x && out)), "mrl_normalize: bad arguments");
+  if (n == 0) return MRL_OK;
+  static double2 *part = nullptr;
+  if (!part) MRL_CUDA(cudaMalloc((void **)&part, sizeof(double2) * NORM_CTAS));
+  cudaStream_t st = as_stream(stream);
+  int ctas = (int)((n + 1023) / 1024);
+  ctas = ctas > NORM_CTAS ? NORM_CTAS : ctas;
+  norm_partial_kernel<<<ctas, 256, 0, st>>>(x, n, part);
+  g_launches.fetch_add(1);
+  norm_apply_kernel<<<ctas, 256, 0, st>>>(x, out, n, eps, part, ctas);
+  MRL_LAUNCHED();
+  return MRL_OK;
 }
 
 extern "C" int mrl_discounted_return_host(const float *reward, const uint8_t *done,

@@ -1,5 +1,5 @@
-from .discounted_return import DiscountedReturn, affine_scan, discounted_reward, gae
+from .discounted_return import DiscountedReturn, affine_scan, discounted_reward, gae, normalize_advantage
 from .n_step_buffer import NStepBuffer
 from .vtrace import get_vs_and_advantages
 
-__all__ = ["DiscountedReturn", "discounted_reward", "gae", "affine_scan", "get_vs_and_advantages", "NStepBuffer"]
+__all__ = ["DiscountedReturn", "discounted_reward", "gae", "affine_scan", "get_vs_and_advantages", "NStepBuffer", "normalize_advantage"]

@@ -191,3 +191,15 @@ def affine_scan(a, b, x_last=None, layout="time_major", mode="auto"):
     _ffi.check(_ffi.lib().mrl_affine_scan(a_ptr, b_ptr, xl_ptr, out.data_ptr(), T, B, lay,
                                           _MODES[mode], K.current_stream()))
     return out
+
+
+def normalize_advantage(advantage, epsilon=1e-8):
+    """(adv - mean) / (sqrt(var) + epsilon) over all elements (PPO's _normalized_advantage,
+    ppo.py:361-368), device arrays only; moments accumulated in float64 in a fixed order."""
+    if _kind(advantage) != "device":
+        raise TypeError("normalize_advantage takes a device array")
+    x, x_ptr = _prep(advantage, np.float32, "device")
+    out = _empty_like(x, "device")
+    _ffi.check(_ffi.lib().mrl_normalize(x_ptr, out.data_ptr(), _prod(x.shape), float(epsilon),
+                                        K.current_stream()))
+    return out

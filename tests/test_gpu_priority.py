@@ -223,3 +223,31 @@ def test_sharded_weights_against_oracle():
     got = g.sample(0.4, uniforms=dev(u), gstats=dev(gstats))
     want = o.sample(0.4, uniforms=u, gstats=gstats)
     same_sample(got, want)
+
+
+def test_checkpoint_round_trip():
+    """state_dict()/load_state_dict(): a restored buffer continues exactly like the original"""
+    rng = np.random.default_rng(9)
+    shapes, types = [(3,), (1,)], [np.float32, np.int32]
+    g = M.PriorityReplayBuffer(0.6, 3000, 32, shapes, types, 4, 5)
+    b = [rng.normal(size=(2500, 3)).astype(np.float32), np.arange(2500, dtype=np.int32)[:, None]]
+    g.insert(*[dev(c) for c in b])
+    g.update_priorities(dev(np.arange(2500)), dev((rng.random(2500) * 3 + 0.01).astype(np.float32)))
+    g.sample(0.4)  # advances the generator
+    sd = g.state_dict()
+    h = M.PriorityReplayBuffer(0.6, 3000, 32, shapes, types, 4, 5)
+    h.load_state_dict(sd)
+    assert h.info() == g.info() and h.max_priority() == g.max_priority()
+    for _ in range(3):
+        a, c = g.sample(0.4), h.sample(0.4)
+        for x, y in zip(a, c):
+            assert torch.equal(x, y)
+        pr = dev((rng.random(32) + 0.01).astype(np.float32))
+        g.update_priorities(a[0], pr)
+        h.update_priorities(c[0], pr)
+    row = [dev(np.ones(3, np.float32)), dev(np.array([7], np.int32))]
+    g.insert(*row)
+    h.insert(*row)
+    gs, gm = g.tree()
+    hs, hm = h.tree()
+    assert np.array_equal(gs[1:], hs[1:]) and np.array_equal(gm[1:], hm[1:])

@@ -235,3 +235,21 @@ def test_empty_and_errors():
     with pytest.raises(ValueError):
         M.DiscountedReturn(0.9)(torch.zeros((3, 4), device="cuda"), torch.zeros((3, 5), dtype=torch.bool, device="cuda"),
                                 torch.zeros((4,), device="cuda"))
+
+
+@pytest.mark.parametrize("n", [1, 7, 1000, 123457, 4096 * 2048])
+def test_normalize_advantage(n):
+    """ppo.py:361-368: (adv - mean) / (sqrt(var) + 1e-8) against a float64 evaluation"""
+    rng = np.random.default_rng(n)
+    x = (rng.normal(size=n) * 3 + 0.7).astype(np.float32)
+    got = M.normalize_advantage(dev(x)).cpu().numpy()
+    mean = x.astype(np.float64).mean()
+    var = x.astype(np.float64).var()
+    want = ((x - np.float32(mean)) * (np.float32(1.0) / (np.sqrt(np.float32(var)) + np.float32(1e-8)))).astype(np.float32)
+    if n == 1:
+        assert got[0] == 0.0
+    else:
+        assert np.allclose(got, want, rtol=2e-6, atol=2e-6)
+        assert abs(got.astype(np.float64).mean()) < 1e-4 and abs(got.astype(np.float64).std() - 1) < 1e-3
+    again = M.normalize_advantage(dev(x)).cpu().numpy()
+    assert np.array_equal(got, again)  # fixed accumulation order
