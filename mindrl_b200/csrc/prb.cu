@@ -582,7 +582,7 @@ __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __gri
   uint32_t *s_node = reinterpret_cast<uint32_t *>(s_raw + kSubMaxLocal);
   float2 *s_val = reinterpret_cast<float2 *>(s_raw + 2 * kSubMaxLocal);
   const int tid = threadIdx.x, nthr = blockDim.x;
-  constexpr int G = kSubCtas;  // == gridDim.x (a power of two: the ownership tests are masks)
+  const int G = (int)gridDim.x;  // a power of two (128..512): the ownership tests are masks
   // max_priority takes every processed priority (also those a later duplicate overwrites); every
   // entry is owned by exactly one CTA, which evaluates p**alpha for it anyway
   float local_max = 0.0f;
@@ -670,6 +670,66 @@ __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __gri
         __stcg(U.mn + g, smin[jn]);
       }
       __syncthreads();
+    }
+  } else if (total_mine > 0 && total_mine <= 32) {
+    // ---- small share (the normal case): one warp, no barriers, no shared-memory exchange ----------
+    // Lanes whose path nodes have the same parent find each other with match.any; duplicates of a leaf
+    // resolve with a max-reduction over their group.
+    if (tid < 32) {
+      constexpr unsigned FULL = 0xffffffffu;
+      const bool on = tid < total_mine;
+      const int k = on ? s_k[tid] : -1;
+      const int64_t leaf = on ? __ldg(U.indices + k) : 0;
+      const uint32_t leaf_node = (uint32_t)(U.cap2 + leaf);
+      float p = 0.0f;
+      float sib_s[kWalkLevels], sib_m[kWalkLevels];
+#pragma unroll
+      for (int d = 0; d < kWalkLevels; ++d) {
+        sib_s[d] = 0.0f, sib_m[d] = FLT_MAX;
+        if (on && d < nlev) {
+          const uint32_t sn = (leaf_node >> d) ^ 1u;
+          sib_s[d] = __ldcg(U.sum + sn);
+          sib_m[d] = __ldcg(U.mn + sn);
+        }
+      }
+      if (on) {
+        p = prb_pow_fn(__ldg(U.priorities + k), U.alpha);
+        local_max = p > local_max ? p : local_max;
+      }
+      const uint32_t lkey = on ? leaf_node : (0x80000000u | (uint32_t)tid);
+      const unsigned same_leaf = __match_any_sync(FULL, lkey);
+      const int win_k = __reduce_max_sync(same_leaf, k);
+      const int win_lane = __ffs(__ballot_sync(same_leaf, k == win_k)) - 1;
+      float vs = __shfl_sync(same_leaf, p, win_lane), vm = vs;
+      if (on && k == win_k) {
+        __stcg(U.sum + leaf_node, vs);
+        __stcg(U.mn + leaf_node, vm);
+      }
+      if (blockIdx.x == 0) dbg_mark_gt(U.dbg, 10);
+#pragma unroll
+      for (int d = 0; d < kWalkLevels; ++d) {
+        if (d < nlev) {
+          const uint32_t node = leaf_node >> d;
+          if (d > 0 && on) {
+            __stcg(U.sum + node, vs);
+            __stcg(U.mn + node, vm);
+          }
+          const uint32_t pkey = on ? (node >> 1) : (0x80000000u | (uint32_t)tid);
+          const unsigned same_parent = __match_any_sync(FULL, pkey);
+          const unsigned odd = __ballot_sync(FULL, on && (node & 1u));
+          const unsigned sibs = same_parent & ((node & 1u) ? ~odd : odd);
+          const int src = sibs ? __ffs(sibs) - 1 : tid;
+          const float o_s = __shfl_sync(FULL, vs, src), o_m = __shfl_sync(FULL, vm, src);
+          const float os = sibs ? o_s : sib_s[d], om = sibs ? o_m : sib_m[d];
+          vs = __fadd_rn(vs, os);
+          vm = om < vm ? om : vm;
+        }
+      }
+      if (on && nlev > 0) {
+        const uint32_t node = leaf_node >> nlev;
+        __stcg(U.sum + node, vs);
+        __stcg(U.mn + node, vm);
+      }
     }
   } else if (total_mine > 0) {
     // ---- sparse share: one thread per entry walks its path in registers ---------------------------
@@ -1099,7 +1159,9 @@ static int prb_update_impl(PrbBuffer *b, const int64_t *indices, const float *pr
     prb_update_walk_kernel<<<1, threads, smem, st>>>(U, bits);
   } else if (g_update_path == 0 && b->levels - kTopLevels <= kWalkLevels && b->levels > kTopLevels &&
              n < (1LL << 31)) {
-    prb_update_sub_kernel<<<kSubCtas, kSubThreads, 0, st>>>(U);
+    int ctas = kSubCtas;  // 128..512 so that a CTA's share stays within one warp (~n/ctas entries)
+    while (ctas < 512 && n > 8 * (int64_t)ctas) ctas <<= 1;
+    prb_update_sub_kernel<<<ctas, kSubThreads, 0, st>>>(U);
   } else {
     prb_update_kernel<<<1, 1024, 0, st>>>(U);
   }
