@@ -107,6 +107,7 @@ struct Staging {
 // waits for `st` by polling an event: the blocking cudaStreamSynchronize adds several microseconds of
 // wake-up latency, which is most of a small *_host call
 int stream_wait_spin(cudaStream_t st);
+int set_scan_option(const char *key, int64_t value);  // scan.cu
 
 // gathers the columns selected by col_mask (bit c = column c)
 int gather_rows(const ColTable &tab, const int64_t *slots, int64_t n, int64_t capacity,

@@ -394,6 +394,7 @@ __global__ void __launch_bounds__(256)
 extern "C" int mrl_set_option(const char *key, int64_t value) {
   MRL_REQUIRE(key, "mrl_set_option: NULL key");
   int rc = mrl::set_copy_option(key, value);
+  if (rc) rc = mrl::set_scan_option(key, value);
   if (rc) mrl::set_error("mrl_set_option: unknown key or value out of range: %s=%lld", key, (long long)value);
   return rc;
 }

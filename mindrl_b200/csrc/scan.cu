@@ -20,25 +20,9 @@
 // bit-comparable kernel.
 #include <stdlib.h>
 
-#include "common.cuh"
+#include "scan.cuh"
 
 namespace mrl {
-
-enum { OP_DR = 0, OP_GAE = 1, OP_AFFINE = 2 };
-
-struct ScanArgs {
-  const float *a;       // reward (DR, GAE) / a (AFFINE)
-  const float *v;       // value (GAE) / b (AFFINE)
-  const float *nv;      // next_value (GAE) or NULL
-  const float *last;    // last_value / x_last or NULL
-  const uint8_t *done;  // or NULL
-  float *out;           // returns / advantages / x
-  float *ret;           // GAE returns or NULL
-  int64_t T, B, E, N;   // N = B*E columns
-  int64_t st, sc;       // element strides along t and along the column index
-  int64_t dst, dsc;     // same for done (indexed by column / E)
-  float gamma, gl;      // gl = fl(gamma*lambda)
-};
 
 template <int OP>
 __device__ __forceinline__ float scan_init(const ScanArgs &A, int64_t col) {
@@ -86,10 +70,6 @@ __device__ __forceinline__ void scan_load(const ScanArgs &A, int64_t t, int64_t 
     b = __fmul_rn(A.gl, m);
     aux = v;
   }
-}
-
-__device__ __forceinline__ float scan_step(float a, float b, float x) {
-  return __fadd_rn(a, __fmul_rn(b, x));
 }
 
 template <int OP>
@@ -950,6 +930,20 @@ static bool aligned16(const void *p) { return (((uintptr_t)p) & 15) == 0; }
 static uint8_t *g_tile_ws = nullptr;
 static size_t g_tile_ws_bytes = 0;
 static int g_tile_mode = -1;  // MRL_TM_KERNEL=chunked forces the two-pass kernel
+static int g_bm_mode = 0;     // 0 auto, 1 warp-per-row register kernel only, 2 TMA row kernel whenever it fits
+extern int64_t g_strip_cols, g_strip_min_cols;  // scan_tma.cu
+
+// "tm_kernel": 0 auto, 2 two-pass chunked, 3 128-column CTA tiles, 5 warp tiles with look-back,
+// 6 TMA strips whenever the alignment allows; "strip_cols": 0 auto / 16 / 32; "bm_kernel": see g_bm_mode
+int set_scan_option(const char *key, int64_t value) {
+  std::string k(key);
+  if (k == "tm_kernel" && (value == 0 || value == 2 || value == 3 || value == 5 || value == 6)) g_tile_mode = (int)value;
+  else if (k == "strip_cols" && (value == 0 || value == 16 || value == 32)) g_strip_cols = value;
+  else if (k == "strip_min_cols" && value >= 0) g_strip_min_cols = value;
+  else if (k == "bm_kernel" && value >= 0 && value <= 2) g_bm_mode = (int)value;
+  else return MRL_ERR_INVALID;
+  return MRL_OK;
+}
 
 static int tile_workspace(size_t need, uint8_t **p) {
   if (need > g_tile_ws_bytes) {
@@ -971,14 +965,22 @@ static int launch_scan_hd(ScanArgs A, int32_t layout, int32_t mode, cudaStream_t
     if (mode == MRL_SCAN_SEQUENTIAL) chunked = false;
     else if (mode == MRL_SCAN_PARALLEL) chunked = A.T >= 2;
     else chunked = A.T >= 64 && A.N < (int64_t)kNumSM * 1024;
+    if (chunked && (g_tile_mode == 0 || g_tile_mode == 6)) {
+      const int rc = scan_tm_strip_launch(A, OP, g_tile_mode == 6, st);
+      if (rc != kScanNotApplicable) {
+        if (rc != MRL_OK) return rc;
+        MRL_LAUNCHED();
+        return MRL_OK;
+      }
+    }
     const bool vec4 = A.E == 1 && A.N % 4 == 0 && aligned16(A.a) && aligned16(A.out) &&
                       (OP == OP_DR || aligned16(A.v)) && (!A.nv || aligned16(A.nv)) &&
                       (!A.ret || aligned16(A.ret)) && (!A.last || aligned16(A.last)) &&
                       (!A.done || (((uintptr_t)A.done) & 3) == 0);
     const bool pipe_ok = A.E == 1 && A.T % WT_S == 0 && A.N % 32 == 0 && aligned16(A.a) &&
                          (OP == OP_DR || aligned16(A.v)) && (!A.done || (((uintptr_t)A.done) & 3) == 0);
-    if (chunked && (g_tile_mode == 5 || g_tile_mode == 0) && !(OP == OP_GAE && A.nv)) {
-      const bool pipe = pipe_ok && g_tile_mode == 0;
+    if (chunked && (g_tile_mode == 5 || g_tile_mode == 0 || g_tile_mode == 6) && !(OP == OP_GAE && A.nv)) {
+      const bool pipe = pipe_ok && g_tile_mode != 5;
       const int64_t nch = (A.T + WT_S - 1) / WT_S;
       const int64_t n_wgroups = (A.N + 31) / 32;
       const int64_t n_cgroups = (n_wgroups + WT_WARPS - 1) / WT_WARPS;
@@ -1026,7 +1028,7 @@ static int launch_scan_hd(ScanArgs A, int32_t layout, int32_t mode, cudaStream_t
             A, ws, ll_ticket_base, ll_epoch, (int)nch, (int)n_wgroups, (int)n_cgroups);
         ll_ticket_base += (unsigned long long)(nch * n_cgroups);
       }
-    } else if (chunked && (g_tile_mode == 3 || g_tile_mode == 0) && vec4) {
+    } else if (chunked && (g_tile_mode == 3 || g_tile_mode == 0 || g_tile_mode == 6) && vec4) {
       const int64_t n4 = (A.T + T4_TC - 1) / T4_TC;
       const int64_t n_groups = (A.N + T4_COLS - 1) / T4_COLS;
       const size_t tiles = (size_t)n4 * n_groups;
@@ -1060,6 +1062,14 @@ static int launch_scan_hd(ScanArgs A, int32_t layout, int32_t mode, cudaStream_t
       const int64_t blocks = (A.N + 127) / 128;
       scan_seq_kernel<OP, HD><<<(unsigned)blocks, 128, 0, st>>>(A);
     } else {
+      if (g_bm_mode != 1) {
+        const int rc = scan_bm_row_launch(A, OP, g_bm_mode == 2, st);
+        if (rc != kScanNotApplicable) {
+          if (rc != MRL_OK) return rc;
+          MRL_LAUNCHED();
+          return MRL_OK;
+        }
+      }
       const bool vec = (A.T % 4 == 0) && aligned16(A.a) && aligned16(A.out) &&
                        (OP == OP_DR || aligned16(A.v)) && (!A.nv || aligned16(A.nv)) &&
                        (!A.ret || aligned16(A.ret)) && (!A.done || (((uintptr_t)A.done) & 3) == 0);
@@ -1079,6 +1089,7 @@ static int launch_scan(ScanArgs A, int32_t layout, int32_t mode, cudaStream_t st
   if (A.T <= 0 || A.N <= 0) return MRL_OK;
   if (g_tile_mode < 0) {
     const char *e = getenv("MRL_TM_KERNEL");
+    // "s": TMA strips whenever aligned (also below the width where auto picks them)
     // default 0: 128-column tiles when aligned, else 32-column tiles; "t": 32-column tiles only;
     // "c": two-pass chunked kernel only
     // "4": 128-column CTA tiles (aligned inputs only)
@@ -1088,6 +1099,7 @@ static int launch_scan(ScanArgs A, int32_t layout, int32_t mode, cudaStream_t st
     if (e && e[0] == 'c') g_tile_mode = 2;
     if (e && e[0] == '4') g_tile_mode = 3;
     if (e && e[0] == 'w') g_tile_mode = 5;
+    if (e && e[0] == 's') g_tile_mode = 6;
   }
   if (OP != OP_AFFINE && A.done) return launch_scan_hd<OP, true>(A, layout, mode, st);
   return launch_scan_hd<OP, false>(A, layout, mode, st);

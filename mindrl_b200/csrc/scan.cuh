@@ -1,0 +1,33 @@
+// scan.cuh -- argument block shared by the reverse-scan kernels (scan.cu, scan_tma.cu).
+#pragma once
+#include "common.cuh"
+
+namespace mrl {
+
+enum { OP_DR = 0, OP_GAE = 1, OP_AFFINE = 2 };
+
+struct ScanArgs {
+  const float *a;       // reward (DR, GAE) / a (AFFINE)
+  const float *v;       // value (GAE) / b (AFFINE)
+  const float *nv;      // next_value (GAE) or NULL
+  const float *last;    // last_value / x_last or NULL
+  const uint8_t *done;  // or NULL
+  float *out;           // returns / advantages / x
+  float *ret;           // GAE returns or NULL
+  int64_t T, B, E, N;   // N = B*E columns
+  int64_t st, sc;       // element strides along t and along the column index
+  int64_t dst, dsc;     // same for done (indexed by column / E)
+  float gamma, gl;      // gl = fl(gamma*lambda)
+};
+
+__device__ __forceinline__ float scan_step(float a, float b, float x) {
+  return __fadd_rn(a, __fmul_rn(b, x));
+}
+
+// TMA-ring kernels (scan_tma.cu).  Return MRL_OK after launching, or kScanNotApplicable when the shape
+// or the alignment does not fit (the caller then takes the register kernels of scan.cu).
+constexpr int kScanNotApplicable = -1000;
+int scan_tm_strip_launch(const ScanArgs &A, int op, bool force, cudaStream_t st);
+int scan_bm_row_launch(const ScanArgs &A, int op, bool force, cudaStream_t st);
+
+}  // namespace mrl

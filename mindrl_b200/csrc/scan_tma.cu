@@ -1,0 +1,619 @@
+// scan_tma.cu -- reverse scans as persistent CTAs fed by the TMA engine (sm_100a).
+//
+// Same recurrences as scan.cu (x[t] = a[t] + b[t]*x[t+1]; DiscountedReturn discounted_return.py:84-92,
+// PPO ppo.py:320-350, MAPPO mappo.py:478-497, V-trace vtrace.py:88-93), different machine mapping:
+//
+//   * one elected thread of a producer warp keeps a ring of shared-memory stages full with
+//     cp.async.bulk[.tensor] (mbarrier complete_tx), so the bytes in flight per SM do not depend on
+//     how many registers or warps the arithmetic needs and no thread computes a global address;
+//   * 8 consumer warps take a stage out of shared memory (conflict-free), build the affine map of
+//     their 8-step (time-major) / 128-step (batch-major) piece, exchange the 8 / 16 maps of the tile
+//     through shared memory (ONE named barrier per tile), chain them from the CTA's running carry and
+//     replay their piece;
+//   * results are staged in shared memory and leave through cp.async.bulk stores (bulk groups), one
+//     per warp, so a warp never waits for another warp's output.
+//
+// A CTA walks its strip (time-major: 32 or 16 columns, all T) or its environments (batch-major: whole
+// rows) from the last step to the first, so the carry never leaves the CTA: no look-back, no flags,
+// no workspace.  Parallel kernels re-associate fp32 (spec: 1e-5 relative).
+#include <cuda.h>
+
+#include "scan.cuh"
+
+namespace mrl {
+namespace {
+
+// ---- PTX helpers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(s32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int x, int y, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
+          "r"(s32(dst)),
+      "l"(map), "r"(x), "r"(y), "r"(s32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, int x, int y, const void *src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map),
+               "r"(x), "r"(y), "r"(s32(src))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+                   "r"(s32(dst)),
+               "l"(src), "r"(bytes), "r"(s32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store(void *dst, const void *src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(s32(src)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+constexpr int kWarps = 8;  // consumer warps; warp kWarps is the producer
+constexpr int kThreads = (kWarps + 1) * 32;
+
+// =============================================================================================
+// time-major strips
+// =============================================================================================
+constexpr int ST_RPU = 8;  // steps per unit (a unit = COLS adjacent lanes of a warp)
+
+template <int OP, bool HD, int COLS>
+struct StripCfg {
+  static constexpr int kUPW = 32 / COLS;                  // units per warp
+  static constexpr int kUnits = kWarps * kUPW;            // units per tile
+  static constexpr int kRows = kUnits * ST_RPU;           // steps per tile (64 / 128)
+  static constexpr int kVRows = OP == OP_GAE ? kRows + 1 : (OP == OP_AFFINE ? kRows : 0);
+  static constexpr int kOffV = kRows * COLS * 4;
+  static constexpr int kOffD = kOffV + (kVRows * COLS * 4 + 127) / 128 * 128;
+  static constexpr int kStage = kOffD + (HD ? kRows * COLS : 0);
+  static constexpr int kTx = kRows * COLS * 4 + kVRows * COLS * 4 + (HD ? kRows * COLS : 0);
+  static constexpr int kNOut = OP == OP_GAE ? 2 : 1;
+  static constexpr int kStages = OP == OP_GAE ? 4 : 6;
+  static constexpr int kWarpOut = ST_RPU * kUPW * COLS;   // floats one warp produces per output array (256)
+  static constexpr int kOutBytes = kWarps * 2 * kNOut * kWarpOut * 4;
+  static constexpr int kCompBytes = 2 * kUnits * COLS * 8;
+  static constexpr int kSmem = kStages * kStage + kOutBytes + kCompBytes + 2 * 8 * 8 + 128;
+};
+
+template <int OP, bool HD, int COLS>
+__global__ void __launch_bounds__(kThreads)
+    scan_tm_strip_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_v,
+                         const __grid_constant__ CUtensorMap tm_d, const __grid_constant__ CUtensorMap tm_out,
+                         const __grid_constant__ CUtensorMap tm_ret, const __grid_constant__ ScanArgs A,
+                         int n_tiles) {
+  using C = StripCfg<OP, HD, COLS>;
+  extern __shared__ __align__(1024) unsigned char strip_raw[];  // (no integer casts: keeps the shared address space)
+  unsigned char *stages = strip_raw;
+  float *ostage = reinterpret_cast<float *>(stages + C::kStages * C::kStage);
+  float2 *comp = reinterpret_cast<float2 *>(reinterpret_cast<unsigned char *>(ostage) + C::kOutBytes);
+  uint64_t *full = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(comp) + C::kCompBytes);
+  uint64_t *empty = full + 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col0 = blockIdx.x * COLS;
+  const int T = (int)A.T;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kWarps);
+    }
+    fence_async_smem();
+  }
+  __syncthreads();
+
+  if (warp == kWarps) {  // ---- producer ----
+    if (lane == 0) {
+#pragma unroll 1
+      for (int k = 0; k < n_tiles; ++k) {
+        const int s = k % C::kStages;
+        if (k >= C::kStages) mbar_wait(&empty[s], (uint32_t)((k / C::kStages - 1) & 1));
+        unsigned char *sb = stages + s * C::kStage;
+        const int row0 = (n_tiles - 1 - k) * C::kRows;  // the first tile may reach past T: zero-filled
+        mbar_expect_tx(&full[s], C::kTx);
+        tma_load_2d(sb, &tm_a, col0, row0, &full[s]);
+        if (OP != OP_DR) tma_load_2d(sb + C::kOffV, &tm_v, col0, row0, &full[s]);
+        if (HD) tma_load_2d(sb + C::kOffD, &tm_d, col0, row0, &full[s]);
+      }
+    }
+    return;
+  }
+
+  // ---- consumers ----
+  const int c = lane % COLS, h = lane / COLS;
+  const int unit = warp * C::kUPW + h;
+  const int col = col0 + c;
+  float X = 0.0f, lastv = 0.0f;
+  if (col < A.N && A.last) {
+    const float l = __ldg(A.last + col);
+    if (OP == OP_GAE) lastv = l;
+    else X = l;
+  }
+  const bool want_ret = OP == OP_GAE && A.ret != nullptr;
+  float *my_out = ostage + warp * (2 * C::kNOut * C::kWarpOut);
+
+#pragma unroll 1
+  for (int k = 0; k < n_tiles; ++k) {
+    const int s = k % C::kStages;
+    mbar_wait(&full[s], (uint32_t)((k / C::kStages) & 1));
+    const unsigned char *sb = stages + s * C::kStage;
+    const int e0 = unit * ST_RPU * COLS + c;  // first element of this lane's column piece
+    float ea[ST_RPU], eb[ST_RPU], aux[ST_RPU];
+    {
+      float r[ST_RPU], vv[ST_RPU + 1];
+      unsigned char dd[ST_RPU];
+      const float *sa = reinterpret_cast<const float *>(sb) + e0;
+#pragma unroll
+      for (int i = 0; i < ST_RPU; ++i) r[i] = sa[i * COLS];
+      if (OP != OP_DR) {
+        const float *sv = reinterpret_cast<const float *>(sb + C::kOffV) + e0;
+#pragma unroll
+        for (int i = 0; i < ST_RPU + (OP == OP_GAE ? 1 : 0); ++i) vv[i] = sv[i * COLS];
+      }
+      if (HD) {
+        const unsigned char *sd = sb + C::kOffD + e0;
+#pragma unroll
+        for (int i = 0; i < ST_RPU; ++i) dd[i] = sd[i * COLS];
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+      const int g0 = (n_tiles - 1 - k) * C::kRows + unit * ST_RPU;  // global step of this lane's first row
+      if (OP == OP_GAE && k == 0) {  // row T (zero-filled by the DMA) is the bootstrap value
+#pragma unroll
+        for (int i = 0; i < ST_RPU; ++i)
+          if (g0 + i + 1 == T) vv[i + 1] = lastv;
+      }
+#pragma unroll
+      for (int i = 0; i < ST_RPU; ++i) {
+        if (OP == OP_AFFINE) {
+          ea[i] = r[i], eb[i] = vv[i], aux[i] = 0.0f;
+        } else {
+          const float m = HD ? (dd[i] ? 0.0f : 1.0f) : 1.0f;
+          if (OP == OP_DR) {
+            ea[i] = r[i], eb[i] = __fmul_rn(m, A.gamma), aux[i] = 0.0f;
+          } else {
+            const float gvm = __fmul_rn(__fmul_rn(A.gamma, vv[i + 1]), m);
+            ea[i] = __fsub_rn(__fadd_rn(r[i], gvm), vv[i]);
+            eb[i] = __fmul_rn(A.gl, m);
+            aux[i] = vv[i];
+          }
+        }
+      }
+      if (k == 0) {  // steps past T in the first tile: identity maps
+#pragma unroll
+        for (int i = 0; i < ST_RPU; ++i)
+          if (g0 + i >= T) ea[i] = 0.0f, eb[i] = 1.0f;
+      }
+    }
+    // this piece as one affine map x[first step] = ca + cb * x[first step after the piece]
+    float ca = 0.0f, cb = 1.0f;
+#pragma unroll
+    for (int i = ST_RPU - 1; i >= 0; --i) {
+      ca = scan_step(ea[i], eb[i], ca);
+      cb = __fmul_rn(eb[i], cb);
+    }
+    float2 *cbuf = comp + (k & 1) * (C::kUnits * COLS);
+    cbuf[unit * COLS + c] = make_float2(ca, cb);
+    consumer_barrier();
+    float x = X, xin = X;
+#pragma unroll
+    for (int u = C::kUnits - 1; u >= 0; --u) {
+      if (u == unit) xin = x;
+      const float2 m = cbuf[u * COLS + c];
+      x = scan_step(m.x, m.y, x);
+    }
+    X = x;
+
+    // replay, stage, store
+    float *oa = my_out + (k & 1) * (C::kNOut * C::kWarpOut);
+    if (lane == 0) bulk_wait_read<1>();  // the store issued from this buffer two tiles ago has been read
+    __syncwarp();
+    x = xin;
+#pragma unroll
+    for (int i = ST_RPU - 1; i >= 0; --i) {
+      x = scan_step(ea[i], eb[i], x);
+      oa[(h * ST_RPU + i) * COLS + c] = x;
+      if (want_ret) oa[C::kWarpOut + (h * ST_RPU + i) * COLS + c] = __fadd_rn(x, aux[i]);
+    }
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      const int row = (n_tiles - 1 - k) * C::kRows + warp * (ST_RPU * C::kUPW);
+      if (row < T) {  // rows past T are clipped by the tensor map
+        tma_store_2d(&tm_out, col0, row, oa);
+        if (want_ret) tma_store_2d(&tm_ret, col0, row, oa + C::kWarpOut);
+      }
+      bulk_commit();
+    }
+  }
+  if (lane == 0) bulk_wait_all();
+}
+
+// ---- host: tensor maps ------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+
+// row-major [rows, cols] array of `esize`-byte elements, box = box_rows x box_cols
+bool make_map(CUtensorMap *m, const void *base, bool is_u8, int64_t rows, int64_t cols, int box_cols,
+              int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  const int esize = is_u8 ? 1 : 4;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * esize};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(m, is_u8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                        const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+bool al16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <int OP, bool HD, int COLS>
+int strip_launch(const ScanArgs &A, cudaStream_t st) {
+  using C = StripCfg<OP, HD, COLS>;
+  CUtensorMap ma, mv, md, mo, mr;
+  if (!make_map(&ma, A.a, false, A.T, A.N, COLS, C::kRows)) return kScanNotApplicable;
+  mv = ma, md = ma;
+  if (OP != OP_DR && !make_map(&mv, A.v, false, A.T, A.N, COLS, C::kVRows)) return kScanNotApplicable;
+  if (HD && !make_map(&md, A.done, true, A.T, A.N, COLS, C::kRows)) return kScanNotApplicable;
+  if (!make_map(&mo, A.out, false, A.T, A.N, COLS, ST_RPU * C::kUPW)) return kScanNotApplicable;
+  mr = mo;
+  if (OP == OP_GAE && A.ret && !make_map(&mr, A.ret, false, A.T, A.N, COLS, ST_RPU * C::kUPW))
+    return kScanNotApplicable;
+  static bool configured = false;
+  if (!configured) {
+    MRL_CUDA(cudaFuncSetAttribute(scan_tm_strip_kernel<OP, HD, COLS>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
+    configured = true;
+  }
+  const int64_t n_strips = (A.N + COLS - 1) / COLS;
+  const int n_tiles = (int)((A.T + C::kRows - 1) / C::kRows);
+  scan_tm_strip_kernel<OP, HD, COLS><<<(unsigned)n_strips, kThreads, C::kSmem, st>>>(ma, mv, md, mo, mr, A,
+                                                                                      n_tiles);
+  return MRL_OK;
+}
+
+template <int OP, bool HD>
+int strip_launch_cols(const ScanArgs &A, int cols, cudaStream_t st) {
+  if (cols == 16) return strip_launch<OP, HD, 16>(A, st);
+  return strip_launch<OP, HD, 32>(A, st);
+}
+
+}  // namespace
+
+int64_t g_strip_cols = 0;     // 0 = auto, 16, 32
+int64_t g_strip_min_cols = 2048;  // auto: narrower batches keep the look-back kernels (time-parallel)
+
+// Time-major [T, N], E == 1.  Needs 16-byte aligned bases and row pitches (N % 4 == 0; N % 16 == 0 with
+// done flags): the tensor maps address rows by pitch.
+int scan_tm_strip_launch(const ScanArgs &A, int op, bool force, cudaStream_t st) {
+  if (A.E != 1 || (op == OP_GAE && A.nv)) return kScanNotApplicable;
+  if (A.T >= (1LL << 31) - 256 || A.N >= (1LL << 31) - 64 || A.N % 4 != 0) return kScanNotApplicable;
+  if (!al16(A.a) || !al16(A.out) || (op != OP_DR && !al16(A.v)) || (A.ret && !al16(A.ret)))
+    return kScanNotApplicable;
+  const bool hd = op != OP_AFFINE && A.done != nullptr;
+  if (hd && (A.N % 16 != 0 || !al16(A.done))) return kScanNotApplicable;
+  if (!force && (A.N < g_strip_min_cols || A.T < 64)) return kScanNotApplicable;
+  int cols = (int)g_strip_cols;
+  if (cols == 0) cols = 32;
+  if (op == OP_DR) return hd ? strip_launch_cols<OP_DR, true>(A, cols, st) : strip_launch_cols<OP_DR, false>(A, cols, st);
+  if (op == OP_GAE) return hd ? strip_launch_cols<OP_GAE, true>(A, cols, st) : strip_launch_cols<OP_GAE, false>(A, cols, st);
+  return strip_launch_cols<OP_AFFINE, false>(A, cols, st);
+}
+
+// =============================================================================================
+// batch-major rows
+// =============================================================================================
+// A tile is one environment's chunk of up to BM_L steps (8 KB per float array, one bulk copy each).
+// Warp w owns positions [256w, 256w+256) as two 128-step sub-tiles (lane l: steps 4l..4l+3 of each,
+// float4 from shared memory); the 16 sub-tile maps of a tile are chained from the running carry of the
+// environment.  A CTA takes environments blockIdx.x, blockIdx.x + gridDim.x, ... and walks the chunks
+// of each from the last to the first.
+namespace {
+
+constexpr int BM_L = 2048;
+constexpr int BM_SUB = 16;  // sub-tiles per tile
+
+template <int OP, bool HD, bool NVF>
+struct RowCfg {
+  static constexpr int kOffV = BM_L * 4;
+  static constexpr int kOffNV = kOffV + (OP != OP_DR ? BM_L * 4 + 128 : 0);  // +: sv[BM_L] stays in bounds
+  static constexpr int kOffD = kOffNV + (NVF ? BM_L * 4 : 0);
+  static constexpr int kStage = kOffD + (HD ? BM_L : 0);
+  static constexpr int kNOut = OP == OP_GAE ? 2 : 1;
+  static constexpr int kStages = OP == OP_DR ? 6 : (NVF ? 3 : 4);
+  static constexpr int kWarpOut = BM_L / kWarps;  // 256 floats
+  static constexpr int kOutBytes = kWarps * 2 * kNOut * kWarpOut * 4;
+  static constexpr int kCompBytes = 2 * BM_SUB * 8;
+  static constexpr int kSmem = kStages * kStage + kOutBytes + kCompBytes + 2 * 8 * 8 + 128;
+};
+
+template <int OP, bool HD, bool NVF>
+__global__ void __launch_bounds__(kThreads)
+    scan_bm_row_kernel(const __grid_constant__ ScanArgs A, int n_chunks) {
+  using C = RowCfg<OP, HD, NVF>;
+  extern __shared__ __align__(1024) unsigned char row_raw[];
+  unsigned char *stages = row_raw;
+  float *ostage = reinterpret_cast<float *>(stages + C::kStages * C::kStage);
+  float2 *comp = reinterpret_cast<float2 *>(reinterpret_cast<unsigned char *>(ostage) + C::kOutBytes);
+  uint64_t *full = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(comp) + C::kCompBytes);
+  uint64_t *empty = full + 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t T = A.T;
+  const int64_t G = gridDim.x;
+  const int64_t n_rows = A.N > (int64_t)blockIdx.x ? (A.N - blockIdx.x + G - 1) / G : 0;
+  const int64_t n_items = n_rows * n_chunks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kWarps);
+    }
+    fence_async_smem();
+  }
+  __syncthreads();
+
+  if (warp == kWarps) {  // ---- producer ----
+    if (lane == 0) {
+      int64_t row = blockIdx.x;
+      int c = 0;
+#pragma unroll 1
+      for (int64_t k = 0; k < n_items; ++k) {
+        const int s = (int)(k % C::kStages);
+        if (k >= C::kStages) mbar_wait(&empty[s], (uint32_t)((k / C::kStages - 1) & 1));
+        unsigned char *sb = stages + s * C::kStage;
+        const int64_t t_end = T - (int64_t)c * BM_L;
+        const int64_t t_begin = t_end > BM_L ? t_end - BM_L : 0;
+        const uint32_t len = (uint32_t)(t_end - t_begin);
+        const int64_t off = row * T + t_begin;
+        mbar_expect_tx(&full[s], len * (4u + (OP != OP_DR ? 4u : 0u) + (NVF ? 4u : 0u) + (HD ? 1u : 0u)));
+        bulk_load(sb, A.a + off, len * 4u, &full[s]);
+        if (OP != OP_DR) bulk_load(sb + C::kOffV, A.v + off, len * 4u, &full[s]);
+        if (NVF) bulk_load(sb + C::kOffNV, A.nv + off, len * 4u, &full[s]);
+        if (HD) bulk_load(sb + C::kOffD, A.done + off, len, &full[s]);
+        if (++c == n_chunks) c = 0, row += G;
+      }
+    }
+    return;
+  }
+
+  // ---- consumers ----
+  constexpr unsigned FULL = 0xffffffffu;
+  const bool want_ret = OP == OP_GAE && A.ret != nullptr;
+  const bool use_last = A.last != nullptr && !(OP == OP_GAE && NVF);
+  float *my_out = ostage + warp * (2 * C::kNOut * C::kWarpOut);
+  float X = 0.0f, v_after = 0.0f;
+  float last_next = (use_last && n_rows > 0) ? __ldg(A.last + blockIdx.x) : 0.0f;
+  int64_t row = blockIdx.x;
+  int c = 0;
+
+#pragma unroll 1
+  for (int64_t k = 0; k < n_items; ++k) {
+    const int s = (int)(k % C::kStages);
+    const int64_t t_end = T - (int64_t)c * BM_L;
+    const int64_t t_begin = t_end > BM_L ? t_end - BM_L : 0;
+    const int len = (int)(t_end - t_begin);
+    if (c == 0) {  // a new environment: boundary values were requested one environment ago
+      X = OP == OP_GAE ? 0.0f : last_next;
+      v_after = OP == OP_GAE ? last_next : 0.0f;
+      last_next = (use_last && row + G < A.N) ? __ldg(A.last + row + G) : 0.0f;
+    }
+    mbar_wait(&full[s], (uint32_t)((k / C::kStages) & 1));
+    const unsigned char *sb = stages + s * C::kStage;
+    float ea[2][4], eb[2][4], aux[2][4];
+    float v_first = 0.0f;
+    {
+      float4 r[2], vv[2], nn[2];
+      uint32_t dd[2] = {0u, 0u};
+      float edge[2] = {0.0f, 0.0f};
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int p0 = (2 * warp + j) * 128 + 4 * lane;
+        r[j] = *reinterpret_cast<const float4 *>(sb + 4 * p0);
+        if (OP != OP_DR) vv[j] = *reinterpret_cast<const float4 *>(sb + C::kOffV + 4 * p0);
+        if (NVF) nn[j] = *reinterpret_cast<const float4 *>(sb + C::kOffNV + 4 * p0);
+        if (HD) dd[j] = *reinterpret_cast<const uint32_t *>(sb + C::kOffD + p0);
+        if (OP == OP_GAE && !NVF && lane == 31) edge[j] = *reinterpret_cast<const float *>(sb + C::kOffV + 4 * (p0 + 4));
+      }
+      if (OP == OP_GAE && !NVF) v_first = *reinterpret_cast<const float *>(sb + C::kOffV);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int p0 = (2 * warp + j) * 128 + 4 * lane;
+        const float rr[4] = {r[j].x, r[j].y, r[j].z, r[j].w};
+        float vq[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+        float nq[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        if (OP != OP_DR) vq[0] = vv[j].x, vq[1] = vv[j].y, vq[2] = vv[j].z, vq[3] = vv[j].w;
+        if (NVF) nq[0] = nn[j].x, nq[1] = nn[j].y, nq[2] = nn[j].z, nq[3] = nn[j].w;
+        if (OP == OP_GAE && !NVF) {
+          const float nb = __shfl_down_sync(FULL, vq[0], 1);
+          vq[4] = lane == 31 ? edge[j] : nb;
+          if (p0 + 4 >= len) vq[4] = v_after;  // the chunk ends inside or right after this quad
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (OP == OP_AFFINE) {
+            ea[j][q] = rr[q], eb[j][q] = vq[q], aux[j][q] = 0.0f;
+          } else {
+            const float m = HD ? (((dd[j] >> (8 * q)) & 0xffu) ? 0.0f : 1.0f) : 1.0f;
+            if (OP == OP_DR) {
+              ea[j][q] = rr[q], eb[j][q] = __fmul_rn(m, A.gamma), aux[j][q] = 0.0f;
+            } else {
+              float nvq = NVF ? nq[q] : vq[q + 1];
+              if (!NVF && q < 3 && p0 + q + 1 >= len) nvq = v_after;
+              const float gvm = __fmul_rn(__fmul_rn(A.gamma, nvq), m);
+              ea[j][q] = __fsub_rn(__fadd_rn(rr[q], gvm), vq[q]);
+              eb[j][q] = __fmul_rn(A.gl, m);
+              aux[j][q] = vq[q];
+            }
+          }
+          if (p0 + q >= len) ea[j][q] = 0.0f, eb[j][q] = 1.0f;  // past the chunk: identity map
+        }
+      }
+    }
+    // per lane: 4 steps as one map; per sub-tile: suffix scan over lanes (later time = higher lane)
+    float ca[2], cb[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      ca[j] = 0.0f, cb[j] = 1.0f;
+#pragma unroll
+      for (int q = 3; q >= 0; --q) {
+        ca[j] = scan_step(ea[j][q], eb[j][q], ca[j]);
+        cb[j] = __fmul_rn(eb[j][q], cb[j]);
+      }
+    }
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const float oa_ = __shfl_down_sync(FULL, ca[j], off);
+        const float ob_ = __shfl_down_sync(FULL, cb[j], off);
+        if (lane + off < 32) {
+          ca[j] = scan_step(ca[j], cb[j], oa_);
+          cb[j] = __fmul_rn(cb[j], ob_);
+        }
+      }
+    }
+    float2 *cbuf = comp + (k & 1) * BM_SUB;
+    if (lane == 0) {
+      cbuf[2 * warp] = make_float2(ca[0], cb[0]);
+      cbuf[2 * warp + 1] = make_float2(ca[1], cb[1]);
+    }
+    consumer_barrier();
+    float x = X, xin[2] = {X, X};
+#pragma unroll
+    for (int u = BM_SUB - 1; u >= 0; --u) {
+      if (u == 2 * warp + 1) xin[1] = x;
+      if (u == 2 * warp) xin[0] = x;
+      const float2 m = cbuf[u];
+      x = scan_step(m.x, m.y, x);
+    }
+    X = x;
+    if (OP == OP_GAE && !NVF) v_after = v_first;
+
+    float *oa = my_out + (k & 1) * (C::kNOut * C::kWarpOut);
+    if (lane == 0) bulk_wait_read<1>();
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const float x_here = scan_step(ca[j], cb[j], xin[j]);  // x at this lane's first step
+      float xe = __shfl_down_sync(FULL, x_here, 1);          // x right after this lane's quad
+      if (lane == 31) xe = xin[j];
+      float o[4], o2[4];
+#pragma unroll
+      for (int q = 3; q >= 0; --q) {
+        xe = scan_step(ea[j][q], eb[j][q], xe);
+        o[q] = xe;
+        o2[q] = __fadd_rn(xe, aux[j][q]);
+      }
+      *reinterpret_cast<float4 *>(oa + j * 128 + 4 * lane) = make_float4(o[0], o[1], o[2], o[3]);
+      if (want_ret)
+        *reinterpret_cast<float4 *>(oa + C::kWarpOut + j * 128 + 4 * lane) = make_float4(o2[0], o2[1], o2[2], o2[3]);
+    }
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      int n = len - warp * C::kWarpOut;
+      n = n > C::kWarpOut ? C::kWarpOut : n;
+      if (n > 0) {
+        const int64_t off = row * T + t_begin + warp * C::kWarpOut;
+        bulk_store(A.out + off, oa, (uint32_t)n * 4u);
+        if (want_ret) bulk_store(A.ret + off, oa + C::kWarpOut, (uint32_t)n * 4u);
+      }
+      bulk_commit();
+    }
+    if (++c == n_chunks) c = 0, row += G;
+  }
+  if (lane == 0) bulk_wait_all();
+}
+
+template <int OP, bool HD, bool NVF>
+int row_launch(const ScanArgs &A, cudaStream_t st) {
+  using C = RowCfg<OP, HD, NVF>;
+  static bool configured = false;
+  if (!configured) {
+    MRL_CUDA(cudaFuncSetAttribute(scan_bm_row_kernel<OP, HD, NVF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  C::kSmem));
+    configured = true;
+  }
+  const int n_chunks = (int)((A.T + BM_L - 1) / BM_L);
+  // as many CTAs as fit at once (2 per SM), trimmed so that every CTA gets the same number of rows
+  int64_t max_ctas = (int64_t)kNumSM * (227 * 1024 / (C::kSmem + 1024));
+  const int64_t per = (A.N + max_ctas - 1) / max_ctas;
+  const int64_t ctas = (A.N + per - 1) / per;
+  scan_bm_row_kernel<OP, HD, NVF><<<(unsigned)ctas, kThreads, C::kSmem, st>>>(A, n_chunks);
+  return MRL_OK;
+}
+
+}  // namespace
+
+int64_t g_row_min_t = 512;
+
+// Batch-major [N, T].  Bulk copies need 16-byte aligned row starts: T % 4 == 0 (T % 16 == 0 with done).
+int scan_bm_row_launch(const ScanArgs &A, int op, bool force, cudaStream_t st) {
+  if (A.T % 4 != 0 || A.T >= (1LL << 40)) return kScanNotApplicable;
+  if (!al16(A.a) || !al16(A.out) || (op != OP_DR && !al16(A.v)) || (A.ret && !al16(A.ret)) ||
+      (A.nv && !al16(A.nv)))
+    return kScanNotApplicable;
+  const bool hd = op != OP_AFFINE && A.done != nullptr;
+  if (hd && (A.T % 16 != 0 || !al16(A.done))) return kScanNotApplicable;
+  if (!force && (A.T < g_row_min_t || A.N * A.T < (1 << 20))) return kScanNotApplicable;
+  if (op == OP_DR) return hd ? row_launch<OP_DR, true, false>(A, st) : row_launch<OP_DR, false, false>(A, st);
+  if (op == OP_AFFINE) return row_launch<OP_AFFINE, false, false>(A, st);
+  if (A.nv) return hd ? row_launch<OP_GAE, true, true>(A, st) : row_launch<OP_GAE, false, true>(A, st);
+  return hd ? row_launch<OP_GAE, true, false>(A, st) : row_launch<OP_GAE, false, false>(A, st);
+}
+
+}  // namespace mrl
