@@ -77,7 +77,16 @@ __device__ __forceinline__ void bulk_wait_read() {
 }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// A consumer warp has read its part of a stage with ordinary (generic-proxy) loads and hands the stage
+// back to the producer, whose refill is an async-proxy write: the proxy fence orders the two (without it
+// the refill was observed to land under loads still in flight: bit-flips of whole tiles, timing dependent).
+__device__ __forceinline__ void release_stage(uint64_t *empty_bar, int lane) {
+  fence_async_smem();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(empty_bar);
+}
+template <int ID = 1>
+__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync %0, 256;" ::"n"(ID) : "memory"); }
 
 constexpr int kWarps = 8;  // consumer warps; warp kWarps is the producer
 constexpr int kThreads = (kWarps + 1) * 32;
@@ -85,64 +94,90 @@ constexpr int kThreads = (kWarps + 1) * 32;
 // =============================================================================================
 // time-major strips
 // =============================================================================================
-constexpr int ST_RPU = 8;  // steps per unit (a unit = COLS adjacent lanes of a warp)
+// a unit = COLS adjacent lanes of a warp x RPU consecutive steps
 
-template <int OP, bool HD, int COLS>
+// The parallel kernels re-associate fp32 anyway (spec: 1e-5 relative), so the maps are composed and
+// replayed with fused multiply-adds: half the dependent latency and one instruction per step.  The
+// per-element (a, b) keep the reference's operation order.
+__device__ __forceinline__ float fstep(float a, float b, float x) { return __fmaf_rn(b, x, a); }
+
+constexpr int kMaxStages = 12;
+
+template <int OP, bool HD, int COLS, int RPU, int NG>
 struct StripCfg {
+  static constexpr int kThreads = (NG * kWarps + 1) * 32;  // NG consumer groups of 8 warps + the producer warp
   static constexpr int kUPW = 32 / COLS;                  // units per warp
   static constexpr int kUnits = kWarps * kUPW;            // units per tile
-  static constexpr int kRows = kUnits * ST_RPU;           // steps per tile (64 / 128)
+  static constexpr int kRows = kUnits * RPU;              // steps per tile (64 .. 256)
   static constexpr int kVRows = OP == OP_GAE ? kRows + 1 : (OP == OP_AFFINE ? kRows : 0);
   static constexpr int kOffV = kRows * COLS * 4;
   static constexpr int kOffD = kOffV + (kVRows * COLS * 4 + 127) / 128 * 128;
   static constexpr int kStage = kOffD + (HD ? kRows * COLS : 0);
   static constexpr int kTx = kRows * COLS * 4 + kVRows * COLS * 4 + (HD ? kRows * COLS : 0);
   static constexpr int kNOut = OP == OP_GAE ? 2 : 1;
-  static constexpr int kStages = OP == OP_GAE ? 4 : 6;
-  static constexpr int kWarpOut = ST_RPU * kUPW * COLS;   // floats one warp produces per output array (256)
-  static constexpr int kOutBytes = kWarps * 2 * kNOut * kWarpOut * 4;
-  static constexpr int kCompBytes = 2 * kUnits * COLS * 8;
-  static constexpr int kSmem = kStages * kStage + kOutBytes + kCompBytes + 2 * 8 * 8 + 128;
+  static constexpr int kWarpRows = RPU * kUPW;            // rows one warp produces per tile
+  static constexpr int kWarpOut = kWarpRows * COLS;       // floats per output array
+  static constexpr int kCompBytes = NG * 2 * kUnits * COLS * 8 + 2 * COLS * 4;  // maps (per group, double-buffered) + carries
+  static constexpr int kFixed = kCompBytes + 2 * 8 * 8;
+  static constexpr int kOut1 = NG * kWarps * kNOut * kWarpOut * 4;  // one output staging buffer
+  static constexpr int kBarBytes = (2 * kMaxStages + 2) * 8;
+  // ring depth and output double-buffering are chosen at launch from the shared memory a CTA may take
+  // (all of the SM when the strips fit one per SM, half otherwise)
+  static constexpr int smem_bytes(int stages, int obufs) {
+    return stages * kStage + obufs * kOut1 + kCompBytes + kBarBytes;
+  }
 };
 
-template <int OP, bool HD, int COLS>
-__global__ void __launch_bounds__(kThreads)
+// NG == 2: two consumer groups take alternate tiles of the strip, so that the loads and the map building
+// of tile k+1 run while tile k is chained, replayed and stored (a lone group of 8 warps is latency-bound
+// on its own dependent chain).  The running carry passes between the groups through shared memory and
+// one mbarrier per tile parity.
+template <int OP, bool HD, int COLS, int RPU, int NG>
+__global__ void __launch_bounds__((NG * kWarps + 1) * 32)
     scan_tm_strip_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_v,
-                         const __grid_constant__ CUtensorMap tm_d, const __grid_constant__ CUtensorMap tm_out,
-                         const __grid_constant__ CUtensorMap tm_ret, const __grid_constant__ ScanArgs A,
-                         int n_tiles) {
-  using C = StripCfg<OP, HD, COLS>;
+                         const __grid_constant__ CUtensorMap tm_v1, const __grid_constant__ CUtensorMap tm_d,
+                         const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_ret,
+                         const __grid_constant__ ScanArgs A, int n_tiles, int n_stages, int n_obufs) {
+  using C = StripCfg<OP, HD, COLS, RPU, NG>;
   extern __shared__ __align__(1024) unsigned char strip_raw[];  // (no integer casts: keeps the shared address space)
   unsigned char *stages = strip_raw;
-  float *ostage = reinterpret_cast<float *>(stages + C::kStages * C::kStage);
-  float2 *comp = reinterpret_cast<float2 *>(reinterpret_cast<unsigned char *>(ostage) + C::kOutBytes);
+  float *ostage = reinterpret_cast<float *>(stages + n_stages * C::kStage);
+  float2 *comp = reinterpret_cast<float2 *>(reinterpret_cast<unsigned char *>(ostage) + n_obufs * C::kOut1);
   uint64_t *full = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(comp) + C::kCompBytes);
-  uint64_t *empty = full + 8;
+  uint64_t *empty = full + kMaxStages;
+  uint64_t *cbar = empty + kMaxStages;  // [2]: carry into the tiles of each parity is published
+  float *carry = reinterpret_cast<float *>(comp + NG * 2 * C::kUnits * COLS);  // [2][COLS]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int col0 = blockIdx.x * COLS;
   const int T = (int)A.T;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < C::kStages; ++s) {
+    for (int s = 0; s < n_stages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], kWarps);
     }
+    mbar_init(&cbar[0], 1);
+    mbar_init(&cbar[1], 1);
     fence_async_smem();
   }
   __syncthreads();
 
-  if (warp == kWarps) {  // ---- producer ----
+  if (warp == NG * kWarps) {  // ---- producer ----
     if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 1;  // parity of the previous use of the stage
 #pragma unroll 1
       for (int k = 0; k < n_tiles; ++k) {
-        const int s = k % C::kStages;
-        if (k >= C::kStages) mbar_wait(&empty[s], (uint32_t)((k / C::kStages - 1) & 1));
+        if (k >= n_stages) mbar_wait(&empty[s], ph);
         unsigned char *sb = stages + s * C::kStage;
         const int row0 = (n_tiles - 1 - k) * C::kRows;  // the first tile may reach past T: zero-filled
         mbar_expect_tx(&full[s], C::kTx);
         tma_load_2d(sb, &tm_a, col0, row0, &full[s]);
         if (OP != OP_DR) tma_load_2d(sb + C::kOffV, &tm_v, col0, row0, &full[s]);
+        // V of the first step after the tile (a box may have at most 256 rows, so it travels alone)
+        if (OP == OP_GAE) tma_load_2d(sb + C::kOffV + C::kRows * COLS * 4, &tm_v1, col0, row0 + C::kRows, &full[s]);
         if (HD) tma_load_2d(sb + C::kOffD, &tm_d, col0, row0, &full[s]);
+        if (++s == n_stages) s = 0, ph ^= 1u;
       }
     }
     return;
@@ -150,7 +185,8 @@ __global__ void __launch_bounds__(kThreads)
 
   // ---- consumers ----
   const int c = lane % COLS, h = lane / COLS;
-  const int unit = warp * C::kUPW + h;
+  const int grp = warp / kWarps, wl = warp % kWarps;
+  const int unit = wl * C::kUPW + h;
   const int col = col0 + c;
   float X = 0.0f, lastv = 0.0f;
   if (col < A.N && A.last) {
@@ -159,41 +195,41 @@ __global__ void __launch_bounds__(kThreads)
     else X = l;
   }
   const bool want_ret = OP == OP_GAE && A.ret != nullptr;
-  float *my_out = ostage + warp * (2 * C::kNOut * C::kWarpOut);
+  float *my_out = ostage + warp * (n_obufs * C::kNOut * C::kWarpOut);
+  int s = grp;  // (n_stages >= 2 >= NG)
+  uint32_t ph = 0;
 
 #pragma unroll 1
-  for (int k = 0; k < n_tiles; ++k) {
-    const int s = k % C::kStages;
-    mbar_wait(&full[s], (uint32_t)((k / C::kStages) & 1));
+  for (int k = grp; k < n_tiles; k += NG) {
+    mbar_wait(&full[s], ph);
     const unsigned char *sb = stages + s * C::kStage;
-    const int e0 = unit * ST_RPU * COLS + c;  // first element of this lane's column piece
-    float ea[ST_RPU], eb[ST_RPU], aux[ST_RPU];
+    const int e0 = unit * RPU * COLS + c;  // first element of this lane's column piece
+    float ea[RPU], eb[RPU], aux[RPU];
     {
-      float r[ST_RPU], vv[ST_RPU + 1];
-      unsigned char dd[ST_RPU];
+      float r[RPU], vv[RPU + 1];
+      unsigned char dd[RPU];
       const float *sa = reinterpret_cast<const float *>(sb) + e0;
 #pragma unroll
-      for (int i = 0; i < ST_RPU; ++i) r[i] = sa[i * COLS];
+      for (int i = 0; i < RPU; ++i) r[i] = sa[i * COLS];
       if (OP != OP_DR) {
         const float *sv = reinterpret_cast<const float *>(sb + C::kOffV) + e0;
 #pragma unroll
-        for (int i = 0; i < ST_RPU + (OP == OP_GAE ? 1 : 0); ++i) vv[i] = sv[i * COLS];
+        for (int i = 0; i < RPU + (OP == OP_GAE ? 1 : 0); ++i) vv[i] = sv[i * COLS];
       }
       if (HD) {
         const unsigned char *sd = sb + C::kOffD + e0;
 #pragma unroll
-        for (int i = 0; i < ST_RPU; ++i) dd[i] = sd[i * COLS];
+        for (int i = 0; i < RPU; ++i) dd[i] = sd[i * COLS];
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[s]);
-      const int g0 = (n_tiles - 1 - k) * C::kRows + unit * ST_RPU;  // global step of this lane's first row
+      release_stage(&empty[s], lane);
+      const int g0 = (n_tiles - 1 - k) * C::kRows + unit * RPU;  // global step of this lane's first row
       if (OP == OP_GAE && k == 0) {  // row T (zero-filled by the DMA) is the bootstrap value
 #pragma unroll
-        for (int i = 0; i < ST_RPU; ++i)
+        for (int i = 0; i < RPU; ++i)
           if (g0 + i + 1 == T) vv[i + 1] = lastv;
       }
 #pragma unroll
-      for (int i = 0; i < ST_RPU; ++i) {
+      for (int i = 0; i < RPU; ++i) {
         if (OP == OP_AFFINE) {
           ea[i] = r[i], eb[i] = vv[i], aux[i] = 0.0f;
         } else {
@@ -210,53 +246,75 @@ __global__ void __launch_bounds__(kThreads)
       }
       if (k == 0) {  // steps past T in the first tile: identity maps
 #pragma unroll
-        for (int i = 0; i < ST_RPU; ++i)
+        for (int i = 0; i < RPU; ++i)
           if (g0 + i >= T) ea[i] = 0.0f, eb[i] = 1.0f;
       }
     }
     // this piece as one affine map x[first step] = ca + cb * x[first step after the piece]
     float ca = 0.0f, cb = 1.0f;
 #pragma unroll
-    for (int i = ST_RPU - 1; i >= 0; --i) {
-      ca = scan_step(ea[i], eb[i], ca);
+    for (int i = RPU - 1; i >= 0; --i) {
+      ca = fstep(ea[i], eb[i], ca);
       cb = __fmul_rn(eb[i], cb);
     }
-    float2 *cbuf = comp + (k & 1) * (C::kUnits * COLS);
+    float2 *cbuf = comp + (grp * 2 + ((k / NG) & 1)) * (C::kUnits * COLS);
     cbuf[unit * COLS + c] = make_float2(ca, cb);
-    consumer_barrier();
+    if (NG == 1 || grp == 0) consumer_barrier<1>();
+    else consumer_barrier<2>();
+    if (NG == 2 && k > 0) {  // the other group has chained tile k-1
+      mbar_wait(&cbar[k & 1], (uint32_t)(((k >> 1) - (1 - (k & 1))) & 1));
+      X = carry[(k & 1) * COLS + c];
+    }
     float x = X, xin = X;
 #pragma unroll
     for (int u = C::kUnits - 1; u >= 0; --u) {
       if (u == unit) xin = x;
       const float2 m = cbuf[u * COLS + c];
-      x = scan_step(m.x, m.y, x);
+      x = fstep(m.x, m.y, x);
     }
     X = x;
+    if (NG == 2 && wl == 0 && k + 1 < n_tiles) {
+      if (h == 0) carry[((k + 1) & 1) * COLS + c] = x;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&cbar[(k + 1) & 1]);
+    }
 
     // replay, stage, store
-    float *oa = my_out + (k & 1) * (C::kNOut * C::kWarpOut);
-    if (lane == 0) bulk_wait_read<1>();  // the store issued from this buffer two tiles ago has been read
+    float *oa = my_out + (n_obufs == 2 ? ((k / NG) & 1) : 0) * (C::kNOut * C::kWarpOut);
+    if (lane == 0) {  // the last store issued from this buffer has been read
+      if (n_obufs == 2) bulk_wait_read<1>();
+      else bulk_wait_read<0>();
+    }
     __syncwarp();
     x = xin;
 #pragma unroll
-    for (int i = ST_RPU - 1; i >= 0; --i) {
-      x = scan_step(ea[i], eb[i], x);
-      oa[(h * ST_RPU + i) * COLS + c] = x;
-      if (want_ret) oa[C::kWarpOut + (h * ST_RPU + i) * COLS + c] = __fadd_rn(x, aux[i]);
+    for (int i = RPU - 1; i >= 0; --i) {
+      x = fstep(ea[i], eb[i], x);
+      oa[(h * RPU + i) * COLS + c] = x;
+      if (want_ret) oa[C::kWarpOut + (h * RPU + i) * COLS + c] = __fadd_rn(x, aux[i]);
     }
     fence_async_smem();
     __syncwarp();
     if (lane == 0) {
-      const int row = (n_tiles - 1 - k) * C::kRows + warp * (ST_RPU * C::kUPW);
+      const int row = (n_tiles - 1 - k) * C::kRows + wl * C::kWarpRows;
       if (row < T) {  // rows past T are clipped by the tensor map
         tma_store_2d(&tm_out, col0, row, oa);
         if (want_ret) tma_store_2d(&tm_ret, col0, row, oa + C::kWarpOut);
       }
       bulk_commit();
     }
+    s += NG;
+    if (s >= n_stages) s -= n_stages, ph ^= 1u;
   }
   if (lane == 0) bulk_wait_all();
 }
+
+}  // namespace
+int64_t g_strip_stages = 0;  // 0 = as many as fit; else an upper bound (for experiments)
+int64_t g_strip_groups = 0;  // consumer groups per CTA: 0 = auto, 1, 2
+int64_t g_row_ctas_per_sm = 4;  // batch-major rows: resident CTAs per SM the ring depth is sized for
+int64_t g_row_stages = 0;       // 0 = from g_row_ctas_per_sm
+namespace {
 
 // ---- host: tensor maps ------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -299,40 +357,53 @@ bool make_map(CUtensorMap *m, const void *base, bool is_u8, int64_t rows, int64_
 
 bool al16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-template <int OP, bool HD, int COLS>
+template <int OP, bool HD, int COLS, int RPU, int NG>
 int strip_launch(const ScanArgs &A, cudaStream_t st) {
-  using C = StripCfg<OP, HD, COLS>;
-  CUtensorMap ma, mv, md, mo, mr;
+  using C = StripCfg<OP, HD, COLS, RPU, NG>;
+  static_assert(C::kRows <= 256 && C::smem_bytes(2, 1) <= (NG == 1 ? 111 : 225) * 1024, "tile too large");
+  CUtensorMap ma, mv, mv1, md, mo, mr;
   if (!make_map(&ma, A.a, false, A.T, A.N, COLS, C::kRows)) return kScanNotApplicable;
-  mv = ma, md = ma;
-  if (OP != OP_DR && !make_map(&mv, A.v, false, A.T, A.N, COLS, C::kVRows)) return kScanNotApplicable;
+  mv = ma, mv1 = ma, md = ma;
+  if (OP != OP_DR && !make_map(&mv, A.v, false, A.T, A.N, COLS, C::kRows)) return kScanNotApplicable;
+  if (OP == OP_GAE && !make_map(&mv1, A.v, false, A.T, A.N, COLS, 1)) return kScanNotApplicable;
   if (HD && !make_map(&md, A.done, true, A.T, A.N, COLS, C::kRows)) return kScanNotApplicable;
-  if (!make_map(&mo, A.out, false, A.T, A.N, COLS, ST_RPU * C::kUPW)) return kScanNotApplicable;
+  if (!make_map(&mo, A.out, false, A.T, A.N, COLS, C::kWarpRows)) return kScanNotApplicable;
   mr = mo;
-  if (OP == OP_GAE && A.ret && !make_map(&mr, A.ret, false, A.T, A.N, COLS, ST_RPU * C::kUPW))
+  if (OP == OP_GAE && A.ret && !make_map(&mr, A.ret, false, A.T, A.N, COLS, C::kWarpRows))
     return kScanNotApplicable;
   static bool configured = false;
   if (!configured) {
-    MRL_CUDA(cudaFuncSetAttribute(scan_tm_strip_kernel<OP, HD, COLS>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
+    MRL_CUDA(cudaFuncSetAttribute(scan_tm_strip_kernel<OP, HD, COLS, RPU, NG>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     configured = true;
   }
   const int64_t n_strips = (A.N + COLS - 1) / COLS;
   const int n_tiles = (int)((A.T + C::kRows - 1) / C::kRows);
-  scan_tm_strip_kernel<OP, HD, COLS><<<(unsigned)n_strips, kThreads, C::kSmem, st>>>(ma, mv, md, mo, mr, A,
-                                                                                      n_tiles);
+  const int budget = ((NG == 2 || n_strips <= kNumSM) ? 226 : 112) * 1024 - 1024;
+  int obufs = 2, stages = (budget - C::smem_bytes(0, 2)) / C::kStage;
+  if (stages < 3) obufs = 1, stages = (budget - C::smem_bytes(0, 1)) / C::kStage;
+  stages = stages > kMaxStages ? kMaxStages : stages;
+  stages = stages > n_tiles ? (n_tiles < 2 ? 2 : n_tiles) : stages;
+  if (g_strip_stages > 0 && g_strip_stages < stages) stages = (int)(g_strip_stages < 2 ? 2 : g_strip_stages);
+  scan_tm_strip_kernel<OP, HD, COLS, RPU, NG><<<(unsigned)n_strips, C::kThreads, C::smem_bytes(stages, obufs), st>>>(
+      ma, mv, mv1, md, mo, mr, A, n_tiles, stages, obufs);
   return MRL_OK;
 }
 
 template <int OP, bool HD>
-int strip_launch_cols(const ScanArgs &A, int cols, cudaStream_t st) {
-  if (cols == 16) return strip_launch<OP, HD, 16>(A, st);
-  return strip_launch<OP, HD, 32>(A, st);
+int strip_launch_cols(const ScanArgs &A, int cols, int rpu, cudaStream_t st) {
+  // two consumer groups per CTA: opt-in (measured equal to one group at 4096 x 2048: once the ring is
+  // deep enough the strips are bound by HBM, not by the consumers' dependent chain)
+  const bool two = g_strip_groups == 2;
+  if (cols == 32 && rpu == 16 && two) return strip_launch<OP, HD, 32, 16, 2>(A, st);
+  if (cols == 16) return rpu == 16 ? strip_launch<OP, HD, 16, 16, 1>(A, st) : strip_launch<OP, HD, 16, 8, 1>(A, st);
+  return rpu == 16 ? strip_launch<OP, HD, 32, 16, 1>(A, st) : strip_launch<OP, HD, 32, 8, 1>(A, st);
 }
 
 }  // namespace
 
 int64_t g_strip_cols = 0;     // 0 = auto, 16, 32
+int64_t g_strip_rpu = 0;      // steps per lane and tile: 0 = auto, 8, 16
 int64_t g_strip_min_cols = 2048;  // auto: narrower batches keep the look-back kernels (time-parallel)
 
 // Time-major [T, N], E == 1.  Needs 16-byte aligned bases and row pitches (N % 4 == 0; N % 16 == 0 with
@@ -345,11 +416,14 @@ int scan_tm_strip_launch(const ScanArgs &A, int op, bool force, cudaStream_t st)
   const bool hd = op != OP_AFFINE && A.done != nullptr;
   if (hd && (A.N % 16 != 0 || !al16(A.done))) return kScanNotApplicable;
   if (!force && (A.N < g_strip_min_cols || A.T < 64)) return kScanNotApplicable;
-  int cols = (int)g_strip_cols;
+  int cols = (int)g_strip_cols, rpu = (int)g_strip_rpu;
   if (cols == 0) cols = 32;
-  if (op == OP_DR) return hd ? strip_launch_cols<OP_DR, true>(A, cols, st) : strip_launch_cols<OP_DR, false>(A, cols, st);
-  if (op == OP_GAE) return hd ? strip_launch_cols<OP_GAE, true>(A, cols, st) : strip_launch_cols<OP_GAE, false>(A, cols, st);
-  return strip_launch_cols<OP_AFFINE, false>(A, cols, st);
+  if (rpu == 0) rpu = 16;
+  if (op == OP_DR)
+    return hd ? strip_launch_cols<OP_DR, true>(A, cols, rpu, st) : strip_launch_cols<OP_DR, false>(A, cols, rpu, st);
+  if (op == OP_GAE)
+    return hd ? strip_launch_cols<OP_GAE, true>(A, cols, rpu, st) : strip_launch_cols<OP_GAE, false>(A, cols, rpu, st);
+  return strip_launch_cols<OP_AFFINE, false>(A, cols, rpu, st);
 }
 
 // =============================================================================================
@@ -363,7 +437,7 @@ int scan_tm_strip_launch(const ScanArgs &A, int op, bool force, cudaStream_t st)
 namespace {
 
 constexpr int BM_L = 2048;
-constexpr int BM_SUB = 16;  // sub-tiles per tile
+constexpr int BM_SUB = 8;   // 256-step pieces per tile, one per warp
 
 template <int OP, bool HD, bool NVF>
 struct RowCfg {
@@ -372,23 +446,24 @@ struct RowCfg {
   static constexpr int kOffD = kOffNV + (NVF ? BM_L * 4 : 0);
   static constexpr int kStage = kOffD + (HD ? BM_L : 0);
   static constexpr int kNOut = OP == OP_GAE ? 2 : 1;
-  static constexpr int kStages = OP == OP_DR ? 6 : (NVF ? 3 : 4);
   static constexpr int kWarpOut = BM_L / kWarps;  // 256 floats
   static constexpr int kOutBytes = kWarps * 2 * kNOut * kWarpOut * 4;
   static constexpr int kCompBytes = 2 * BM_SUB * 8;
-  static constexpr int kSmem = kStages * kStage + kOutBytes + kCompBytes + 2 * 8 * 8 + 128;
+  static constexpr int smem_bytes(int stages) {
+    return stages * kStage + kOutBytes + kCompBytes + 2 * kMaxStages * 8;
+  }
 };
 
 template <int OP, bool HD, bool NVF>
 __global__ void __launch_bounds__(kThreads)
-    scan_bm_row_kernel(const __grid_constant__ ScanArgs A, int n_chunks) {
+    scan_bm_row_kernel(const __grid_constant__ ScanArgs A, int n_chunks, int n_stages) {
   using C = RowCfg<OP, HD, NVF>;
   extern __shared__ __align__(1024) unsigned char row_raw[];
   unsigned char *stages = row_raw;
-  float *ostage = reinterpret_cast<float *>(stages + C::kStages * C::kStage);
+  float *ostage = reinterpret_cast<float *>(stages + n_stages * C::kStage);
   float2 *comp = reinterpret_cast<float2 *>(reinterpret_cast<unsigned char *>(ostage) + C::kOutBytes);
   uint64_t *full = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(comp) + C::kCompBytes);
-  uint64_t *empty = full + 8;
+  uint64_t *empty = full + kMaxStages;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t T = A.T;
   const int64_t G = gridDim.x;
@@ -396,7 +471,7 @@ __global__ void __launch_bounds__(kThreads)
   const int64_t n_items = n_rows * n_chunks;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < C::kStages; ++s) {
+    for (int s = 0; s < n_stages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], kWarps);
     }
@@ -408,10 +483,11 @@ __global__ void __launch_bounds__(kThreads)
     if (lane == 0) {
       int64_t row = blockIdx.x;
       int c = 0;
+      int s = 0;
+      uint32_t ph = 1;  // parity of the previous use of the stage
 #pragma unroll 1
       for (int64_t k = 0; k < n_items; ++k) {
-        const int s = (int)(k % C::kStages);
-        if (k >= C::kStages) mbar_wait(&empty[s], (uint32_t)((k / C::kStages - 1) & 1));
+        if (k >= n_stages) mbar_wait(&empty[s], ph);
         unsigned char *sb = stages + s * C::kStage;
         const int64_t t_end = T - (int64_t)c * BM_L;
         const int64_t t_begin = t_end > BM_L ? t_end - BM_L : 0;
@@ -423,12 +499,14 @@ __global__ void __launch_bounds__(kThreads)
         if (NVF) bulk_load(sb + C::kOffNV, A.nv + off, len * 4u, &full[s]);
         if (HD) bulk_load(sb + C::kOffD, A.done + off, len, &full[s]);
         if (++c == n_chunks) c = 0, row += G;
+        if (++s == n_stages) s = 0, ph ^= 1u;
       }
     }
     return;
   }
 
   // ---- consumers ----
+  // warp w owns positions [256w, 256w+256) of the tile, lane l the 8 consecutive steps 256w+8l..+7
   constexpr unsigned FULL = 0xffffffffu;
   const bool want_ret = OP == OP_GAE && A.ret != nullptr;
   const bool use_last = A.last != nullptr && !(OP == OP_GAE && NVF);
@@ -437,10 +515,12 @@ __global__ void __launch_bounds__(kThreads)
   float last_next = (use_last && n_rows > 0) ? __ldg(A.last + blockIdx.x) : 0.0f;
   int64_t row = blockIdx.x;
   int c = 0;
+  const int p0 = warp * 256 + 8 * lane;
+  int s = 0;
+  uint32_t ph = 0;
 
 #pragma unroll 1
   for (int64_t k = 0; k < n_items; ++k) {
-    const int s = (int)(k % C::kStages);
     const int64_t t_end = T - (int64_t)c * BM_L;
     const int64_t t_begin = t_end > BM_L ? t_end - BM_L : 0;
     const int len = (int)(t_end - t_begin);
@@ -449,96 +529,92 @@ __global__ void __launch_bounds__(kThreads)
       v_after = OP == OP_GAE ? last_next : 0.0f;
       last_next = (use_last && row + G < A.N) ? __ldg(A.last + row + G) : 0.0f;
     }
-    mbar_wait(&full[s], (uint32_t)((k / C::kStages) & 1));
+    mbar_wait(&full[s], ph);
     const unsigned char *sb = stages + s * C::kStage;
-    float ea[2][4], eb[2][4], aux[2][4];
+    float ea[8], eb[8], aux[8];
     float v_first = 0.0f;
     {
-      float4 r[2], vv[2], nn[2];
-      uint32_t dd[2] = {0u, 0u};
-      float edge[2] = {0.0f, 0.0f};
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int p0 = (2 * warp + j) * 128 + 4 * lane;
-        r[j] = *reinterpret_cast<const float4 *>(sb + 4 * p0);
-        if (OP != OP_DR) vv[j] = *reinterpret_cast<const float4 *>(sb + C::kOffV + 4 * p0);
-        if (NVF) nn[j] = *reinterpret_cast<const float4 *>(sb + C::kOffNV + 4 * p0);
-        if (HD) dd[j] = *reinterpret_cast<const uint32_t *>(sb + C::kOffD + p0);
-        if (OP == OP_GAE && !NVF && lane == 31) edge[j] = *reinterpret_cast<const float *>(sb + C::kOffV + 4 * (p0 + 4));
+      float rr[8], vq[9], nq[8];
+      uint2 dd = make_uint2(0u, 0u);
+      float edge = 0.0f;
+      {
+        const float4 r0 = *reinterpret_cast<const float4 *>(sb + 4 * p0);
+        const float4 r1 = *reinterpret_cast<const float4 *>(sb + 4 * p0 + 16);
+        rr[0] = r0.x, rr[1] = r0.y, rr[2] = r0.z, rr[3] = r0.w, rr[4] = r1.x, rr[5] = r1.y, rr[6] = r1.z, rr[7] = r1.w;
       }
-      if (OP == OP_GAE && !NVF) v_first = *reinterpret_cast<const float *>(sb + C::kOffV);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[s]);
+      if (OP != OP_DR) {
+        const float4 v0 = *reinterpret_cast<const float4 *>(sb + C::kOffV + 4 * p0);
+        const float4 v1 = *reinterpret_cast<const float4 *>(sb + C::kOffV + 4 * p0 + 16);
+        vq[0] = v0.x, vq[1] = v0.y, vq[2] = v0.z, vq[3] = v0.w, vq[4] = v1.x, vq[5] = v1.y, vq[6] = v1.z, vq[7] = v1.w;
+      }
+      if (NVF) {
+        const float4 n0 = *reinterpret_cast<const float4 *>(sb + C::kOffNV + 4 * p0);
+        const float4 n1 = *reinterpret_cast<const float4 *>(sb + C::kOffNV + 4 * p0 + 16);
+        nq[0] = n0.x, nq[1] = n0.y, nq[2] = n0.z, nq[3] = n0.w, nq[4] = n1.x, nq[5] = n1.y, nq[6] = n1.z, nq[7] = n1.w;
+      }
+      if (HD) dd = *reinterpret_cast<const uint2 *>(sb + C::kOffD + p0);
+      if (OP == OP_GAE && !NVF) {
+        if (lane == 31) edge = *reinterpret_cast<const float *>(sb + C::kOffV + 4 * (p0 + 8));
+        v_first = *reinterpret_cast<const float *>(sb + C::kOffV);
+      }
+      release_stage(&empty[s], lane);
+      const bool whole = len == BM_L;  // (block-uniform) no step of the tile lies past the chunk
+      if (OP == OP_GAE && !NVF) {
+        const float nb = __shfl_down_sync(FULL, vq[0], 1);
+        vq[8] = lane == 31 ? edge : nb;
+        if (p0 + 8 >= len) vq[8] = v_after;  // the chunk ends inside or right after this lane's run
+        if (!whole) {
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int p0 = (2 * warp + j) * 128 + 4 * lane;
-        const float rr[4] = {r[j].x, r[j].y, r[j].z, r[j].w};
-        float vq[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-        float nq[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-        if (OP != OP_DR) vq[0] = vv[j].x, vq[1] = vv[j].y, vq[2] = vv[j].z, vq[3] = vv[j].w;
-        if (NVF) nq[0] = nn[j].x, nq[1] = nn[j].y, nq[2] = nn[j].z, nq[3] = nn[j].w;
-        if (OP == OP_GAE && !NVF) {
-          const float nb = __shfl_down_sync(FULL, vq[0], 1);
-          vq[4] = lane == 31 ? edge[j] : nb;
-          if (p0 + 4 >= len) vq[4] = v_after;  // the chunk ends inside or right after this quad
+          for (int q = 1; q < 8; ++q)
+            if (p0 + q >= len) vq[q] = v_after;  // only read as V[t+1] of the last valid step
         }
+      }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          if (OP == OP_AFFINE) {
-            ea[j][q] = rr[q], eb[j][q] = vq[q], aux[j][q] = 0.0f;
+      for (int q = 0; q < 8; ++q) {
+        if (OP == OP_AFFINE) {
+          ea[q] = rr[q], eb[q] = vq[q], aux[q] = 0.0f;
+        } else {
+          const bool dn = HD && (((q < 4 ? dd.x : dd.y) >> (8 * (q & 3))) & 0xffu) != 0u;
+          if (OP == OP_DR) {
+            ea[q] = rr[q], eb[q] = dn ? 0.0f : A.gamma, aux[q] = 0.0f;
           } else {
-            const float m = HD ? (((dd[j] >> (8 * q)) & 0xffu) ? 0.0f : 1.0f) : 1.0f;
-            if (OP == OP_DR) {
-              ea[j][q] = rr[q], eb[j][q] = __fmul_rn(m, A.gamma), aux[j][q] = 0.0f;
-            } else {
-              float nvq = NVF ? nq[q] : vq[q + 1];
-              if (!NVF && q < 3 && p0 + q + 1 >= len) nvq = v_after;
-              const float gvm = __fmul_rn(__fmul_rn(A.gamma, nvq), m);
-              ea[j][q] = __fsub_rn(__fadd_rn(rr[q], gvm), vq[q]);
-              eb[j][q] = __fmul_rn(A.gl, m);
-              aux[j][q] = vq[q];
-            }
+            const float gv = __fmul_rn(A.gamma, NVF ? nq[q] : vq[q + 1]);
+            ea[q] = __fsub_rn(__fadd_rn(rr[q], dn ? 0.0f : gv), vq[q]);
+            eb[q] = dn ? 0.0f : A.gl;
+            aux[q] = vq[q];
           }
-          if (p0 + q >= len) ea[j][q] = 0.0f, eb[j][q] = 1.0f;  // past the chunk: identity map
         }
+      }
+      if (!whole) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (p0 + q >= len) ea[q] = 0.0f, eb[q] = 1.0f;  // past the chunk: identity map
       }
     }
-    // per lane: 4 steps as one map; per sub-tile: suffix scan over lanes (later time = higher lane)
-    float ca[2], cb[2];
+    // per lane: 8 steps as one map; then a suffix scan over the lanes (later time = higher lane)
+    float ca = 0.0f, cb = 1.0f;
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      ca[j] = 0.0f, cb[j] = 1.0f;
-#pragma unroll
-      for (int q = 3; q >= 0; --q) {
-        ca[j] = scan_step(ea[j][q], eb[j][q], ca[j]);
-        cb[j] = __fmul_rn(eb[j][q], cb[j]);
-      }
+    for (int q = 7; q >= 0; --q) {
+      ca = fstep(ea[q], eb[q], ca);
+      cb = __fmul_rn(eb[q], cb);
     }
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const float oa_ = __shfl_down_sync(FULL, ca[j], off);
-        const float ob_ = __shfl_down_sync(FULL, cb[j], off);
-        if (lane + off < 32) {
-          ca[j] = scan_step(ca[j], cb[j], oa_);
-          cb[j] = __fmul_rn(cb[j], ob_);
-        }
-      }
+      float oa_ = __shfl_down_sync(FULL, ca, off);
+      float ob_ = __shfl_down_sync(FULL, cb, off);
+      if (lane + off >= 32) oa_ = 0.0f, ob_ = 1.0f;  // identity beyond the last lane
+      ca = fstep(ca, cb, oa_);
+      cb = __fmul_rn(cb, ob_);
     }
     float2 *cbuf = comp + (k & 1) * BM_SUB;
-    if (lane == 0) {
-      cbuf[2 * warp] = make_float2(ca[0], cb[0]);
-      cbuf[2 * warp + 1] = make_float2(ca[1], cb[1]);
-    }
+    if (lane == 0) cbuf[warp] = make_float2(ca, cb);
     consumer_barrier();
-    float x = X, xin[2] = {X, X};
+    float x = X, xin = X;
 #pragma unroll
-    for (int u = BM_SUB - 1; u >= 0; --u) {
-      if (u == 2 * warp + 1) xin[1] = x;
-      if (u == 2 * warp) xin[0] = x;
+    for (int u = kWarps - 1; u >= 0; --u) {
+      if (u == warp) xin = x;
       const float2 m = cbuf[u];
-      x = scan_step(m.x, m.y, x);
+      x = fstep(m.x, m.y, x);
     }
     X = x;
     if (OP == OP_GAE && !NVF) v_after = v_first;
@@ -546,21 +622,25 @@ __global__ void __launch_bounds__(kThreads)
     float *oa = my_out + (k & 1) * (C::kNOut * C::kWarpOut);
     if (lane == 0) bulk_wait_read<1>();
     __syncwarp();
+    {
+      const float x_here = fstep(ca, cb, xin);            // x at this lane's first step
+      float xe = __shfl_down_sync(FULL, x_here, 1);       // x right after this lane's run
+      if (lane == 31) xe = xin;
+      float o[8], o2[8];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const float x_here = scan_step(ca[j], cb[j], xin[j]);  // x at this lane's first step
-      float xe = __shfl_down_sync(FULL, x_here, 1);          // x right after this lane's quad
-      if (lane == 31) xe = xin[j];
-      float o[4], o2[4];
-#pragma unroll
-      for (int q = 3; q >= 0; --q) {
-        xe = scan_step(ea[j][q], eb[j][q], xe);
+      for (int q = 7; q >= 0; --q) {
+        xe = fstep(ea[q], eb[q], xe);
         o[q] = xe;
-        o2[q] = __fadd_rn(xe, aux[j][q]);
+        o2[q] = __fadd_rn(xe, aux[q]);
       }
-      *reinterpret_cast<float4 *>(oa + j * 128 + 4 * lane) = make_float4(o[0], o[1], o[2], o[3]);
-      if (want_ret)
-        *reinterpret_cast<float4 *>(oa + C::kWarpOut + j * 128 + 4 * lane) = make_float4(o2[0], o2[1], o2[2], o2[3]);
+      float4 *dst = reinterpret_cast<float4 *>(oa + 8 * lane);
+      dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+      dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+      if (want_ret) {
+        float4 *dst2 = reinterpret_cast<float4 *>(oa + C::kWarpOut + 8 * lane);
+        dst2[0] = make_float4(o2[0], o2[1], o2[2], o2[3]);
+        dst2[1] = make_float4(o2[4], o2[5], o2[6], o2[7]);
+      }
     }
     fence_async_smem();
     __syncwarp();
@@ -575,6 +655,7 @@ __global__ void __launch_bounds__(kThreads)
       bulk_commit();
     }
     if (++c == n_chunks) c = 0, row += G;
+    if (++s == n_stages) s = 0, ph ^= 1u;
   }
   if (lane == 0) bulk_wait_all();
 }
@@ -585,15 +666,23 @@ int row_launch(const ScanArgs &A, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
     MRL_CUDA(cudaFuncSetAttribute(scan_bm_row_kernel<OP, HD, NVF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  C::kSmem));
+                                  C::smem_bytes(kMaxStages) < 226 * 1024 ? C::smem_bytes(kMaxStages) : 226 * 1024));
     configured = true;
   }
   const int n_chunks = (int)((A.T + BM_L - 1) / BM_L);
-  // as many CTAs as fit at once (2 per SM), trimmed so that every CTA gets the same number of rows
-  int64_t max_ctas = (int64_t)kNumSM * (227 * 1024 / (C::kSmem + 1024));
+  // ring depth: the SM's shared memory split between g_row_ctas_per_sm resident CTAs
+  const int per_sm = (int)g_row_ctas_per_sm;
+  int stages = ((227 * 1024) / per_sm - 1024 - C::smem_bytes(0)) / C::kStage;
+  stages = stages > kMaxStages ? kMaxStages : (stages < 2 ? 2 : stages);
+  if (g_row_stages > 0) stages = (int)(g_row_stages < 2 ? 2 : g_row_stages);
+  const int smem = C::smem_bytes(stages);
+  // as many CTAs as fit at once, trimmed so that every CTA gets the same number of rows
+  int fit = (227 * 1024) / (smem + 1024);
+  fit = fit > 7 ? 7 : (fit < 1 ? 1 : fit);  // 2048 threads per SM / 288
+  const int64_t max_ctas = (int64_t)kNumSM * fit;
   const int64_t per = (A.N + max_ctas - 1) / max_ctas;
   const int64_t ctas = (A.N + per - 1) / per;
-  scan_bm_row_kernel<OP, HD, NVF><<<(unsigned)ctas, kThreads, C::kSmem, st>>>(A, n_chunks);
+  scan_bm_row_kernel<OP, HD, NVF><<<(unsigned)ctas, kThreads, smem, st>>>(A, n_chunks, stages);
   return MRL_OK;
 }
 

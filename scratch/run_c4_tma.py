@@ -13,6 +13,7 @@ adv = torch.empty((T, B), device="cuda"); ret = torch.empty((T, B), device="cuda
 p = lambda x: x.data_ptr()
 cols = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 _ffi.set_option("tm_kernel", 6); _ffi.set_option("strip_cols", cols); _ffi.set_option("bm_kernel", 2)
+_ffi.set_option("strip_rpu", int(sys.argv[2]) if len(sys.argv) > 2 else 16)
 for _ in range(2):
     _ffi.check(L.mrl_gae(p(r), p(v), None, p(v[T]), p(d), p(adv), p(ret), T, B, 0.99, 0.95, 0, 0, 0))
     _ffi.check(L.mrl_discounted_return(p(r), p(d), p(v[T]), p(adv), T, B, 1, 0.99, 0, 0, 0))

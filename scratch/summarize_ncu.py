@@ -55,10 +55,24 @@ def launches(csvpath, tag):
 if __name__ == "__main__":
     g = os.path.join(ROOT, "gpurun_out")
     for rep, tag in [("prof_c2_r1.ncu-rep", "r1_ncu_full_c2_per_kernels"), ("prof_c3_r1.ncu-rep", "r1_ncu_full_c3_per_kernels"),
-                     ("prof_c4_r1.ncu-rep", "r1_ncu_full_c4_scan_kernels"), ("prof_scan_r1e.ncu-rep", "r1_ncu_full_wtile_before_fastpath")]:
+                     ("prof_c4_r1.ncu-rep", "r1_ncu_full_c4_scan_kernels"),
+                     ("prof_c4_r1b.ncu-rep", "r1_ncu_full_c4_tma_scan_kernels"), ("prof_scan_r1e.ncu-rep", "r1_ncu_full_wtile_before_fastpath")]:
         p = os.path.join(g, rep)
         if os.path.exists(p):
             for d in report(p, tag):
                 print(tag, d["kernel"][:60], d["gpu__time_duration.sum"], d.get("gpu__time_duration.sum_unit"), round(d["dram_traffic_bytes"] / 1e6, 2), "MB")
+    # per-launch traffic of the TMA scan kernels -> profiles/r1_traffic.json (bench.py's roofline.traffic)
+    tp = os.path.join(OUT, "r1_traffic.json")
+    tj = os.path.join(OUT, "r1_ncu_full_c4_tma_scan_kernels.json")
+    if os.path.exists(tp) and os.path.exists(tj):
+        t = json.load(open(tp))
+        for d in json.load(open(tj)):
+            name = d["kernel"].split("::")[-1].split("(")[0]
+            t["c4:" + name] = {"ncu_duration_us": round(d["gpu__time_duration.sum"], 2),
+                               "dram_traffic_bytes": int(d["dram_traffic_bytes"]),
+                               "dram_read_bytes": int(d["dram__bytes_read.sum"]),
+                               "dram_write_bytes": int(d["dram__bytes_write.sum"]), "launches_captured": 1,
+                               "source": "profiles/r1_ncu_full_c4_tma_scan_kernels.json (ncu --set full --clock-control none; cold caches, serialised)"}
+        json.dump(t, open(tp, "w"), indent=1)
     if os.path.exists(os.path.join(g, "launches_r1.csv")):
         launches(os.path.join(g, "launches_r1.csv"), "r1_launch_list_bench_steps20")

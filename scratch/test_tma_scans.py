@@ -22,9 +22,11 @@ def close(got, want, what):
         print("FAIL", what, "err", err, "tol", tol, "first bad", bad[:3].tolist(), flush=True)
 
 
-def parity_tm(cols):
+def parity_tm(cols, rpu=8, groups=1):
     _ffi.set_option("tm_kernel", 6)
+    _ffi.set_option("strip_groups", groups)
     _ffi.set_option("strip_cols", cols)
+    _ffi.set_option("strip_rpu", rpu)
     for T, B in [(1, 16), (5, 16), (64, 32), (65, 48), (127, 80), (128, 64), (300, 4112), (1000, 96), (2048, 128),
                  (513, 36), (77, 4)]:
         rng = np.random.default_rng(T * 7 + B)
@@ -56,6 +58,8 @@ def parity_tm(cols):
         close(M.affine_scan(dev(r), dev(b), dev(lv), layout="time_major", mode="parallel"), ref, f"tm{cols} affine T{T} B{B}")
     _ffi.set_option("tm_kernel", 0)
     _ffi.set_option("strip_cols", 0)
+    _ffi.set_option("strip_rpu", 0)
+    _ffi.set_option("strip_groups", 0)
 
 
 def parity_bm():
@@ -88,51 +92,63 @@ def parity_bm():
     _ffi.set_option("bm_kernel", 0)
 
 
-def timeit(fn, iters=30):
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    for _ in range(3):
-        fn()
+def timeit(fns, reps=10):
+    """fns: the same call on different buffer sets (rotated so that nothing is reused out of L2);
+    back-to-back launches inside one event pair -> average device time per launch"""
+    for f in fns:
+        f()
     torch.cuda.synchronize()
-    ts = []
-    for _ in range(iters):
-        flush.fill_(1)
-        flush.sum()
+    best = 1e9
+    for _ in range(3):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        fn()
+        for _ in range(reps):
+            for f in fns:
+                f()
         e1.record()
         torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1) * 1e3)
-    ts.sort()
-    return round(ts[len(ts) // 2], 2), round(ts[0], 2)
+        best = min(best, e0.elapsed_time(e1) * 1e3 / (reps * len(fns)))
+    return round(best, 2)
 
 
 def timing():
     L = _ffi.lib()
     T, B = 2048, 4096
     g = torch.Generator(device="cuda"); g.manual_seed(4)
-    r = torch.randn((T, B), device="cuda", generator=g)
-    v = torch.randn((T + 1, B), device="cuda", generator=g)
-    d = (torch.rand((T, B), device="cuda", generator=g) < 1 / 200).to(torch.uint8)
-    adv = torch.empty((T, B), device="cuda"); ret = torch.empty((T, B), device="cuda")
     p = lambda x: x.data_ptr()
-    gae_tm = lambda: L.mrl_gae(p(r), p(v), None, p(v[T]), p(d), p(adv), p(ret), T, B, 0.99, 0.95, 0, 0, 0)
-    dr_tm = lambda: L.mrl_discounted_return(p(r), p(d), p(v[T]), p(adv), T, B, 1, 0.99, 0, 0, 0)
-    gae_bm = lambda: L.mrl_gae(p(r), p(v), None, p(v[T]), p(d), p(adv), p(ret), 2048, 4096, 0.99, 0.95, 1, 0, 0)
-    dr_bm = lambda: L.mrl_discounted_return(p(r), p(d), p(v[T]), p(adv), 2048, 4096, 1, 0.99, 1, 0, 0)
+    sets = []
+    for i in range(5):
+        r = torch.randn((T, B), device="cuda", generator=g)
+        v = torch.randn((T + 1, B), device="cuda", generator=g)
+        d = (torch.rand((T, B), device="cuda", generator=g) < 1 / 200).to(torch.uint8)
+        adv = torch.empty((T, B), device="cuda"); ret = torch.empty((T, B), device="cuda")
+        sets.append((r, v, d, adv, ret))
+    mk = lambda f: [(lambda s=s: f(*s)) for s in sets]
+    gae_tm = mk(lambda r, v, d, adv, ret: L.mrl_gae(p(r), p(v), None, p(v[T]), p(d), p(adv), p(ret), T, B, 0.99, 0.95, 0, 0, 0))
+    dr_tm = mk(lambda r, v, d, adv, ret: L.mrl_discounted_return(p(r), p(d), p(v[T]), p(adv), T, B, 1, 0.99, 0, 0, 0))
+    gae_bm = mk(lambda r, v, d, adv, ret: L.mrl_gae(p(r), p(v), None, p(v[T]), p(d), p(adv), p(ret), 2048, 4096, 0.99, 0.95, 1, 0, 0))
+    dr_bm = mk(lambda r, v, d, adv, ret: L.mrl_discounted_return(p(r), p(d), p(v[T]), p(adv), 2048, 4096, 1, 0.99, 1, 0, 0))
     res = {}
-    for name, opts in [("tm_strip32", {"tm_kernel": 6, "strip_cols": 32}), ("tm_strip16", {"tm_kernel": 6, "strip_cols": 16}),
+    base = {"tm_kernel": 6, "strip_cols": 32, "strip_rpu": 16, "strip_groups": 0, "strip_stages": 0, "strip_min_cols": 2048}
+    for name, opts in [("tm_strip32x16_g2", {"strip_groups": 2}), ("tm_strip32x16_g2_s3", {"strip_groups": 2, "strip_stages": 3}),
+                       ("tm_strip32x16_g2_s4", {"strip_groups": 2, "strip_stages": 4}),
+                       ("tm_strip32x16_g1", {"strip_groups": 1}), ("tm_strip32x16_g1_s3", {"strip_groups": 1, "strip_stages": 3}),
+                       ("tm_strip32x8", {"strip_rpu": 8}), ("tm_strip16x8", {"strip_cols": 16, "strip_rpu": 8}),
+                       ("tm_strip16x16", {"strip_cols": 16}),
                        ("tm_pipe", {"tm_kernel": 0, "strip_min_cols": 1 << 40})]:
-        for k_, v_ in opts.items():
+        o = dict(base); o.update(opts)
+        for k_, v_ in o.items():
             _ffi.set_option(k_, v_)
         res[name] = {"gae": timeit(gae_tm), "dr": timeit(dr_tm)}
         print(name, res[name], flush=True)
-    _ffi.set_option("tm_kernel", 0); _ffi.set_option("strip_min_cols", 2048); _ffi.set_option("strip_cols", 0)
-    for name, mode in [("bm_row", 2), ("bm_warp", 1)]:
+    for k_, v_ in base.items():
+        _ffi.set_option(k_, 0 if k_ != "strip_min_cols" else 2048)
+    for name, mode, per_sm in [("bm_row_1", 2, 1), ("bm_row_2", 2, 2), ("bm_row_3", 2, 3), ("bm_row_4", 2, 4), ("bm_row_5", 2, 5), ("bm_warp", 1, 3)]:
         _ffi.set_option("bm_kernel", mode)
+        _ffi.set_option("row_ctas_per_sm", per_sm)
         res[name] = {"gae": timeit(gae_bm), "dr": timeit(dr_bm)}
         print(name, res[name], flush=True)
-    _ffi.set_option("bm_kernel", 0)
+    _ffi.set_option("bm_kernel", 0); _ffi.set_option("row_ctas_per_sm", 3)
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(res, open("gpurun_out/tma_scan_timing.json", "w"), indent=1)
 
@@ -140,8 +156,10 @@ def timing():
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("all", "parity"):
-        parity_tm(32); print("tm32 done", fails, flush=True)
-        parity_tm(16); print("tm16 done", fails, flush=True)
+        parity_tm(32, 16, 2); print("tm 32 16 g2 done", fails, flush=True)
+        for cols in (32, 16):
+            for rpu in (8, 16):
+                parity_tm(cols, rpu); print("tm", cols, rpu, "done", fails, flush=True)
         parity_bm(); print("bm done", fails, flush=True)
     if what in ("all", "timing"):
         timing()

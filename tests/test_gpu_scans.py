@@ -253,3 +253,120 @@ def test_normalize_advantage(n):
         assert abs(got.astype(np.float64).mean()) < 1e-4 and abs(got.astype(np.float64).std() - 1) < 1e-3
     again = M.normalize_advantage(dev(x)).cpu().numpy()
     assert np.array_equal(got, again)  # fixed accumulation order
+
+
+# ---- TMA-ring kernels (scan_tma.cu), forced through the library options ------------------------
+class _options:
+    """sets library options for the duration of a test and restores the defaults afterwards"""
+    DEFAULTS = {"tm_kernel": 0, "strip_cols": 0, "strip_rpu": 0, "strip_groups": 0, "strip_stages": 0,
+                "bm_kernel": 0, "row_stages": 0}
+
+    def __init__(self, **kw):
+        self.kw = kw
+
+    def __enter__(self):
+        from mindrl_b200 import _ffi
+        for k, v in self.kw.items():
+            _ffi.set_option(k, v)
+
+    def __exit__(self, *exc):
+        from mindrl_b200 import _ffi
+        for k in self.kw:
+            _ffi.set_option(k, self.DEFAULTS[k])
+
+
+TM_SHAPES = [(1, 16), (5, 16), (64, 32), (65, 48), (127, 80), (128, 64), (300, 4112), (1000, 96), (2048, 128),
+             (513, 36), (77, 4)]
+
+
+@pytest.mark.parametrize("cols,rpu,groups,stages", [(32, 16, 1, 0), (32, 16, 2, 0), (32, 16, 1, 2), (32, 8, 1, 0),
+                                                    (16, 8, 1, 0), (16, 16, 1, 2)])
+def test_tma_strip_kernels(cols, rpu, groups, stages):
+    """time-major strips: ragged T (partial first tile), ragged N (clipped last strip), bootstrap row,
+    with and without done flags, every recurrence; ring depth 2 forces stage reuse on the small shapes"""
+    with _options(tm_kernel=6, strip_cols=cols, strip_rpu=rpu, strip_groups=groups, strip_stages=stages):
+        for T, B in TM_SHAPES:
+            rng = np.random.default_rng(T * 7 + B)
+            r = rng.normal(size=(T, B)).astype(np.float32)
+            val = rng.normal(size=(T + 1, B)).astype(np.float32)
+            lv = rng.normal(size=(B,)).astype(np.float32)
+            vd = dev(val)
+            for with_done in (False, True):
+                if with_done and B % 16:
+                    continue  # (falls back to the register kernels: covered by test_gae_time_major)
+                d = (rng.random((T, B)) < 0.05) if with_done else None
+                dd = None if d is None else dev(d)
+                adv_r, ret_r = O.gae(r, val[:T], None, val[T], d, 0.99, 0.95, layout=0)
+                adv, ret = M.gae(dev(r), vd[:T], 0.99, 0.95, last_value=vd[T], done=dd, mode="parallel")
+                close(adv, adv_r)
+                close(ret, ret_r)
+                adv_r, _ = O.gae(r, val[:T], None, None, d, 0.99, 0.95, layout=0)
+                adv, ret = M.gae(dev(r), vd[:T], 0.99, 0.95, done=dd, mode="parallel", want_returns=False)
+                assert ret is None
+                close(adv, adv_r)
+                if with_done:
+                    close(M.DiscountedReturn(0.99, mode="parallel")(dev(r), dd, dev(lv)), O.discounted_return(r, d, lv, 0.99))
+                else:
+                    close(M.discounted_reward(dev(r), 0.99, last_value=dev(lv), layout="time_major", mode="parallel"),
+                          O.discounted_return(r, None, lv, 0.99))
+                    close(M.discounted_reward(dev(r), 0.9, layout="time_major", mode="parallel"),
+                          O.discounted_return(r, None, None, 0.9))
+            b = rng.uniform(0.0, 1.0, size=(T, B)).astype(np.float32)
+            close(M.affine_scan(dev(r), dev(b), dev(lv), layout="time_major", mode="parallel"),
+                  O.affine_scan(r, b, lv, layout=0))
+
+
+@pytest.mark.parametrize("stages", [0, 2, 3])
+def test_tma_row_kernel(stages):
+    """batch-major rows: several chunks per environment, a partial last chunk, T below one tile"""
+    with _options(bm_kernel=2, row_stages=stages):
+        for B, T in [(1, 4), (3, 16), (7, 128), (30, 1000), (17, 144), (64, 2048), (5, 4096), (9, 2064), (2, 4112),
+                     (300, 512), (3, 6160), (8, 16384)]:
+            rng = np.random.default_rng(B * 1009 + T)
+            r = rng.normal(size=(B, T)).astype(np.float32)
+            v = rng.normal(size=(B, T)).astype(np.float32)
+            nv = rng.normal(size=(B, T)).astype(np.float32)
+            lv = rng.normal(size=(B,)).astype(np.float32)
+            for with_done in (False, True):
+                if with_done and T % 16:
+                    continue
+                d = (rng.random((B, T)) < 0.05) if with_done else None
+                dd = None if d is None else dev(d)
+                close(M.discounted_reward(dev(r), 0.99, last_value=dev(lv), done=dd),
+                      O.discounted_return(r, d, lv, 0.99, layout=1))
+                adv_r, ret_r = O.gae(r, v, None, lv, d, 0.99, 0.95, layout=1)
+                adv, ret = M.gae(dev(r), dev(v), 0.99, 0.95, last_value=dev(lv), done=dd, layout="batch_major")
+                close(adv, adv_r)
+                close(ret, ret_r)
+                adv_r, ret_r = O.gae(r, v, nv, None, d, 0.99, 0.95, layout=1)
+                adv, ret = M.gae(dev(r), dev(v), 0.99, 0.95, next_value=dev(nv), done=dd, layout="batch_major")
+                close(adv, adv_r)
+                close(ret, ret_r)
+            b = rng.uniform(0.0, 1.0, size=(B, T)).astype(np.float32)
+            close(M.affine_scan(dev(r), dev(b), dev(lv), layout="batch_major"), O.affine_scan(r, b, lv, layout=1))
+
+
+@pytest.mark.parametrize("layout", ["time_major", "batch_major"])
+def test_tma_ring_reuse_identity(layout):
+    """gamma = 0 turns GAE into adv[t] = r[t] - V[t] = r[t] (V = 0), r = its own index: any element read out
+    of a stage the DMA is already refilling (or not yet filled) shows up as a wrong integer.  Ring depth 2,
+    many tiles per CTA, repeated with warm caches (the refill then lands fastest).  Guards the proxy fence
+    in release_stage()."""
+    if layout == "time_major":
+        T, B = 16384, 64
+        r = (torch.arange(T, device="cuda", dtype=torch.float32)[:, None] * 64
+             + torch.arange(B, device="cuda", dtype=torch.float32)[None, :]).contiguous()
+        opts = dict(tm_kernel=6, strip_stages=2)
+    else:
+        B, T = 16, 16384
+        r = (torch.arange(T, device="cuda", dtype=torch.float32)[None, :]
+             + 100000.0 * torch.arange(B, device="cuda", dtype=torch.float32)[:, None]).contiguous()
+        opts = dict(bm_kernel=2, row_stages=2)
+    z = torch.zeros_like(r)
+    with _options(**opts):
+        for _ in range(6):
+            adv, ret = M.gae(r, z, 0.0, 0.0, next_value=z if layout == "batch_major" else None, layout=layout,
+                             mode="parallel")
+            assert torch.equal(adv, r)
+            out = M.discounted_reward(r, 0.0, layout=layout, mode="parallel")
+            assert torch.equal(out, r)
