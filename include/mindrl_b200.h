@@ -106,6 +106,12 @@ int mrl_urb_columns(int64_t handle, void **col_ptrs_out);
  * FIFO overwrite when full. */
 int mrl_urb_append(int64_t handle, int64_t nrows, const void *const *src_cols, void *stream);
 int mrl_urb_append_host(int64_t handle, int64_t nrows, const void *const *src_cols, void *stream);
+/* Emplace of ReservoirReplayBufferPush (reservoir_replay_buffer.py:69-82): overwrite nrows rows at
+ * PHYSICAL slot `slot`; count and head do not move. */
+int mrl_urb_write_at(int64_t handle, int64_t slot, int64_t nrows, const void *const *src_cols,
+                     void *stream);
+int mrl_urb_write_at_host(int64_t handle, int64_t slot, int64_t nrows, const void *const *src_cols,
+                          void *stream);
 /* BufferGetItem (:128): row at LOGICAL position index (0 = oldest, negative = from the end) */
 int mrl_urb_get_item(int64_t handle, int64_t index, void *const *out_cols, void *stream);
 int mrl_urb_get_item_host(int64_t handle, int64_t index, void *const *out_cols, void *stream);

@@ -1,5 +1,6 @@
 from .priority_replay_buffer import PriorityReplayBuffer
+from .reservoir_replay_buffer import ReservoirReplayBuffer
 from .sharded_priority_replay_buffer import ShardedPriorityReplayBuffer
 from .uniform_replay_buffer import UniformReplayBuffer
 
-__all__ = ["UniformReplayBuffer", "PriorityReplayBuffer", "ShardedPriorityReplayBuffer"]
+__all__ = ["UniformReplayBuffer", "PriorityReplayBuffer", "ShardedPriorityReplayBuffer", "ReservoirReplayBuffer"]

@@ -270,6 +270,47 @@ extern "C" int mrl_urb_append_host(int64_t handle, int64_t nrows, const void *co
   return MRL_OK;
 }
 
+// Emplace of the reservoir buffer (reservoir_replay_buffer.py:69-82): overwrite the rows at PHYSICAL
+// slots slot..slot+nrows-1; the cursors do not move.
+extern "C" int mrl_urb_write_at(int64_t handle, int64_t slot, int64_t nrows, const void *const *src_cols,
+                                void *stream) {
+  URB_GET(b, handle);
+  MRL_REQUIRE(src_cols && nrows >= 1 && slot >= 0 && slot + nrows <= b->capacity,
+              "mrl_urb_write_at: rows [%lld, %lld) outside the buffer", (long long)slot, (long long)(slot + nrows));
+  ColTable tab;
+  fill_table(tab, b->ncols, b->cols, b->row_bytes, (void *const *)src_cols);
+  return copy_segments_dir(tab, slot, 0, nrows, 1, as_stream(stream));
+}
+
+extern "C" int mrl_urb_write_at_host(int64_t handle, int64_t slot, int64_t nrows, const void *const *src_cols,
+                                     void *stream) {
+  URB_GET(b, handle);
+  MRL_REQUIRE(src_cols && nrows >= 1 && slot >= 0 && slot + nrows <= b->capacity,
+              "mrl_urb_write_at_host: rows [%lld, %lld) outside the buffer", (long long)slot,
+              (long long)(slot + nrows));
+  cudaStream_t st = as_stream(stream);
+  size_t off[MRL_MAX_COLS + 1];
+  off[0] = 0;
+  for (int c = 0; c < b->ncols; ++c)
+    off[c + 1] = off[c] + ((size_t)nrows * b->row_bytes[c] + 255) / 256 * 256;
+  int rc = b->stage.wait();
+  if (rc) return rc;
+  rc = b->stage.ensure(off[b->ncols]);
+  if (rc) return rc;
+  void *src_dev[MRL_MAX_COLS];
+  for (int c = 0; c < b->ncols; ++c) {
+    memcpy(b->stage.host + off[c], src_cols[c], (size_t)nrows * b->row_bytes[c]);
+    src_dev[c] = b->stage.dev + off[c];
+  }
+  MRL_CUDA(cudaMemcpyAsync(b->stage.dev, b->stage.host, off[b->ncols], cudaMemcpyHostToDevice, st));
+  ColTable tab;
+  fill_table(tab, b->ncols, b->cols, b->row_bytes, src_dev);
+  rc = copy_segments_dir(tab, slot, 0, nrows, 1, st);
+  if (rc) return rc;
+  MRL_CUDA(cudaEventRecord(b->stage.done, st));
+  return MRL_OK;
+}
+
 extern "C" int mrl_urb_get_item(int64_t handle, int64_t index, void *const *out_cols,
                                 void *stream) {
   URB_GET(b, handle);

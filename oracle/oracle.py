@@ -174,6 +174,46 @@ class UniformBufferOracle:
         return c.value, h.value
 
 
+class ReservoirBufferOracle:
+    """reservoir_replay_buffer.py:61-100 restated in numpy (test infrastructure).  Vitter's algorithm R as the
+    docstring cites it (:27-31): rows 0..capacity-1 fill the reservoir in order; transition number `total`
+    (0-based) after that is kept with probability capacity / (total + 1) and then overwrites a uniformly
+    drawn slot.  sample(): min(sample_size, size) distinct rows.  Draw order: one U[0,1) per offered
+    transition once full, one integer per kept transition, one permutation per sample.  MindSpore's kernel
+    is not in /root/reference: parity unpinned, the distribution is what tests check."""
+
+    def __init__(self, capacity, sample_size, shapes, dtypes, seed0=0, seed1=0):
+        self.capacity, self.sample_size = int(capacity), int(sample_size)
+        self.shapes = [tuple(s) for s in shapes]
+        self.dtypes = [np.dtype(d) for d in dtypes]
+        self.cols = [np.zeros((self.capacity,) + s, dtype=d) for s, d in zip(self.shapes, self.dtypes)]
+        self.rng = np.random.Generator(np.random.PCG64([int(seed0), int(seed1)]))
+        self.total = 0
+
+    def push(self, *transition):
+        row = [np.asarray(t, dtype=d).reshape(s) for t, s, d in zip(transition, self.shapes, self.dtypes)]
+        if self.total < self.capacity:
+            slot = self.total
+        elif self.rng.random() < self.capacity / float(self.total + 1):
+            slot = int(self.rng.integers(0, self.capacity))
+        else:
+            slot = None
+        self.total += 1
+        if slot is not None:
+            for c, r in zip(self.cols, row):
+                c[slot] = r
+        return slot
+
+    def size(self):
+        return min(self.total, self.capacity)
+
+    def sample(self):
+        size = self.size()
+        n = min(self.sample_size, size)
+        slots = self.rng.permutation(size)[:n]
+        return slots, [c[slots] for c in self.cols]
+
+
 class PriorityBufferOracle:
     """priority_replay_buffer.py:60-138 on the CPU oracle."""
 

@@ -175,3 +175,48 @@ def test_n_step_buffer_and_checkpoint():
     for i in (0, 5, -1):
         for a, b in zip(g.get_item(i), h.get_item(i)):
             assert torch.equal(a, b)
+
+
+def test_reservoir_buffer_matches_oracle_and_reference_test():
+    """ReservoirReplayBuffer against its numpy oracle (same seeds -> same keep/replace decisions -> identical
+    columns and samples), plus the expectations of the reference's (skipped) test
+    tests/st/test_reservoir_replay_buffer.py:34-56."""
+    import ctypes as C
+    from mindrl_b200 import _ffi
+    cap, batch = 100, 256
+    shapes, dtypes = [(17,), (6,)], [np.float32, np.int32]
+    g = M.ReservoirReplayBuffer(cap, batch, shapes, dtypes, seed0=0, seed1=42)
+    o = O.ReservoirBufferOracle(cap, batch, shapes, dtypes, seed0=0, seed1=42)
+    for i in range(100):
+        g.push(dev(np.ones(17, np.float32) * i), dev(np.ones(6, np.int32) * i))
+        o.push(np.ones(17, np.float32) * i, np.ones(6, np.int32) * i)
+    states, actions = g.sample()
+    states, actions = states.cpu().numpy(), actions.cpu().numpy()
+    assert states.shape == (100, 17) and actions.shape == (100, 6)  # "variable-length": min(batch, size)
+    assert np.allclose(states, states[:, 0:1]) and np.allclose(actions, actions[:, 0:1])
+    assert np.allclose(states[:, 0], actions[:, 0])
+    slots, want = o.sample()
+    assert np.array_equal(g.last_slots, slots)
+    assert np.array_equal(states, want[0]) and np.array_equal(actions, want[1])
+    # past capacity: host and device inputs mixed, drops and replacements
+    for i in range(100, 1500):
+        s, a = np.ones(17, np.float32) * i, np.ones(6, np.int32) * i
+        if i % 3:
+            g.push(dev(s), dev(a))
+        else:
+            g.push(s, a)
+        o.push(s, a)
+    ptrs = (C.c_void_p * 2)()
+    _ffi.check(_ffi.lib().mrl_urb_columns(g._handle, ptrs))
+    got = np.empty((cap, 17), np.float32)
+    _ffi.check(_ffi.lib().mrl_memcpy_d2h(got.ctypes.data, ptrs[0], got.nbytes, 0))
+    _ffi.check(_ffi.lib().mrl_stream_sync(0))
+    assert np.array_equal(got, o.cols[0])
+    assert len(np.unique(got[:, 0])) == cap and got.max() > 100  # replaced rows, no duplicates
+    for _ in range(3):
+        states, actions = g.sample()
+        slots, want = o.sample()
+        assert np.array_equal(states.cpu().numpy(), want[0]) and np.array_equal(actions.cpu().numpy(), want[1])
+    with pytest.raises(ValueError):
+        g.push(dev(np.ones((2, 17), np.float32)), dev(np.ones((2, 6), np.int32)))
+    assert g.destroy()[0] > 0 and g.destroy()[0] == -1

@@ -317,3 +317,26 @@ def test_priority_sharded_weights():
     other = np.array([st[0] * 3, st[1] / 2, 64.0, 1.0], np.float32)
     i3, w3 = b.sample(0.5, uniforms=u, gather=False, gstats=np.stack([st, other]))
     assert np.array_equal(i1, i3) and not np.array_equal(w1, w3) and w3.max() <= 1.0
+
+
+def test_reservoir_oracle_keeps_an_unbiased_sample():
+    """Vitter's property the reference's docstring promises ("keeps an 'unbiased' sample of previous
+    iterations", reservoir_replay_buffer.py:27-31): after N offers every transition is in the reservoir with
+    probability capacity / N, whatever its age."""
+    cap, n_offers, trials = 20, 200, 600
+    hits = np.zeros(n_offers)
+    for trial in range(trials):
+        o = O.ReservoirBufferOracle(cap, 8, [(1,)], [np.int64], seed0=trial, seed1=7)
+        for i in range(n_offers):
+            o.push(np.asarray([i]))
+        hits[o.cols[0][:, 0]] += 1
+        assert len(set(o.cols[0][:, 0].tolist())) == cap  # distinct transitions
+    p = hits / trials
+    assert abs(p.mean() - cap / n_offers) < 1e-12
+    # thirds of the stream by age: each within 4 sigma of capacity / N
+    for part in np.array_split(p, 4):
+        sigma = np.sqrt((cap / n_offers) * (1 - cap / n_offers) / (trials * len(part)))
+        assert abs(part.mean() - cap / n_offers) < 4 * sigma + 1e-3
+    slots, cols = o.sample()
+    assert len(slots) == 8 and len(set(slots.tolist())) == 8
+    assert np.array_equal(cols[0], o.cols[0][slots])
