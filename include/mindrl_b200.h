@@ -131,6 +131,11 @@ int mrl_urb_reset(int64_t handle, void *stream);
 int mrl_urb_state(int64_t handle, int32_t *count, int32_t *head);
 int mrl_urb_set_state(int64_t handle, int32_t count, int32_t head);
 
+/* MSRL.get_replay_buffer_elements(transpose=True, shape=(1, 0, 2)) (core/msrl.py:535-557): swap the two
+ * leading axes of a column, out[b][a][:] = in[a][b][:], rows of row_bytes bytes.  (The scans take either
+ * layout, so a learner can also skip this pass: see mrl_gae / mrl_discounted_return `layout`.) */
+int mrl_transpose01(const void *in, void *out, int64_t A, int64_t B, int64_t row_bytes, void *stream);
+
 /* ---- PriorityReplayBuffer (priority_replay_buffer.py:60-138) ---------- */
 /* PriorityReplayBufferCreate(capacity, alpha, shapes, types, seed0, seed1) (:62-66) */
 int mrl_prb_create(int64_t capacity, float alpha, int32_t ncols, const int64_t *row_bytes,

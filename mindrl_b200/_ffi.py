@@ -40,6 +40,7 @@ SIGNATURES = {
     "mrl_urb_columns": [i64, vp],
     "mrl_urb_append": [i64, i64, vp, vp],
     "mrl_urb_append_host": [i64, i64, vp, vp],
+    "mrl_transpose01": [vp, vp, i64, i64, i64, vp],
     "mrl_urb_write_at": [i64, i64, i64, vp, vp],
     "mrl_urb_write_at_host": [i64, i64, i64, vp, vp],
     "mrl_urb_get_item": [i64, i64, vp, vp],

@@ -22,6 +22,29 @@ class _BufferAppend:
         return buffer
 
 
+def get_replay_buffer_elements(columns, transpose=False, shape=None):
+    """free-function form of MSRL.get_replay_buffer_elements (core/msrl.py:535-557) over a tuple of device
+    columns: identity, or the swap of the two leading axes (mrl_transpose01)."""
+    if not transpose:
+        return tuple(columns)
+    out = []
+    for e in columns:
+        dims = tuple(int(x) for x in e.shape)
+        perm = tuple(range(len(dims))) if shape is None else tuple(int(x) for x in shape)
+        if len(perm) != len(dims) or len(dims) < 2 or perm[:2] != (1, 0) or perm[2:] != tuple(range(2, len(dims))):
+            raise ValueError(f"get_replay_buffer_elements: permutation {shape} of a {len(dims)}-d column is not "
+                             "supported (only the swap of the two leading axes, e.g. (1, 0, 2))")
+        if K.is_torch(e) and not e.is_contiguous():
+            e = e.contiguous()
+        o = K.device_empty((dims[1], dims[0]) + dims[2:], (K.np_dtype(e.dtype) if K.is_torch(e) else e.dtype))
+        row_bytes = K.nbytes_of(e) // max(dims[0] * dims[1], 1)
+        if dims[0] * dims[1]:
+            _ffi.check(_ffi.lib().mrl_transpose01(e.data_ptr(), o.data_ptr(), dims[0], dims[1], row_bytes,
+                                                  K.current_stream()))
+        out.append(o)
+    return tuple(out)
+
+
 class UniformReplayBuffer:
     """FIFO ring of transition columns on the GPU.
 
@@ -120,6 +143,12 @@ class UniformReplayBuffer:
     def full(self):
         """count >= capacity as a bool array of shape (1,) (:162-172)"""
         return np.asarray([self.count >= self._capacity])
+
+    def get_replay_buffer_elements(self, transpose=False, shape=None):
+        """MSRL.get_replay_buffer_elements (core/msrl.py:535-557): every WHOLE column (all `capacity` rows);
+        with transpose=True, `shape` is the permutation -- the reference's callers all pass (1, 0, 2), i.e.
+        [T, env, d] -> [env, T, d] (ppo_trainer.py:70); permutations that move other axes are not supported."""
+        return get_replay_buffer_elements(self.buffer, transpose, shape)
 
     # -- checkpointing (not in the reference, which never saves its buffers: SURVEY.md section 5) ---
     def state_dict(self):

@@ -389,6 +389,60 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ---- swap of the two leading axes of a column: out[b][a][:] = in[a][b][:] -------------------
+// MSRL.get_replay_buffer_elements(transpose=True, shape=(1, 0, 2)) (core/msrl.py:535-557): every PPO
+// trainer turns its [T, env, d] columns into [env, T, d] this way before the [env, T] scans.
+// Elements of 1/2/4/8 bytes: 32 x 32 tiles through shared memory (both sides coalesced).  Wider rows:
+// one thread per aligned unit of the OUTPUT (coalesced stores, row-contiguous loads served by L2).
+template <typename T>
+__global__ void __launch_bounds__(256) transpose_tile_kernel(const T *__restrict__ in, T *__restrict__ out,
+                                                            int64_t A, int64_t B) {
+  __shared__ T tile[32][33];
+  const int64_t tiles_b = (B + 31) / 32;
+  const int64_t n_tiles = ((A + 31) / 32) * tiles_b;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int64_t a0 = (t / tiles_b) * 32, b0 = (t % tiles_b) * 32;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      const int64_t a = a0 + ty + j, b = b0 + tx;
+      if (a < A && b < B) tile[ty + j][tx] = in[a * B + b];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      const int64_t b = b0 + ty + j, a = a0 + tx;
+      if (a < A && b < B) out[b * A + a] = tile[tx][ty + j];
+    }
+    __syncthreads();
+  }
+}
+
+template <typename V>
+__global__ void __launch_bounds__(256) transpose_rows_kernel(const V *__restrict__ in, V *__restrict__ out,
+                                                            int64_t A, int64_t B, int64_t U) {
+  const int64_t total = A * B * U;
+  for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t u = o % U, ba = o / U;
+    const int64_t a = ba % A, b = ba / A;
+    out[o] = in[(a * B + b) * U + u];
+  }
+}
+
+template <typename T>
+static void launch_tile(const void *in, void *out, int64_t A, int64_t B, cudaStream_t st) {
+  const int64_t n_tiles = ((A + 31) / 32) * ((B + 31) / 32);
+  const int64_t grid = n_tiles < (int64_t)kNumSM * 8 ? n_tiles : (int64_t)kNumSM * 8;
+  transpose_tile_kernel<T><<<(unsigned)grid, 256, 0, st>>>((const T *)in, (T *)out, A, B);
+}
+template <typename V>
+static void launch_rows(const void *in, void *out, int64_t A, int64_t B, int64_t row_bytes, cudaStream_t st) {
+  const int64_t U = row_bytes / (int64_t)sizeof(V);
+  const int64_t blocks = (A * B * U + 255) / 256;
+  const int64_t grid = blocks < (int64_t)kNumSM * 16 ? blocks : (int64_t)kNumSM * 16;
+  transpose_rows_kernel<V><<<(unsigned)grid, 256, 0, st>>>((const V *)in, (V *)out, A, B, U);
+}
+
 }  // namespace mrl
 
 extern "C" int mrl_set_option(const char *key, int64_t value) {
@@ -397,6 +451,26 @@ extern "C" int mrl_set_option(const char *key, int64_t value) {
   if (rc) rc = mrl::set_scan_option(key, value);
   if (rc) mrl::set_error("mrl_set_option: unknown key or value out of range: %s=%lld", key, (long long)value);
   return rc;
+}
+
+extern "C" int mrl_transpose01(const void *in, void *out, int64_t A, int64_t B, int64_t row_bytes,
+                               void *stream) {
+  MRL_REQUIRE(A >= 0 && B >= 0 && row_bytes > 0, "mrl_transpose01: bad shape");
+  if (A == 0 || B == 0) return MRL_OK;
+  MRL_REQUIRE(in && out && in != out, "mrl_transpose01: need distinct input and output");
+  cudaStream_t st = mrl::as_stream(stream);
+  const uintptr_t al = (uintptr_t)in | (uintptr_t)out | (uintptr_t)row_bytes;
+  if (row_bytes == 8 && al % 8 == 0) mrl::launch_tile<uint64_t>(in, out, A, B, st);
+  else if (row_bytes == 4 && al % 4 == 0) mrl::launch_tile<uint32_t>(in, out, A, B, st);
+  else if (row_bytes == 2 && al % 2 == 0) mrl::launch_tile<uint16_t>(in, out, A, B, st);
+  else if (row_bytes == 1) mrl::launch_tile<uint8_t>(in, out, A, B, st);
+  else if (al % 16 == 0) mrl::launch_rows<uint4>(in, out, A, B, row_bytes, st);
+  else if (al % 8 == 0) mrl::launch_rows<uint2>(in, out, A, B, row_bytes, st);
+  else if (al % 4 == 0) mrl::launch_rows<uint32_t>(in, out, A, B, row_bytes, st);
+  else if (al % 2 == 0) mrl::launch_rows<uint16_t>(in, out, A, B, row_bytes, st);
+  else mrl::launch_rows<uint8_t>(in, out, A, B, row_bytes, st);
+  MRL_LAUNCHED();
+  return MRL_OK;
 }
 
 extern "C" int mrl_fill_rows(void *col, int64_t nrows, int64_t row_bytes, uint64_t seed,

@@ -220,3 +220,41 @@ def test_reservoir_buffer_matches_oracle_and_reference_test():
     with pytest.raises(ValueError):
         g.push(dev(np.ones((2, 17), np.float32)), dev(np.ones((2, 6), np.int32)))
     assert g.destroy()[0] > 0 and g.destroy()[0] == -1
+
+
+@pytest.mark.parametrize("A,B,inner,dtype", [(1000, 30, (17,), np.float32), (1000, 30, (1,), np.float32),
+                                             (1000, 30, (), np.float32), (33, 65, (6,), np.int32), (7, 5, (3,), np.uint8),
+                                             (64, 64, (), np.float64), (100, 31, (), np.bool_), (50, 20, (5,), np.float16),
+                                             (2048, 4096, (), np.float32), (1, 9, (4,), np.int64)])
+def test_get_replay_buffer_elements_transpose(A, B, inner, dtype):
+    """MSRL.get_replay_buffer_elements(transpose=True, shape=(1, 0, 2)) (core/msrl.py:535-557): bit-exact
+    swap of the leading axes for every row width the kernels dispatch on"""
+    rng = np.random.default_rng(A * 31 + B)
+    x = (rng.integers(0, 200, size=(A, B) + inner)).astype(dtype)
+    perm = (1, 0) + tuple(range(2, 2 + len(inner)))
+    (got,) = M.get_replay_buffer_elements((dev(x),), transpose=True, shape=perm)
+    assert tuple(got.shape) == (B, A) + inner
+    assert np.array_equal(got.cpu().numpy(), np.transpose(x, perm))
+    (same,) = M.get_replay_buffer_elements((dev(x),))
+    assert np.array_equal(same.cpu().numpy(), x)
+    if inner:
+        with pytest.raises(ValueError):
+            M.get_replay_buffer_elements((dev(x),), transpose=True, shape=(0, 2, 1)[:2 + len(inner)] if len(inner) == 1 else (1, 0))
+
+
+def test_buffer_elements_feed_the_scans_without_a_transpose():
+    """the PPO path (ppo_trainer.py:70 -> ppo.py:320-350): columns [T, env, 1] are transposed to [env, T, 1] and
+    scanned batch-major; scanning the untransposed column time-major gives the same numbers, transposed"""
+    T, env = 1000, 32
+    ub = M.UniformReplayBuffer(1, T, [(env, 1), (env, 1)], [np.float32, np.float32])
+    rng = np.random.default_rng(5)
+    r = rng.normal(size=(T, env, 1)).astype(np.float32)
+    v = rng.normal(size=(T, env, 1)).astype(np.float32)
+    ub.insert([dev(r), dev(v)])
+    rt, vt = ub.get_replay_buffer_elements(transpose=True, shape=(1, 0, 2))
+    assert tuple(rt.shape) == (env, T, 1)
+    want = O.discounted_return(r[:, :, 0].T.copy(), None, None, 0.99, layout=1)
+    a = M.discounted_reward(rt.reshape(env, T), 0.99, layout="batch_major").cpu().numpy()
+    b = M.discounted_reward(ub.buffer[0].reshape(T, env), 0.99, layout="time_major").cpu().numpy()
+    tol = 1e-5 * max(1.0, float(np.abs(want).max()))
+    assert np.abs(a - want).max() <= tol and np.abs(b.T - want).max() <= tol
