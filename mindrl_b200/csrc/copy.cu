@@ -289,11 +289,16 @@ static int64_t g_bulk_chunk = env_i64("MRL_BULK_CHUNK", 8192);
 static int64_t g_bulk_ctas_per_sm = env_i64("MRL_BULK_CTAS_PER_SM", 4);
 
 extern long long *g_debug_timers;  // prb.cu
+extern bool g_no_inline_update;    // prb.cu
 
 int set_copy_option(const char *key, int64_t value) {
   std::string k(key);
   if (k == "debug_timers") {
     g_debug_timers = reinterpret_cast<long long *>(value);
+    return MRL_OK;
+  }
+  if (k == "inline_update" && (value == 0 || value == 1)) {
+    g_no_inline_update = value == 0;
     return MRL_OK;
   }
   if (k == "gather_path" && value >= 0 && value <= 2) g_gather_path = value;

@@ -571,7 +571,18 @@ constexpr int kSubThreads = 512;
 constexpr int kSubMaxLocal = kSubThreads;  // indices scanned per pass = most entries a CTA can keep
 constexpr int kSubDenseAt = 128;            // a share larger than this is rebuilt subtree by subtree
 
-__global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __grid_constant__ UpdateArgs U) {
+// INL: the batch travels in the kernel's own parameter block (InlineBatch, 2 KB) instead of device
+// memory -- the *_host entry point then needs no host-to-device copy, no staging buffer and no event
+// for a learner-sized batch; every CTA moves it from the constant bank to shared memory first.
+constexpr int kInlineMax = 256;
+struct InlineBatch {
+  int32_t idx[kInlineMax];
+  float pr[kInlineMax];
+};
+
+template <bool INL>
+__global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __grid_constant__ UpdateArgs U,
+                                                                     const __grid_constant__ InlineBatch IB) {
   __shared__ float ssum[2 << kTopLevels];
   __shared__ float smin[2 << kTopLevels];
   __shared__ int s_raw[4 * kSubMaxLocal];  // sparse: entry lists; dense: per-leaf winner table
@@ -581,7 +592,15 @@ __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __gri
   int *s_k = s_raw;                                                 // batch position of each entry
   uint32_t *s_node = reinterpret_cast<uint32_t *>(s_raw + kSubMaxLocal);
   float2 *s_val = reinterpret_cast<float2 *>(s_raw + 2 * kSubMaxLocal);
+  __shared__ int32_t s_in_idx[INL ? kInlineMax : 1];
+  __shared__ float s_in_pr[INL ? kInlineMax : 1];
   const int tid = threadIdx.x, nthr = blockDim.x;
+  if (INL) {
+    for (int i = tid; i < (int)U.n; i += nthr) s_in_idx[i] = IB.idx[i], s_in_pr[i] = IB.pr[i];
+    __syncthreads();
+  }
+  auto ld_idx = [&](int64_t k) -> int64_t { return INL ? (int64_t)s_in_idx[k] : __ldg(U.indices + k); };
+  auto ld_pr = [&](int64_t k) -> float { return INL ? s_in_pr[k] : __ldg(U.priorities + k); };
   const int G = (int)gridDim.x;  // a power of two (128..512): the ownership tests are masks
   // max_priority takes every processed priority (also those a later duplicate overwrites); every
   // entry is owned by exactly one CTA, which evaluates p**alpha for it anyway
@@ -599,7 +618,7 @@ __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __gri
     // one scan: count this CTA's share, note its dirty subtrees, and optimistically build the entry list
     unsigned int dirty = 0u;
     for (int64_t k = tid; k < U.n; k += nthr) {
-      const int top = (int)(__ldg(U.indices + k) >> nlev);
+      const int top = (int)(ld_idx(k) >> nlev);
       if ((top & (G - 1)) == (int)blockIdx.x) {
         dirty |= 1u << ((top / G) & 31);
         const int pos = atomicAdd(&s_cnt, 1);
@@ -629,10 +648,10 @@ __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __gri
       for (int i = tid; i < S; i += nthr) win[i] = 0;
       __syncthreads();
       for (int64_t k = tid; k < U.n; k += nthr) {
-        const int64_t leaf = __ldg(U.indices + k);
+        const int64_t leaf = ld_idx(k);
         if ((leaf >> nlev) == sub) {
           atomicMax(&win[leaf - leaf0], (int)k + 1);
-          const float p = prb_pow_fn(__ldg(U.priorities + k), U.alpha);
+          const float p = prb_pow_fn(ld_pr(k), U.alpha);
           local_max = p > local_max ? p : local_max;
         }
       }
@@ -641,7 +660,7 @@ __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __gri
         const int wk = win[i];
         float vs, vm;
         if (wk) {
-          vs = vm = prb_pow_fn(__ldg(U.priorities + (wk - 1)), U.alpha);
+          vs = vm = prb_pow_fn(ld_pr(wk - 1), U.alpha);
           __stcg(U.sum + U.cap2 + leaf0 + i, vs);
           __stcg(U.mn + U.cap2 + leaf0 + i, vm);
         } else {
@@ -679,7 +698,7 @@ __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __gri
       constexpr unsigned FULL = 0xffffffffu;
       const bool on = tid < total_mine;
       const int k = on ? s_k[tid] : -1;
-      const int64_t leaf = on ? __ldg(U.indices + k) : 0;
+      const int64_t leaf = on ? ld_idx(k) : 0;
       const uint32_t leaf_node = (uint32_t)(U.cap2 + leaf);
       float p = 0.0f;
       float sib_s[kWalkLevels], sib_m[kWalkLevels];
@@ -693,7 +712,7 @@ __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __gri
         }
       }
       if (on) {
-        p = prb_pow_fn(__ldg(U.priorities + k), U.alpha);
+        p = prb_pow_fn(ld_pr(k), U.alpha);
         local_max = p > local_max ? p : local_max;
       }
       const uint32_t lkey = on ? leaf_node : (0x80000000u | (uint32_t)tid);
@@ -742,7 +761,7 @@ __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __gri
         if (tid == 0) s_cnt = 0;
         __syncthreads();
         for (int64_t k = base + tid; k < end; k += nthr) {
-          const int top = (int)(__ldg(U.indices + k) >> nlev);
+          const int top = (int)(ld_idx(k) >> nlev);
           if ((top & (G - 1)) == (int)blockIdx.x) s_k[atomicAdd(&s_cnt, 1)] = (int)(k - base);
         }
         __syncthreads();
@@ -751,7 +770,7 @@ __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __gri
       const int j = tid;
       const bool on = j < m;
       const int64_t k = on ? base + s_k[j] : 0;
-      const int64_t leaf = on ? __ldg(U.indices + k) : 0;
+      const int64_t leaf = on ? ld_idx(k) : 0;
       const uint32_t leaf_node = (uint32_t)(U.cap2 + leaf);
       float p = 0.0f;
       float sib_s[kWalkLevels], sib_m[kWalkLevels];
@@ -765,7 +784,7 @@ __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __gri
             sib_m[d] = __ldcg(U.mn + sn);
           }
         }
-        p = prb_pow_fn(__ldg(U.priorities + k), U.alpha);
+        p = prb_pow_fn(ld_pr(k), U.alpha);
         local_max = p > local_max ? p : local_max;
       }
       // leaf level: among entries of the same leaf the highest batch position provides the value
@@ -1132,8 +1151,15 @@ static int prb_sample_impl(PrbBuffer *b, int64_t n, float beta, const float *uni
 // 2 = one-CTA global-tag level-synchronous kernel (MRL_UPDATE_PATH=tags; measured 18 us at n=256)
 static int g_update_path = -1;
 
+static bool update_takes_inline(const PrbBuffer *b, int64_t n) {
+  return n <= kInlineMax && g_update_path <= 0 && b->levels - kTopLevels <= kWalkLevels && b->levels > kTopLevels &&
+         b->cap2 < (1LL << 31);
+}
+
+bool g_no_inline_update = false;  // option "inline_update" = 0: always stage through device memory
+
 static int prb_update_impl(PrbBuffer *b, const int64_t *indices, const float *priorities,
-                           int64_t n, cudaStream_t st) {
+                           int64_t n, cudaStream_t st, const InlineBatch *inl = nullptr) {
   if (g_update_path < 0) {
     const char *e = getenv("MRL_UPDATE_PATH");
     g_update_path = (e && e[0] == 'w') ? 1 : ((e && e[0] == 't') ? 2 : 0);
@@ -1161,7 +1187,9 @@ static int prb_update_impl(PrbBuffer *b, const int64_t *indices, const float *pr
              n < (1LL << 31)) {
     int ctas = kSubCtas;  // 128..512 so that a CTA's share stays within one warp (~n/ctas entries)
     while (ctas < 512 && n > 8 * (int64_t)ctas) ctas <<= 1;
-    prb_update_sub_kernel<<<ctas, kSubThreads, 0, st>>>(U);
+    static const InlineBatch none = {};
+    if (inl) prb_update_sub_kernel<true><<<ctas, kSubThreads, 0, st>>>(U, *inl);
+    else prb_update_sub_kernel<false><<<ctas, kSubThreads, 0, st>>>(U, none);
   } else {
     prb_update_kernel<<<1, 1024, 0, st>>>(U);
   }
@@ -1414,6 +1442,22 @@ extern "C" int mrl_prb_update_host(int64_t handle, const int64_t *indices,
   MRL_REQUIRE(n >= 0 && (n == 0 || (indices && priorities)), "mrl_prb_update_host: bad arguments");
   if (n == 0) return MRL_OK;
   cudaStream_t st = as_stream(stream);
+  if (g_update_path < 0) {
+    const char *e = getenv("MRL_UPDATE_PATH");
+    g_update_path = (e && e[0] == 'w') ? 1 : ((e && e[0] == 't') ? 2 : 0);
+  }
+  if (update_takes_inline(b, n) && !g_no_inline_update) {
+    // learner-sized batch: it rides in the launch itself (no copy, no staging, the caller's arrays are free
+    // again when this returns)
+    InlineBatch ib;
+    bool fits = true;
+    for (int64_t i = 0; i < n; ++i) {
+      fits = fits && indices[i] >= 0 && indices[i] < (1LL << 31);
+      ib.idx[i] = (int32_t)indices[i];
+      ib.pr[i] = priorities[i];
+    }
+    if (fits) return prb_update_impl(b, nullptr, nullptr, n, st, &ib);
+  }
   const size_t o_p = (size_t)n * 8, total = o_p + (size_t)n * 4;
   int rc = b->stage.wait();
   if (rc) return rc;

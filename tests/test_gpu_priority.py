@@ -251,3 +251,39 @@ def test_checkpoint_round_trip():
     gs, gm = g.tree()
     hs, hm = h.tree()
     assert np.array_equal(gs[1:], hs[1:]) and np.array_equal(gm[1:], hm[1:])
+
+
+@pytest.mark.parametrize("batch", [1, 37, 256, 300])
+def test_host_update_inline_batch_matches_staged_and_oracle(batch):
+    """mrl_prb_update_host: batches of <= 256 ride in the kernel's parameter block (no copy); larger ones
+    and inline_update=0 stage through device memory.  Same tree either way, duplicates and clamped
+    priorities included, bit-exact against the oracle."""
+    from mindrl_b200 import _ffi
+    rng = np.random.default_rng(batch)
+    cap = 70000  # 2^17 leaves: the subtree-partitioned kernel
+    shapes, types = [(2,)], [np.float32]
+    bufs = [M.PriorityReplayBuffer(0.6, cap, batch, shapes, types, 3, 4, carrier="numpy") for _ in range(2)]
+    o = O.PriorityBufferOracle(0.6, cap, batch, shapes, types, 3, 4)
+    rows = [rng.normal(size=(cap, 2)).astype(np.float32)]
+    for g in bufs:
+        g.insert(*rows)
+    o.insert_batch(rows)
+    try:
+        for it in range(6):
+            idx = rng.integers(0, cap, size=batch).astype(np.int64)
+            if batch > 1 and it % 2:
+                idx[: batch // 2] = idx[batch // 2: 2 * (batch // 2)]  # duplicates: last writer wins
+            pr = (np.abs(rng.normal(size=batch)) + 1e-3).astype(np.float32)
+            if it == 3:
+                pr[::3] = 0.0
+                pr[1::5] = -1.0
+            _ffi.set_option("inline_update", 1)
+            bufs[0].update_priorities(idx, pr)
+            _ffi.set_option("inline_update", 0)
+            bufs[1].update_priorities(idx, pr)
+            o.update_priorities(idx, pr)
+            for g in bufs:
+                same_tree(g, o)
+                assert g.max_priority() == o.max_priority()
+    finally:
+        _ffi.set_option("inline_update", 1)
