@@ -464,8 +464,13 @@ def bench_gae(ctx, steps, warmup):
                                       "traffic": ncu_traffic("c4:scan_bm_row_kernel<1, 1, 0>")}
     roofline["back_to_back"] = {"achieved": main["back_to_back_GBps"], "frac": main["back_to_back_frac"],
                                 "note": "5 rotated buffer sets, launches back to back in one event pair"}
-    return {"workload": "C4 GAE 4096 envs x 2048 steps fp32 gamma=0.99 lambda=0.95 done~Bernoulli(1/200)",
-            "metric": "gae_elements_per_s", "value": main["elems_per_s"], "unit": "elements/s",
+    w = ctx.world
+    e2e["value"] *= w
+    name = "C4 GAE 4096 envs x 2048 steps fp32 gamma=0.99 lambda=0.95 done~Bernoulli(1/200)"
+    if w > 1:
+        name += f", env axis sharded over {w} ranks (4096 envs per rank, no communication; whole-job elements/s)"
+    return {"workload": name,
+            "metric": "gae_elements_per_s", "value": main["elems_per_s"] * w, "unit": "elements/s",
             "ms_per_step": main["ms"], "steps": steps, "roofline": roofline, "e2e": e2e,
             "variants": out}
 
@@ -610,6 +615,7 @@ def main():
         r = bench_per(ctx, "C5 sharded PER 1M/rank batch 4096/rank, root-stat all-gather per sample",
                       C2_ROWS, 4096, max(20, min(args.steps, 300)), args.warmup, False)
         also.append(r)
+        also.append(bench_gae(ctx, max(10, min(args.steps, 50)), args.warmup))
 
     if ctx.rank == 0:
         if not args.no_cpu:

@@ -287,6 +287,7 @@ static int64_t g_gather_path = env_i64("MRL_GATHER_PATH", 0);
 static int64_t g_bulk_min_row = env_i64("MRL_BULK_MIN_ROW", 2048);
 static int64_t g_bulk_chunk = env_i64("MRL_BULK_CHUNK", 8192);
 static int64_t g_bulk_ctas_per_sm = env_i64("MRL_BULK_CTAS_PER_SM", 4);
+static int64_t g_bulk_stages = env_i64("MRL_BULK_STAGES", 4);
 
 extern long long *g_debug_timers;  // prb.cu
 extern bool g_no_inline_update;    // prb.cu
@@ -305,11 +306,23 @@ int set_copy_option(const char *key, int64_t value) {
   else if (k == "bulk_min_row" && value >= 16) g_bulk_min_row = value;
   else if (k == "bulk_chunk" && value >= 16 && value <= 49152 && value % 16 == 0) g_bulk_chunk = value;
   else if (k == "bulk_ctas_per_sm" && value >= 1 && value <= 16) g_bulk_ctas_per_sm = value;
+  else if (k == "bulk_stages" && (value == 2 || value == 4 || value == 8 || value == 12)) g_bulk_stages = value;
   else return MRL_ERR_INVALID;
   return MRL_OK;
 }
 
-constexpr int kBulkStages = 4;
+template <int STAGES>
+static int launch_bulk(const ColTable &tab, const BulkPlan &plan, const int64_t *slots, int64_t capacity,
+                       int32_t stage_bytes, int64_t blocks, cudaStream_t st) {
+  const size_t smem = (size_t)stage_bytes * STAGES;
+  static size_t configured = 0;
+  if (smem > configured) {
+    MRL_CUDA(cudaFuncSetAttribute(gather_bulk_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  gather_bulk_kernel<STAGES><<<(unsigned)blocks, 32, smem, st>>>(tab, plan, slots, capacity, stage_bytes);
+  return MRL_OK;
+}
 
 int gather_rows(const ColTable &tab, const int64_t *slots, int64_t n, int64_t capacity,
                 cudaStream_t st, uint32_t col_mask) {
@@ -345,15 +358,14 @@ int gather_rows(const ColTable &tab, const int64_t *slots, int64_t n, int64_t ca
     int64_t blocks = kNumSM * bulk_ctas_per_sm;
     if (blocks > total) blocks = total;
     stage_bytes = (stage_bytes + 127) / 128 * 128;
-    const size_t smem = (size_t)stage_bytes * kBulkStages;
-    static size_t configured = 0;
-    if (smem > configured) {
-      MRL_CUDA(cudaFuncSetAttribute(gather_bulk_kernel<kBulkStages>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = smem;
-    }
-    gather_bulk_kernel<kBulkStages>
-        <<<(unsigned)blocks, 32, smem, st>>>(tab, plan, slots, capacity, stage_bytes);
+    int stages = (int)g_bulk_stages;
+    while (stages > 2 && (size_t)stage_bytes * stages > 200 * 1024) stages = stages == 12 ? 8 : stages / 2;
+    int rc;
+    if (stages == 12) rc = launch_bulk<12>(tab, plan, slots, capacity, stage_bytes, blocks, st);
+    else if (stages == 8) rc = launch_bulk<8>(tab, plan, slots, capacity, stage_bytes, blocks, st);
+    else if (stages == 4) rc = launch_bulk<4>(tab, plan, slots, capacity, stage_bytes, blocks, st);
+    else rc = launch_bulk<2>(tab, plan, slots, capacity, stage_bytes, blocks, st);
+    if (rc) return rc;
     MRL_LAUNCHED();
   }
   if (ldg_mask) {
