@@ -8,6 +8,7 @@
 #include <mutex>
 #include <string>
 #include <unordered_map>
+#include <utility>
 
 #include "../../include/mindrl_b200.h"
 #include "../../include/mrl_arith.h"
@@ -45,6 +46,32 @@ inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s
     ::mrl::g_launches.fetch_add(1);             \
     MRL_CUDA(cudaPeekAtLastError());            \
   } while (0)
+
+#ifdef __CUDACC__
+// Programmatic dependent launch: the tree kernels of a learner loop are 10-16 us long and follow each
+// other (sample -> update -> sample ...), so the ~3 us between one kernel draining and the next one being
+// resident is a fifth of the step.  Each kernel lets its successor become resident as soon as its own CTAs
+// have all started (launch_dependents) and waits for its predecessor to complete, memory flushed, before it
+// touches global memory (wait; a no-op when the kernel was launched the ordinary way).
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+extern bool g_pdl;  // option "pdl" (copy.cu)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr, cfg.numAttrs = g_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
+#endif
 
 // process-global handle registry (mcts_factory.h:39-82 is the reference's model)
 template <class T>

@@ -236,6 +236,7 @@ __global__ void __launch_bounds__(32)
 
   for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1);
   fence_async_smem();
+  pdl_prologue();  // the slots come from the sample kernel just before this one
 
   const int64_t total = plan.item_begin[plan.ncols];
   const int64_t first = blockIdx.x;
@@ -291,6 +292,7 @@ static int64_t g_bulk_stages = env_i64("MRL_BULK_STAGES", 4);
 
 extern long long *g_debug_timers;  // prb.cu
 extern bool g_no_inline_update;    // prb.cu
+bool g_pdl = true;                 // programmatic dependent launch of the PER-path kernels
 
 int set_copy_option(const char *key, int64_t value) {
   std::string k(key);
@@ -300,6 +302,10 @@ int set_copy_option(const char *key, int64_t value) {
   }
   if (k == "inline_update" && (value == 0 || value == 1)) {
     g_no_inline_update = value == 0;
+    return MRL_OK;
+  }
+  if (k == "pdl" && (value == 0 || value == 1)) {
+    g_pdl = value == 1;
     return MRL_OK;
   }
   if (k == "gather_path" && value >= 0 && value <= 2) g_gather_path = value;
@@ -320,7 +326,8 @@ static int launch_bulk(const ColTable &tab, const BulkPlan &plan, const int64_t 
     MRL_CUDA(cudaFuncSetAttribute(gather_bulk_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  gather_bulk_kernel<STAGES><<<(unsigned)blocks, 32, smem, st>>>(tab, plan, slots, capacity, stage_bytes);
+  MRL_CUDA(launch_pdl(gather_bulk_kernel<STAGES>, dim3((unsigned)blocks), dim3(32), smem, st, tab, plan, slots,
+                      capacity, stage_bytes));
   return MRL_OK;
 }
 

@@ -29,6 +29,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <utility>
+
 #include "common.cuh"
 
 namespace mrl {
@@ -128,6 +130,7 @@ struct SampleArgs {
 
 __global__ void __launch_bounds__(kSampleWarps * 32)
     prb_sample_kernel(const __grid_constant__ SampleArgs S, const __grid_constant__ ColTable tab) {
+  pdl_prologue();
   dbg_mark(S.dbg, 0);
   const int lane = threadIdx.x & 31;
   const int64_t i = (int64_t)blockIdx.x * kSampleWarps + (threadIdx.x >> 5);
@@ -595,6 +598,7 @@ __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __gri
   __shared__ int32_t s_in_idx[INL ? kInlineMax : 1];
   __shared__ float s_in_pr[INL ? kInlineMax : 1];
   const int tid = threadIdx.x, nthr = blockDim.x;
+  pdl_prologue();
   if (INL) {
     for (int i = tid; i < (int)U.n; i += nthr) s_in_idx[i] = IB.idx[i], s_in_pr[i] = IB.pr[i];
     __syncthreads();
@@ -1139,7 +1143,7 @@ static int prb_sample_impl(PrbBuffer *b, int64_t n, float beta, const float *uni
   ColTable tab;
   fill_table(tab, b, out_cols);
   const int64_t blocks = (n + kSampleWarps - 1) / kSampleWarps;
-  prb_sample_kernel<<<(unsigned)blocks, kSampleWarps * 32, 0, st>>>(S, tab);
+  MRL_CUDA(launch_pdl(prb_sample_kernel, dim3((unsigned)blocks), dim3(kSampleWarps * 32), 0, st, S, tab));
   MRL_LAUNCHED();
   if (!uniforms) b->ctr += (uint64_t)n;
   if (wide) return gather_rows(tab, indices, n, b->capacity, st, wide);
@@ -1188,8 +1192,8 @@ static int prb_update_impl(PrbBuffer *b, const int64_t *indices, const float *pr
     int ctas = kSubCtas;  // 128..512 so that a CTA's share stays within one warp (~n/ctas entries)
     while (ctas < 512 && n > 8 * (int64_t)ctas) ctas <<= 1;
     static const InlineBatch none = {};
-    if (inl) prb_update_sub_kernel<true><<<ctas, kSubThreads, 0, st>>>(U, *inl);
-    else prb_update_sub_kernel<false><<<ctas, kSubThreads, 0, st>>>(U, none);
+    if (inl) MRL_CUDA(launch_pdl(prb_update_sub_kernel<true>, dim3(ctas), dim3(kSubThreads), 0, st, U, *inl));
+    else MRL_CUDA(launch_pdl(prb_update_sub_kernel<false>, dim3(ctas), dim3(kSubThreads), 0, st, U, none));
   } else {
     prb_update_kernel<<<1, 1024, 0, st>>>(U);
   }
