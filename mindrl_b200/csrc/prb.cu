@@ -640,61 +640,7 @@ __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __gri
   const int S = 1 << nlev;  // leaves per subtree
   const bool dense = total_mine > kSubDenseAt && 2 * S <= (2 << kTopLevels) && S <= 4 * kSubMaxLocal &&
                      (width + G - 1) / G <= 32;
-  if (dense) {
-    // ---- dense share: rebuild every dirty subtree completely in shared memory -------------------
-    // (coalesced loads of all its leaves instead of scattered sibling loads; cost independent of how
-    // many of its leaves the batch touches)
-    int *win = s_raw;  // per leaf of the subtree: highest batch position + 1
-    for (int jsub = 0; jsub * G + (int)blockIdx.x < width; ++jsub) {
-      if (!((dirty_mask >> (jsub & 31)) & 1u)) continue;
-      const int sub = jsub * G + (int)blockIdx.x;
-      const int64_t leaf0 = (int64_t)sub << nlev;
-      for (int i = tid; i < S; i += nthr) win[i] = 0;
-      __syncthreads();
-      for (int64_t k = tid; k < U.n; k += nthr) {
-        const int64_t leaf = ld_idx(k);
-        if ((leaf >> nlev) == sub) {
-          atomicMax(&win[leaf - leaf0], (int)k + 1);
-          const float p = prb_pow_fn(ld_pr(k), U.alpha);
-          local_max = p > local_max ? p : local_max;
-        }
-      }
-      __syncthreads();
-      for (int i = tid; i < S; i += nthr) {
-        const int wk = win[i];
-        float vs, vm;
-        if (wk) {
-          vs = vm = prb_pow_fn(ld_pr(wk - 1), U.alpha);
-          __stcg(U.sum + U.cap2 + leaf0 + i, vs);
-          __stcg(U.mn + U.cap2 + leaf0 + i, vm);
-        } else {
-          vs = __ldcg(U.sum + U.cap2 + leaf0 + i);
-          vm = __ldcg(U.mn + U.cap2 + leaf0 + i);
-        }
-        ssum[S + i] = vs;
-        smin[S + i] = vm;
-      }
-      __syncthreads();
-#pragma unroll 1
-      for (int level = nlev - 1; level >= 0; --level) {
-        const int w = 1 << level;
-        for (int i = tid; i < w; i += nthr) {
-          const int node = w + i;
-          ssum[node] = __fadd_rn(ssum[2 * node], ssum[2 * node + 1]);
-          const float ma = smin[2 * node], mb = smin[2 * node + 1];
-          smin[node] = ma < mb ? ma : mb;
-        }
-        __syncthreads();
-      }
-      for (int jn = tid + 1; jn < S; jn += nthr) {  // local heap node -> global heap node
-        const int l = 31 - __clz(jn);
-        const int64_t g = ((int64_t)(width + sub) << l) + (jn - (1 << l));
-        __stcg(U.sum + g, ssum[jn]);
-        __stcg(U.mn + g, smin[jn]);
-      }
-      __syncthreads();
-    }
-  } else if (total_mine > 0 && total_mine <= 32) {
+  if (__builtin_expect(total_mine > 0 && total_mine <= 32, 1)) {  // (never dense: that needs > 128 entries)
     // ---- small share (the normal case): one warp, no barriers, no shared-memory exchange ----------
     // Lanes whose path nodes have the same parent find each other with match.any; duplicates of a leaf
     // resolve with a max-reduction over their group.
@@ -753,6 +699,60 @@ __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __gri
         __stcg(U.sum + node, vs);
         __stcg(U.mn + node, vm);
       }
+    }
+  } else if (dense) {
+    // ---- dense share: rebuild every dirty subtree completely in shared memory -------------------
+    // (coalesced loads of all its leaves instead of scattered sibling loads; cost independent of how
+    // many of its leaves the batch touches)
+    int *win = s_raw;  // per leaf of the subtree: highest batch position + 1
+    for (int jsub = 0; jsub * G + (int)blockIdx.x < width; ++jsub) {
+      if (!((dirty_mask >> (jsub & 31)) & 1u)) continue;
+      const int sub = jsub * G + (int)blockIdx.x;
+      const int64_t leaf0 = (int64_t)sub << nlev;
+      for (int i = tid; i < S; i += nthr) win[i] = 0;
+      __syncthreads();
+      for (int64_t k = tid; k < U.n; k += nthr) {
+        const int64_t leaf = ld_idx(k);
+        if ((leaf >> nlev) == sub) {
+          atomicMax(&win[leaf - leaf0], (int)k + 1);
+          const float p = prb_pow_fn(ld_pr(k), U.alpha);
+          local_max = p > local_max ? p : local_max;
+        }
+      }
+      __syncthreads();
+      for (int i = tid; i < S; i += nthr) {
+        const int wk = win[i];
+        float vs, vm;
+        if (wk) {
+          vs = vm = prb_pow_fn(ld_pr(wk - 1), U.alpha);
+          __stcg(U.sum + U.cap2 + leaf0 + i, vs);
+          __stcg(U.mn + U.cap2 + leaf0 + i, vm);
+        } else {
+          vs = __ldcg(U.sum + U.cap2 + leaf0 + i);
+          vm = __ldcg(U.mn + U.cap2 + leaf0 + i);
+        }
+        ssum[S + i] = vs;
+        smin[S + i] = vm;
+      }
+      __syncthreads();
+#pragma unroll 1
+      for (int level = nlev - 1; level >= 0; --level) {
+        const int w = 1 << level;
+        for (int i = tid; i < w; i += nthr) {
+          const int node = w + i;
+          ssum[node] = __fadd_rn(ssum[2 * node], ssum[2 * node + 1]);
+          const float ma = smin[2 * node], mb = smin[2 * node + 1];
+          smin[node] = ma < mb ? ma : mb;
+        }
+        __syncthreads();
+      }
+      for (int jn = tid + 1; jn < S; jn += nthr) {  // local heap node -> global heap node
+        const int l = 31 - __clz(jn);
+        const int64_t g = ((int64_t)(width + sub) << l) + (jn - (1 << l));
+        __stcg(U.sum + g, ssum[jn]);
+        __stcg(U.mn + g, smin[jn]);
+      }
+      __syncthreads();
     }
   } else if (total_mine > 0) {
     // ---- sparse share: one thread per entry walks its path in registers ---------------------------
@@ -869,7 +869,7 @@ __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __gri
   if (!s_last) return;
   dbg_mark_gt(U.dbg, 13);
   __threadfence();
-  if (width == 4 * kSubThreads && nthr == kSubThreads) {
+  if (__builtin_expect(width == 4 * kSubThreads && nthr == kSubThreads, 1)) {
     // 2048 level-11 nodes, 4 per thread: two levels in registers, five by warp shuffles, the last
     // four by one warp -- one block barrier instead of eleven, no shared-memory tree
     const float4 a = __ldcg(reinterpret_cast<const float4 *>(U.sum + width) + tid);

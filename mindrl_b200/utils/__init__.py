@@ -1,5 +1,6 @@
 from .discounted_return import DiscountedReturn, affine_scan, discounted_reward, gae, normalize_advantage
 from .n_step_buffer import NStepBuffer
+from .tensor_array import TensorArray
 from .vtrace import get_vs_and_advantages
 
-__all__ = ["DiscountedReturn", "discounted_reward", "gae", "affine_scan", "get_vs_and_advantages", "NStepBuffer", "normalize_advantage"]
+__all__ = ["DiscountedReturn", "discounted_reward", "gae", "affine_scan", "get_vs_and_advantages", "NStepBuffer", "normalize_advantage", "TensorArray"]

@@ -56,7 +56,8 @@ if __name__ == "__main__":
     g = os.path.join(ROOT, "gpurun_out")
     for rep, tag in [("prof_c2_r1.ncu-rep", "r1_ncu_full_c2_per_kernels"), ("prof_c3_r1.ncu-rep", "r1_ncu_full_c3_per_kernels"),
                      ("prof_c4_r1.ncu-rep", "r1_ncu_full_c4_scan_kernels"),
-                     ("prof_c4_r1b.ncu-rep", "r1_ncu_full_c4_tma_scan_kernels"), ("prof_scan_r1e.ncu-rep", "r1_ncu_full_wtile_before_fastpath")]:
+                     ("prof_c4_r1b.ncu-rep", "r1_ncu_full_c4_tma_scan_kernels"),
+                     ("prof_c2_r1b.ncu-rep", "r1_ncu_full_c2_per_kernels_pdl"), ("prof_c3_r1b.ncu-rep", "r1_ncu_full_c3_per_kernels_pdl"), ("prof_scan_r1e.ncu-rep", "r1_ncu_full_wtile_before_fastpath")]:
         p = os.path.join(g, rep)
         if os.path.exists(p):
             for d in report(p, tag):
@@ -74,5 +75,25 @@ if __name__ == "__main__":
                                "dram_write_bytes": int(d["dram__bytes_write.sum"]), "launches_captured": 1,
                                "source": "profiles/r1_ncu_full_c4_tma_scan_kernels.json (ncu --set full --clock-control none; cold caches, serialised)"}
         json.dump(t, open(tp, "w"), indent=1)
+    for cfg, tag in (("c2", "r1_ncu_full_c2_per_kernels_pdl"), ("c3", "r1_ncu_full_c3_per_kernels_pdl")):
+        tj = os.path.join(OUT, tag + ".json")
+        if os.path.exists(tp) and os.path.exists(tj):
+            t = json.load(open(tp))
+            seen = collections.defaultdict(list)
+            for d in json.load(open(tj)):
+                name = d["kernel"].split("::")[-1].split("(")[0].replace("void ", "")
+                name = name.split("<")[0] if name.startswith("prb_") else name
+                seen[name].append(d)
+            for name, ds in seen.items():
+                n = len(ds)
+                t[f"{cfg}:{name}"] = {"ncu_duration_us": round(sum(d["gpu__time_duration.sum"] for d in ds) / n, 2),
+                                      "dram_traffic_bytes": int(sum(d["dram_traffic_bytes"] for d in ds) / n),
+                                      "dram_read_bytes": int(sum(d["dram__bytes_read.sum"] for d in ds) / n),
+                                      "dram_write_bytes": int(sum(d["dram__bytes_write.sum"] for d in ds) / n),
+                                      "launches_captured": n,
+                                      "source": f"profiles/{tag}.json (ncu --set full --clock-control none; cold caches, serialised)"}
+            json.dump(t, open(tp, "w"), indent=1)
+    if os.path.exists(os.path.join(g, "launches_r1b.csv")):
+        launches(os.path.join(g, "launches_r1b.csv"), "r1_launch_list_bench_steps20_final")
     if os.path.exists(os.path.join(g, "launches_r1.csv")):
         launches(os.path.join(g, "launches_r1.csv"), "r1_launch_list_bench_steps20")

@@ -370,3 +370,48 @@ def test_tma_ring_reuse_identity(layout):
             assert torch.equal(adv, r)
             out = M.discounted_reward(r, 0.0, layout=layout, mode="parallel")
             assert torch.equal(out, r)
+
+
+def test_tensor_array_stages_a_trajectory_for_the_scan():
+    """TensorArray (utils/tensor_array.py:25-190): the docstring example (:41-58), fixed-size and dynamic
+    semantics, and the A2C use (a2c.py:116-164): write(t, ...) per step, stack(), DiscountedReturn."""
+    ta = M.TensorArray(np.int64, ())
+    ta.write(0, 1)
+    ta.write(1, 2)
+    assert int(ta.read(1).cpu()) == 2
+    assert ta.stack().cpu().tolist() == [1, 2] and ta.size() == 2
+    ta.clear()
+    ta.write(0, 3)
+    assert int(ta.read(0).cpu()) == 3 and ta.size() == 1
+    for i in range(1, 100):  # grows past its first allocation, keeps what it holds
+        ta.write(i, i * 7)
+    assert ta.stack().cpu().tolist() == [3] + [i * 7 for i in range(1, 100)]
+    ta.close()
+    with pytest.raises(RuntimeError):
+        ta.read(0)
+
+    T, B = 64, 8
+    rng = np.random.default_rng(9)
+    r = rng.normal(size=(T, B)).astype(np.float32)
+    d = rng.random((T, B)) < 0.1
+    rewards = M.TensorArray(np.float32, (B,), dynamic_size=False, size=T)
+    dones = M.TensorArray(np.bool_, (B,), dynamic_size=False, size=T)
+    for t in range(T):
+        rewards.write(t, dev(r[t]) if t % 2 else r[t])  # device and host values
+        dones.write(t, dev(d[t]))
+    with pytest.raises(IndexError):
+        rewards.write(T, r[0])
+    with pytest.raises(ValueError):
+        rewards.write(0, np.zeros(B + 1, np.float32))
+    assert tuple(rewards.stack().shape) == (T, B)
+    assert np.array_equal(rewards.stack().cpu().numpy(), r) and np.array_equal(dones.view().cpu().numpy(), d)
+    lv = rng.normal(size=(B,)).astype(np.float32)
+    want = O.discounted_return(r, d, lv, 0.99)
+    exact(M.DiscountedReturn(0.99, mode="sequential")(rewards.view(), dones.view(), dev(lv)), want)
+    close(M.DiscountedReturn(0.99)(rewards.stack(), dones.stack(), dev(lv)), want)
+    rewards.clear()
+    assert rewards.size() == 0 and not rewards.stack().cpu().numpy().any()
+    with pytest.raises(TypeError):
+        M.TensorArray("complex64", ())
+    with pytest.raises(ValueError):
+        M.TensorArray(np.float32, (), size=-1)
