@@ -258,7 +258,7 @@ def test_normalize_advantage(n):
 # ---- TMA-ring kernels (scan_tma.cu), forced through the library options ------------------------
 class _options:
     """sets library options for the duration of a test and restores the defaults afterwards"""
-    DEFAULTS = {"tm_kernel": 0, "strip_cols": 0, "strip_rpu": 0, "strip_groups": 0, "strip_stages": 0,
+    DEFAULTS = {"host_scan_chunks": 0, "tm_kernel": 0, "strip_cols": 0, "strip_rpu": 0, "strip_groups": 0, "strip_stages": 0,
                 "bm_kernel": 0, "row_stages": 0}
 
     def __init__(self, **kw):
@@ -415,3 +415,35 @@ def test_tensor_array_stages_a_trajectory_for_the_scan():
         M.TensorArray("complex64", ())
     with pytest.raises(ValueError):
         M.TensorArray(np.float32, (), size=-1)
+
+
+@pytest.mark.parametrize("chunks", [1, 3, 16])
+def test_host_scans_pipelined_in_pieces(chunks):
+    """*_host entry points cut the batch axis into pieces (copy-in / scan / copy-out overlapped): ragged
+    last piece, trailing dims, both layouts, every optional array; results identical to the device path"""
+    with _options(host_scan_chunks=chunks):
+        rng = np.random.default_rng(chunks)
+        for T, B, E in [(50, 100, 1), (33, 70, 3), (7, 1, 1), (128, 333, 1)]:
+            shape = (T, B, E) if E > 1 else (T, B)
+            r = rng.normal(size=shape).astype(np.float32)
+            d = rng.random((T, B)) < 0.05
+            lv = rng.normal(size=shape[1:]).astype(np.float32)
+            got = M.DiscountedReturn(0.99)(r, d, lv)   # numpy in -> *_host path, numpy out
+            assert isinstance(got, np.ndarray)
+            close(got, O.discounted_return(r, d, lv, 0.99))
+            exact(M.DiscountedReturn(0.99, mode="sequential")(r, d, lv), O.discounted_return(r, d, lv, 0.99))
+            if E == 1:
+                v = rng.normal(size=(T, B)).astype(np.float32)
+                nv = rng.normal(size=(T, B)).astype(np.float32)
+                adv_r, ret_r = O.gae(r, v, None, lv, d, 0.99, 0.95, layout=0)
+                adv, ret = M.gae(r, v, 0.99, 0.95, last_value=lv, done=d, mode="sequential")
+                exact(adv, adv_r)
+                exact(ret, ret_r)
+                # batch-major: the same arrays read as [T envs, B steps]
+                adv_r, ret_r = O.gae(r, v, nv, None, d, 0.99, 0.95, layout=1)
+                adv, ret = M.gae(r, v, 0.99, 0.95, next_value=nv, done=d, layout="batch_major", mode="sequential")
+                exact(adv, adv_r)
+                exact(ret, ret_r)
+                adv, ret = M.gae(r, v, 0.99, 0.95, next_value=nv, layout="batch_major", want_returns=False)
+                assert ret is None
+                close(adv, O.gae(r, v, nv, None, None, 0.99, 0.95, layout=1)[0])
