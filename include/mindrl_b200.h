@@ -74,8 +74,18 @@ int mrl_get_device(int *device);
 /* number of kernels this library has launched since load (per process) */
 int64_t mrl_launch_count(void);
 
-/* tunables: "gather_path" (0 auto, 1 register path only, 2 TMA ring whenever aligned),
- * "bulk_min_row", "bulk_chunk", "bulk_ctas_per_sm" */
+/* tunables (defaults in brackets; every one of them only selects among kernels that give the same results):
+ *   "gather_path" [0] 0 auto, 1 register path only, 2 TMA ring whenever aligned; "bulk_min_row" [2048],
+ *   "bulk_chunk" [8192], "bulk_ctas_per_sm" [4], "bulk_stages" [4] (2/4/8/12): the TMA-ring gather
+ *   "pdl" [1]: programmatic dependent launch of the PER sample / gather / update kernels
+ *   "inline_update" [1]: mrl_prb_update_host passes batches <= 256 in the kernel parameter block
+ *   "tm_kernel" [0]: time-major scans: 0 auto, 2 two-pass, 3 128-column tiles, 5 warp tiles + look-back,
+ *       6 TMA strips whenever aligned; "strip_cols" [0 = 32], "strip_rpu" [0 = 16], "strip_groups" [0 = 1],
+ *       "strip_stages" [0 = as many as fit], "strip_min_cols" [2048]
+ *   "bm_kernel" [0]: batch-major scans: 0 auto, 1 warp-per-row register kernel, 2 TMA rows whenever aligned;
+ *       "row_ctas_per_sm" [4], "row_stages" [0 = from row_ctas_per_sm]
+ *   "host_scan_chunks" [0 = ~16 MB of input per piece]: pieces of the *_host scans (1 = no pipelining)
+ *   "debug_timers": device pointer to >= 32 int64 phase marks of the tree kernels (0 = off) */
 int mrl_set_option(const char *key, int64_t value);
 
 /* carrier-free memory helpers (PyTorch is optional; these are plain cudaMalloc etc.) */
