@@ -141,6 +141,7 @@ class Ctx:
         self.flush_val = 0
         self.clocks = ClockSampler(self.local_rank)
         self.args = args
+        self.align_buf = torch.zeros(1, dtype=torch.float32, device="cuda") if self.world > 1 else None
 
     def flush(self):
         # write 256 MiB (evicts everything), then read another 256 MiB so that the L2 is left holding
@@ -148,6 +149,11 @@ class Ctx:
         self.flush_val = (self.flush_val + 1) & 0xFF
         self.flush_buf.fill_(self.flush_val)
         self.flush_src.sum()
+        if self.world > 1 and os.environ.get("MRL_BENCH_ALIGN", "1") == "1":
+            # the flush takes ~150 us and not the same time on every GPU: without this every rank's step would
+            # also be charged the time its peers' flushes ran longer (the sharded sample waits for all ranks).
+            # An (untimed) all-reduce ends on all ranks within about a microsecond of each other.
+            self.dist.all_reduce(self.align_buf)
 
     def barrier(self):
         if self.world > 1:
@@ -648,7 +654,9 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": primary["workload"], "per_rank": True,
                        "l2": "flushed before every timed iteration (256 MiB written, then 256 MiB read; untimed); "
-                             "step time = sum of per-iteration CUDA-event durations on the launching stream",
+                             "step time = sum of per-iteration CUDA-event durations on the launching stream"
+                             + ("; ranks re-aligned after every flush by an untimed 4-byte NCCL all-reduce"
+                                if ctx.world > 1 and os.environ.get("MRL_BENCH_ALIGN", "1") == "1" else ""),
                        "sharding": ("per-rank sub-buffers (1M rows each); root statistics exchanged inside the sample "
                                     "kernel by peer stores over NVLink (MRL_SHARD_EXCHANGE=nccl: NCCL all-gather)"
                                     if ctx.world > 1 else "single GPU")},

@@ -78,6 +78,10 @@ int64_t mrl_launch_count(void);
  *   "gather_path" [0] 0 auto, 1 register path only, 2 TMA ring whenever aligned; "bulk_min_row" [2048],
  *   "bulk_chunk" [8192], "bulk_ctas_per_sm" [4], "bulk_stages" [4] (2/4/8/12): the TMA-ring gather
  *   "pdl" [1]: programmatic dependent launch of the PER sample / gather / update kernels
+ *   "tree_prefetch" [1]: the PER sample / update kernels prefetch the tree lines of their later dependent
+ *       round trips (depth 10 and 15 of the descent, depth 11 of the top rebuild) into L2 at kernel start
+ *   "host_zero_copy" [1]: mrl_prb_sample_host results <= 64 KB are written by the kernel straight into mapped
+ *       pinned memory (0: device arena + one DMA; measured 6 us slower per call)
  *   "inline_update" [1]: mrl_prb_update_host passes batches <= 256 in the kernel parameter block
  *   "tm_kernel" [0]: time-major scans: 0 auto, 2 two-pass, 3 128-column tiles, 5 warp tiles + look-back,
  *       6 TMA strips whenever aligned; "strip_cols" [0 = 32], "strip_rpu" [0 = 16], "strip_groups" [0 = 1],

@@ -58,6 +58,7 @@ __device__ __forceinline__ void pdl_prologue() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 extern bool g_pdl;  // option "pdl" (copy.cu)
+extern bool g_tree_prefetch;  // option "tree_prefetch" (copy.cu)
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
@@ -125,6 +126,11 @@ struct Staging {
   uint8_t *dev = nullptr;
   size_t bytes = 0;
   cudaEvent_t done = nullptr;  // last async use of `host`
+  bool pending = false;        // `done` was recorded since the last wait()
+  cudaError_t mark(cudaStream_t st) {
+    pending = true;
+    return cudaEventRecord(done, st);
+  }
   int ensure(size_t need);
   int wait();
   void release();

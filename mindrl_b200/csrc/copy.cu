@@ -292,7 +292,9 @@ static int64_t g_bulk_stages = env_i64("MRL_BULK_STAGES", 4);
 
 extern long long *g_debug_timers;  // prb.cu
 extern bool g_no_inline_update;    // prb.cu
+extern bool g_host_zero_copy;      // prb.cu
 bool g_pdl = true;                 // programmatic dependent launch of the PER-path kernels
+bool g_tree_prefetch = true;       // tree kernels pull the lines of their later round trips into L2 first
 
 int set_copy_option(const char *key, int64_t value) {
   std::string k(key);
@@ -306,6 +308,14 @@ int set_copy_option(const char *key, int64_t value) {
   }
   if (k == "pdl" && (value == 0 || value == 1)) {
     g_pdl = value == 1;
+    return MRL_OK;
+  }
+  if (k == "host_zero_copy" && (value == 0 || value == 1)) {
+    g_host_zero_copy = value == 1;
+    return MRL_OK;
+  }
+  if (k == "tree_prefetch" && (value == 0 || value == 1)) {
+    g_tree_prefetch = value == 1;
     return MRL_OK;
   }
   if (k == "gather_path" && value >= 0 && value <= 2) g_gather_path = value;

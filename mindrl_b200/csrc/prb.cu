@@ -126,10 +126,24 @@ struct SampleArgs {
   const uint2 *mailbox;
   int32_t rank;
   uint32_t epoch;
+  int32_t prefetch;  // option "tree_prefetch"
 };
 
 __global__ void __launch_bounds__(kSampleWarps * 32)
     prb_sample_kernel(const __grid_constant__ SampleArgs S, const __grid_constant__ ColTable tab) {
+  // Before anything is known about the masses: pull the lines the 2nd and 3rd hop can land on (all of
+  // depth 10 = 4 KB, all of depth 15 = 128 KB) into L2, spread over the grid.  L2 is the point of
+  // coherence, so this may run ahead of the predecessor kernel (before griddepcontrol.wait); with a
+  // cold L2 two of the four dependent round trips of the descent become L2 hits.
+  if (S.prefetch) {
+    const int64_t gthreads = (int64_t)gridDim.x * blockDim.x;
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t l10 = S.levels > 10 ? 32 : 0, l15 = S.levels > 15 ? 1024 : 0;
+    for (int64_t q = gid; q < l10 + l15 && q < gid + 4 * gthreads; q += gthreads) {
+      const float *line = q < l10 ? S.sum + 1024 + 32 * q : S.sum + 32768 + 32 * (q - l10);
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
+    }
+  }
   pdl_prologue();
   dbg_mark(S.dbg, 0);
   const int lane = threadIdx.x & 31;
@@ -137,9 +151,12 @@ __global__ void __launch_bounds__(kSampleWarps * 32)
   if (i >= S.n) return;
   constexpr unsigned FULL = 0xffffffffu;
 
-  // everything that does not depend on the descent is requested first
+  // everything that does not depend on the descent is requested first: the root, and the line of the
+  // first hop (its address does not depend on the mass)
   const float root_sum = __ldcg(S.sum + 1);
   float w_min = __ldcg(S.mn + 1);
+  const int h0 = S.levels < 5 ? S.levels : 5;
+  const float hop0 = (S.levels > 0 && lane < (1 << h0)) ? __ldcg(S.sum + (1 << h0) + lane) : 0.0f;
   if (S.peers && blockIdx.x == 0 && threadIdx.x < S.world) {
     // Fused exchange, part 1: this rank's root statistics go straight into every rank's mailbox
     // (peer stores over NVLink).  The words are self-validating {value, epoch}: no fence, no flag.
@@ -177,7 +194,7 @@ __global__ void __launch_bounds__(kSampleWarps * 32)
     const int h = remaining < 5 ? remaining : 5;
     const int64_t base = node << h;
     float p[6];
-    p[0] = lane < (1 << h) ? __ldcg(S.sum + base + lane) : 0.0f;
+    p[0] = node == 1 ? hop0 : (lane < (1 << h) ? __ldcg(S.sum + base + lane) : 0.0f);
 #pragma unroll
     for (int k = 1; k <= 5; ++k) p[k] = __fadd_rn(p[k - 1], __shfl_xor_sync(FULL, p[k - 1], 1 << (k - 1)));
     int off = 0;
@@ -268,6 +285,7 @@ struct UpdateArgs {
   float alpha;
   uint64_t epoch;
   long long *dbg;
+  int32_t prefetch;  // option "tree_prefetch"
 };
 
 __device__ __forceinline__ void recompute_node(float *sum, float *mn, int64_t node) {
@@ -598,6 +616,16 @@ __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __gri
   __shared__ int32_t s_in_idx[INL ? kInlineMax : 1];
   __shared__ float s_in_pr[INL ? kInlineMax : 1];
   const int tid = threadIdx.x, nthr = blockDim.x;
+  if (U.prefetch && tid == 0) {
+    // the top rebuild at the end reads all of depth min(levels, 11) (2 x 8 KB): have it in L2 by then.
+    // L2 is the point of coherence, so this may run ahead of the predecessor (before griddepcontrol.wait).
+    const int sp = U.levels < kTopLevels ? U.levels : kTopLevels;
+    const int lines = ((1 << sp) + 31) / 32;  // per array
+    for (int q = blockIdx.x; q < 2 * lines; q += gridDim.x) {
+      const float *line = (q < lines ? U.sum : U.mn) + (1 << sp) + 32 * (q < lines ? q : q - lines);
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
+    }
+  }
   pdl_prologue();
   if (INL) {
     for (int i = tid; i < (int)U.n; i += nthr) s_in_idx[i] = IB.idx[i], s_in_pr[i] = IB.pr[i];
@@ -1140,6 +1168,7 @@ static int prb_sample_impl(PrbBuffer *b, int64_t n, float beta, const float *uni
     }
   S.gather_mask = fused;
   S.dbg = g_debug_timers;
+  S.prefetch = g_tree_prefetch ? 1 : 0;
   ColTable tab;
   fill_table(tab, b, out_cols);
   const int64_t blocks = (n + kSampleWarps - 1) / kSampleWarps;
@@ -1161,6 +1190,7 @@ static bool update_takes_inline(const PrbBuffer *b, int64_t n) {
 }
 
 bool g_no_inline_update = false;  // option "inline_update" = 0: always stage through device memory
+bool g_host_zero_copy = true;     // option "host_zero_copy": small *_host sample results are written by the kernel itself
 
 static int prb_update_impl(PrbBuffer *b, const int64_t *indices, const float *priorities,
                            int64_t n, cudaStream_t st, const InlineBatch *inl = nullptr) {
@@ -1174,6 +1204,7 @@ static int prb_update_impl(PrbBuffer *b, const int64_t *indices, const float *pr
   U.n = n, U.cap2 = b->cap2, U.levels = b->levels, U.alpha = b->alpha;
   U.epoch = ++b->epoch;
   U.dbg = g_debug_timers;
+  U.prefetch = g_tree_prefetch ? 1 : 0;
   if (n <= kWalkMax && b->levels - kTopLevels <= kWalkLevels && g_update_path == 1) {
     int threads = (int)((n + 31) / 32 * 32);
     threads = threads < 256 ? 256 : (threads > kWalkThreads ? kWalkThreads : threads);
@@ -1333,7 +1364,7 @@ extern "C" int mrl_prb_push_batch_host(int64_t handle, int64_t nrows, const void
   MRL_CUDA(cudaMemcpyAsync(b->stage.dev, b->stage.host, off[b->ncols], cudaMemcpyHostToDevice, st));
   rc = prb_push_batch_impl(b, nrows, src_dev, st);
   if (rc) return rc;
-  MRL_CUDA(cudaEventRecord(b->stage.done, st));
+  MRL_CUDA(b->stage.mark(st));
   return MRL_OK;
 }
 
@@ -1381,9 +1412,14 @@ static int prb_sample_host_impl(PrbBuffer *b, int64_t n, float beta, const float
     MRL_CUDA(cudaMemcpyAsync(d + o_u, b->stage.host + o_u, (size_t)n * 4, cudaMemcpyHostToDevice, st));
   }
   void *out_dev[MRL_MAX_COLS];
-  if (total <= (1u << 16)) {
+  if (total <= (1u << 16) && g_host_zero_copy) {
     // small result: the kernel writes straight into the pinned staging buffer (it is mapped into the
-    // device address space), so there is no device-to-host copy to launch -- only the stream wait
+    // device address space), so there is no device-to-host copy to launch -- only the stream wait.
+    // (Measured and dropped: per-warp completion words in the same pinned memory, polled by the host
+    // instead of the event -- the system-scope fences and 256 more PCIe writes cost 1.3 us more than
+    // the event record + query they replace; and collecting a CTA's 8 results in shared memory to store
+    // each output array's piece with full-width stores -- 1 us slower: the cost is the PCIe round trip
+    // at the end of the kernel, not the number of transactions.)
     uint8_t *hz = b->stage.host;
     for (int c = 0; c < b->ncols; ++c) out_dev[c] = hz + off[c];
     rc = prb_sample_impl(b, n, beta, uniforms ? (const float *)(d + o_u) : nullptr, nullptr, 0,
@@ -1401,7 +1437,16 @@ static int prb_sample_host_impl(PrbBuffer *b, int64_t n, float beta, const float
   rc = prb_sample_impl(b, n, beta, uniforms ? (const float *)(d + o_u) : nullptr, nullptr, 0,
                        (int64_t *)(d + o_idx), (float *)(d + o_w), out_cols ? out_dev : nullptr, st, p2p);
   if (rc) return rc;
-  {
+  if (total <= (1u << 16)) {  // (option "host_zero_copy" = 0) one DMA of the whole arena, then host copies
+    MRL_CUDA(cudaMemcpyAsync(b->stage.host, d, total, cudaMemcpyDeviceToHost, st));
+    rc = stream_wait_spin(st);
+    if (rc) return rc;
+    const uint8_t *hz = b->stage.host;
+    memcpy(indices, hz + o_idx, (size_t)n * 8);
+    memcpy(weights, hz + o_w, (size_t)n * 4);
+    if (out_cols)
+      for (int c = 0; c < b->ncols; ++c) memcpy(out_cols[c], hz + off[c], (size_t)n * b->row_bytes[c]);
+  } else {
     MRL_CUDA(cudaMemcpyAsync(b->stage.host, d, o_u, cudaMemcpyDeviceToHost, st));
     if (out_cols)
       for (int c = 0; c < b->ncols; ++c)
@@ -1472,7 +1517,7 @@ extern "C" int mrl_prb_update_host(int64_t handle, const int64_t *indices,
   MRL_CUDA(cudaMemcpyAsync(b->stage.dev, b->stage.host, total, cudaMemcpyHostToDevice, st));
   rc = prb_update_impl(b, (const int64_t *)b->stage.dev, (const float *)(b->stage.dev + o_p), n, st);
   if (rc) return rc;
-  MRL_CUDA(cudaEventRecord(b->stage.done, st));
+  MRL_CUDA(b->stage.mark(st));
   return MRL_OK;
 }
 

@@ -38,7 +38,8 @@ int Staging::ensure(size_t need) {
   return MRL_OK;
 }
 int Staging::wait() {
-  if (done) MRL_CUDA(cudaEventSynchronize(done));
+  if (done && pending) MRL_CUDA(cudaEventSynchronize(done));  // (~2 us even when long complete: skipped when idle)
+  pending = false;
   return MRL_OK;
 }
 void Staging::release() {
@@ -47,6 +48,7 @@ void Staging::release() {
   if (done) cudaEventDestroy(done);
   host = dev = nullptr;
   done = nullptr;
+  pending = false;
   bytes = 0;
 }
 
@@ -266,7 +268,7 @@ extern "C" int mrl_urb_append_host(int64_t handle, int64_t nrows, const void *co
   MRL_CUDA(cudaMemcpyAsync(b->stage.dev, b->stage.host, off[b->ncols], cudaMemcpyHostToDevice, st));
   rc = urb_append_impl(b, nrows, src_dev, st);
   if (rc) return rc;
-  MRL_CUDA(cudaEventRecord(b->stage.done, st));
+  MRL_CUDA(b->stage.mark(st));
   return MRL_OK;
 }
 
@@ -307,7 +309,7 @@ extern "C" int mrl_urb_write_at_host(int64_t handle, int64_t slot, int64_t nrows
   fill_table(tab, b->ncols, b->cols, b->row_bytes, src_dev);
   rc = copy_segments_dir(tab, slot, 0, nrows, 1, st);
   if (rc) return rc;
-  MRL_CUDA(cudaEventRecord(b->stage.done, st));
+  MRL_CUDA(b->stage.mark(st));
   return MRL_OK;
 }
 

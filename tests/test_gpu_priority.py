@@ -104,24 +104,28 @@ def test_random_program_against_oracle(capacity, batch, carrier):
     same_sample(g.sample(0.7), o.sample(0.7))
 
 
-def test_host_carrier_matches_oracle():
+@pytest.mark.parametrize("batch,types", [(32, [np.float32, np.int32]), (13, [np.float32, np.int32]),
+                                         (1, [np.float32, np.int32]), (37, [np.float32, np.uint8]),
+                                         (32, [np.float64, np.int16])])
+def test_host_carrier_matches_oracle(batch, types):
+    """numpy in / numpy out (ragged last CTA: 13, 37; columns that are not whole words: uint8[1], int16[1])"""
     rng = np.random.default_rng(3)
-    shapes, types = [(4,), (1,)], [np.float32, np.int32]
-    g = M.PriorityReplayBuffer(0.6, 500, 32, shapes, types, 1, 2, carrier="numpy")
-    o = O.PriorityBufferOracle(0.6, 500, 32, shapes, types, 1, 2)
+    shapes = [(4,), (1,)]
+    g = M.PriorityReplayBuffer(0.6, 500, batch, shapes, types, 1, 2, carrier="numpy")
+    o = O.PriorityBufferOracle(0.6, 500, batch, shapes, types, 1, 2)
     for i in range(20):
-        row = [rng.normal(size=4).astype(np.float32), np.array([i], np.int32)]
+        row = [rng.normal(size=4).astype(types[0]), np.array([i], types[1])]
         g.insert(*row)
         o.insert(*row)
-    b = [rng.normal(size=(700, 4)).astype(np.float32), np.arange(700, dtype=np.int32)[:, None]]
+    b = [rng.normal(size=(700, 4)).astype(types[0]), (np.arange(700) % 100).astype(types[1])[:, None]]
     g.insert(*b)
     o.insert_batch(b)
     for _ in range(4):
-        u = rng.random(32).astype(np.float32)
+        u = rng.random(batch).astype(np.float32)
         got, want = g.sample(0.5, uniforms=u), o.sample(0.5, uniforms=u)
         assert isinstance(got[0], np.ndarray)
         same_sample(got, want)
-        pr = (rng.random(32) * 3).astype(np.float32)
+        pr = (rng.random(batch) * 3).astype(np.float32)
         g.update_priorities(want[0], pr)
         o.update_priorities(want[0], pr)
     same_tree(g, o)
@@ -287,3 +291,55 @@ def test_host_update_inline_batch_matches_staged_and_oracle(batch):
                 assert g.max_priority() == o.max_priority()
     finally:
         _ffi.set_option("inline_update", 1)
+
+
+@pytest.mark.parametrize("pdl", [1, 0])
+def test_sample_update_captured_in_a_cuda_graph(pdl):
+    """The device entry points are pure stream work (cursors are host integers, no hidden syncs), so a
+    learner can capture sample -> update_priorities once and replay it; each replay is checked bit for bit
+    against the oracle.  (Not capturable by design: draws from the internal generator and insert(), whose
+    counters / cursors advance on the host.)"""
+    rng = np.random.default_rng(11)
+    cap, batch = 5000, 64
+    shapes, types = [(4,), (1,)], [np.float32, np.int32]
+    _ffi.set_option("pdl", pdl)
+    try:
+        g = M.PriorityReplayBuffer(0.6, cap, batch, shapes, types, 0, 1)
+        o = O.PriorityBufferOracle(0.6, cap, batch, shapes, types, 0, 1)
+        b = [rng.normal(size=(cap, 4)).astype(np.float32), rng.integers(0, 9, (cap, 1)).astype(np.int32)]
+        g.insert(*[dev(c) for c in b])
+        o.insert_batch(b)
+        pr0 = (np.abs(rng.normal(size=cap)) + 1e-3).astype(np.float32)
+        g.update_priorities(dev(np.arange(cap)), dev(pr0))
+        o.update_priorities(np.arange(cap), pr0)
+        u_dev = torch.zeros(batch, dtype=torch.float32, device="cuda")
+        p_dev = torch.ones(batch, dtype=torch.float32, device="cuda")
+        # one eager step first (one-off function attributes are set outside the capture), mirrored on the oracle
+        u = rng.random(batch).astype(np.float32)
+        pr = (np.abs(rng.normal(size=batch)) + 1e-3).astype(np.float32)
+        u_dev.copy_(torch.from_numpy(u)), p_dev.copy_(torch.from_numpy(pr))
+        got = g.sample(0.4, uniforms=u_dev)
+        g.update_priorities(got[0], p_dev)
+        want = o.sample(0.4, uniforms=u)
+        o.update_priorities(want[0], pr)
+        same_sample(got, want)
+        torch.cuda.synchronize()
+        launches0 = _ffi.launch_count()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            got = g.sample(0.4, uniforms=u_dev)
+            g.update_priorities(got[0], p_dev)
+        assert _ffi.launch_count() - launches0 == 2  # captured, not run
+        same_tree(g, o)  # capture did not execute anything
+        for _ in range(5):
+            u = rng.random(batch).astype(np.float32)
+            pr = (np.abs(rng.normal(size=batch)) + 1e-3).astype(np.float32)
+            u_dev.copy_(torch.from_numpy(u)), p_dev.copy_(torch.from_numpy(pr))
+            graph.replay()
+            torch.cuda.synchronize()
+            want = o.sample(0.4, uniforms=u)
+            o.update_priorities(want[0], pr)
+            same_sample(got, want)
+            same_tree(g, o)
+    finally:
+        _ffi.set_option("pdl", 1)
