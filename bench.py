@@ -149,10 +149,10 @@ class Ctx:
         self.flush_val = (self.flush_val + 1) & 0xFF
         self.flush_buf.fill_(self.flush_val)
         self.flush_src.sum()
-        if self.world > 1 and os.environ.get("MRL_BENCH_ALIGN", "1") == "1":
-            # the flush takes ~150 us and not the same time on every GPU: without this every rank's step would
-            # also be charged the time its peers' flushes ran longer (the sharded sample waits for all ranks).
-            # An (untimed) all-reduce ends on all ranks within about a microsecond of each other.
+        if self.world > 1 and os.environ.get("MRL_BENCH_ALIGN", "0") == "1":
+            # opt-in experiment: re-align the ranks after the flush with an (untimed) all-reduce.  Measured at
+            # N=8: WORSE (33.8 us/step against 28.7 free-running) -- the ranks leave the all-reduce further
+            # apart than the previous step's exchange left them.  Off by default.
             self.dist.all_reduce(self.align_buf)
 
     def barrier(self):
@@ -656,7 +656,7 @@ def main():
                        "l2": "flushed before every timed iteration (256 MiB written, then 256 MiB read; untimed); "
                              "step time = sum of per-iteration CUDA-event durations on the launching stream"
                              + ("; ranks re-aligned after every flush by an untimed 4-byte NCCL all-reduce"
-                                if ctx.world > 1 and os.environ.get("MRL_BENCH_ALIGN", "1") == "1" else ""),
+                                if ctx.world > 1 and os.environ.get("MRL_BENCH_ALIGN", "0") == "1" else ""),
                        "sharding": ("per-rank sub-buffers (1M rows each); root statistics exchanged inside the sample "
                                     "kernel by peer stores over NVLink (MRL_SHARD_EXCHANGE=nccl: NCCL all-gather)"
                                     if ctx.world > 1 else "single GPU")},
