@@ -670,8 +670,8 @@ __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __gri
                      (width + G - 1) / G <= 32;
   if (__builtin_expect(total_mine > 0 && total_mine <= 32, 1)) {  // (never dense: that needs > 128 entries)
     // ---- small share (the normal case): one warp, no barriers, no shared-memory exchange ----------
-    // Lanes whose path nodes have the same parent find each other with match.any; duplicates of a leaf
-    // resolve with a max-reduction over their group.
+    // Lanes whose path nodes are siblings find each other by comparing against every entry of the share
+    // (shuffles); duplicates of a leaf resolve to the highest batch position the same way.
     if (tid < 32) {
       constexpr unsigned FULL = 0xffffffffu;
       const bool on = tid < total_mine;
@@ -693,11 +693,18 @@ __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __gri
         p = prb_pow_fn(ld_pr(k), U.alpha);
         local_max = p > local_max ? p : local_max;
       }
-      const uint32_t lkey = on ? leaf_node : (0x80000000u | (uint32_t)tid);
-      const unsigned same_leaf = __match_any_sync(FULL, lkey);
-      const int win_k = __reduce_max_sync(same_leaf, k);
-      const int win_lane = __ffs(__ballot_sync(same_leaf, k == win_k)) - 1;
-      float vs = __shfl_sync(same_leaf, p, win_lane), vm = vs;
+      // Partners are found by comparing against the share's m <= 32 entries one shuffle at a time: m is 2
+      // on average (256 entries over 128 CTAs).  (match.any did this in one instruction per level, but it
+      // costs ~0.3 us when all 32 keys differ: 5.5 of the kernel's 10 us were spent in the ten of them.)
+      const int m = total_mine;
+      // leaf level: among the entries of one leaf the highest batch position provides the value
+      int win_k = k, win_lane = tid;
+      for (int j = 0; j < m; ++j) {
+        const uint32_t lj = __shfl_sync(FULL, leaf_node, j);
+        const int kj = __shfl_sync(FULL, k, j);
+        if (on && lj == leaf_node && kj > win_k) win_k = kj, win_lane = j;
+      }
+      float vs = __shfl_sync(FULL, p, win_lane), vm = vs;
       if (on && k == win_k) {
         __stcg(U.sum + leaf_node, vs);
         __stcg(U.mn + leaf_node, vm);
@@ -706,18 +713,19 @@ __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __gri
 #pragma unroll
       for (int d = 0; d < kWalkLevels; ++d) {
         if (d < nlev) {
-          const uint32_t node = leaf_node >> d;
+          const uint32_t node = on ? leaf_node >> d : 0u;  // (0 is never a sibling: the root's index is 1)
           if (d > 0 && on) {
             __stcg(U.sum + node, vs);
             __stcg(U.mn + node, vm);
           }
-          const uint32_t pkey = on ? (node >> 1) : (0x80000000u | (uint32_t)tid);
-          const unsigned same_parent = __match_any_sync(FULL, pkey);
-          const unsigned odd = __ballot_sync(FULL, on && (node & 1u));
-          const unsigned sibs = same_parent & ((node & 1u) ? ~odd : odd);
-          const int src = sibs ? __ffs(sibs) - 1 : tid;
-          const float o_s = __shfl_sync(FULL, vs, src), o_m = __shfl_sync(FULL, vm, src);
-          const float os = sibs ? o_s : sib_s[d], om = sibs ? o_m : sib_m[d];
+          // entries whose paths have merged carry identical values: any lane holding the sibling will do
+          int src = -1;
+          for (int j = 0; j < m; ++j) {
+            const uint32_t nj = __shfl_sync(FULL, node, j);
+            if (nj == (node ^ 1u)) src = j;
+          }
+          const float o_s = __shfl_sync(FULL, vs, src < 0 ? tid : src), o_m = __shfl_sync(FULL, vm, src < 0 ? tid : src);
+          const float os = src >= 0 ? o_s : sib_s[d], om = src >= 0 ? o_m : sib_m[d];
           vs = __fadd_rn(vs, os);
           vm = om < vm ? om : vm;
         }
