@@ -130,20 +130,35 @@ struct SampleArgs {
   int32_t word_units;  // > 0: every fused column is made of aligned 4-byte words; their total per row
 };
 
+constexpr int kHop = 7;  // tree levels per dependent load of the descent
+
+// the 2^h descendants h levels below `node`, spread over the warp: 4 per lane for h = 7, 2 for h = 6, else 1
+__device__ __forceinline__ float4 hop_load(const float *sum, int64_t node, int h, int lane) {
+  float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  const float *base = sum + (node << h);
+  if (h == 7) {
+    v = __ldcg(reinterpret_cast<const float4 *>(base) + lane);
+  } else if (h == 6) {
+    const float2 q = __ldcg(reinterpret_cast<const float2 *>(base) + lane);
+    v.x = q.x, v.y = q.y;
+  } else if (lane < (1 << h)) {
+    v.x = __ldcg(base + lane);
+  }
+  return v;
+}
+
 __global__ void __launch_bounds__(kSampleWarps * 32)
     prb_sample_kernel(const __grid_constant__ SampleArgs S, const __grid_constant__ ColTable tab) {
-  // Before anything is known about the masses: pull the lines the 2nd and 3rd hop can land on (all of
-  // depth 10 = 4 KB, all of depth 15 = 128 KB) into L2, spread over the grid.  L2 is the point of
-  // coherence, so this may run ahead of the predecessor kernel (before griddepcontrol.wait); with a
-  // cold L2 two of the four dependent round trips of the descent become L2 hits.
-  if (S.prefetch) {
+  // Before anything is known about the masses: pull the lines the 2nd hop can land on (all of depth 14 =
+  // 64 KB) into L2, spread over the grid.  L2 is the point of coherence, so this may run ahead of the
+  // predecessor kernel (before griddepcontrol.wait); with a cold L2 one of the three dependent round
+  // trips of the descent becomes an L2 hit.
+  if (S.prefetch && S.levels > 2 * kHop) {
     const int64_t gthreads = (int64_t)gridDim.x * blockDim.x;
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t l10 = S.levels > 10 ? 32 : 0, l15 = S.levels > 15 ? 1024 : 0;
-    for (int64_t q = gid; q < l10 + l15 && q < gid + 4 * gthreads; q += gthreads) {
-      const float *line = q < l10 ? S.sum + 1024 + 32 * q : S.sum + 32768 + 32 * (q - l10);
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
-    }
+    const int64_t lines = (1LL << (2 * kHop)) / 32;
+    for (int64_t q = gid; q < lines && q < gid + 4 * gthreads; q += gthreads)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(S.sum + (1LL << (2 * kHop)) + 32 * q));
   }
   pdl_prologue();
   dbg_mark(S.dbg, 0);
@@ -156,8 +171,8 @@ __global__ void __launch_bounds__(kSampleWarps * 32)
   // first hop (its address does not depend on the mass)
   const float root_sum = __ldcg(S.sum + 1);
   float w_min = __ldcg(S.mn + 1);
-  const int h0 = S.levels < 5 ? S.levels : 5;
-  const float hop0 = (S.levels > 0 && lane < (1 << h0)) ? __ldcg(S.sum + (1 << h0) + lane) : 0.0f;
+  float4 hop0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  if (S.levels > 0) hop0 = hop_load(S.sum, 1, S.levels < kHop ? S.levels : kHop, lane);
   if (S.peers && blockIdx.x == 0 && threadIdx.x < S.world) {
     // Fused exchange, part 1: this rank's root statistics go straight into every rank's mailbox
     // (peer stores over NVLink).  The words are self-validating {value, epoch}: no fence, no flag.
@@ -184,24 +199,31 @@ __global__ void __launch_bounds__(kSampleWarps * 32)
   float mass = __fmul_rn(__fadd_rn(u, (float)i), seg);
   dbg_mark(S.dbg, 1);
 
-  // Warp hops from the root, h <= 5 levels per coalesced 128-byte load.  (Staging the top 11 levels
-  // in shared memory first was measured slower: 3.3 us for the staging alone against ~0.4 us per hop;
-  // the top lines are shared by all warps and stay in L1/L2 anyway.)
+  // Warp hops from the root, h <= 7 levels per coalesced load of the 2^h descendants h levels below the
+  // node (512 bytes: lane l holds descendants 4l..4l+3).  The sums in between are rebuilt exactly as they
+  // are stored -- every parent is fl(left + right) -- two levels inside the lane, five with shuffles; the
+  // walk then takes five shuffle-compare steps to the lane and two inside its quad.  20 levels = 3
+  // dependent round trips.  (Staging the top 11 levels in shared memory first was measured slower: 3.3 us
+  // for the staging alone against ~0.5 us per hop; the top lines are shared by all warps.)
   int64_t node = 1;
   float leaf_p = root_sum;  // capacity 1: the root is the leaf
   int remaining = S.levels;
 #pragma unroll 1
   while (remaining > 0) {
-    const int h = remaining < 5 ? remaining : 5;
+    const int h = remaining < kHop ? remaining : kHop;
+    const int wl = h > 5 ? h - 5 : 0;  // levels inside a lane (0, 1 or 2)
+    const int hx = h - wl;             // levels across lanes
     const int64_t base = node << h;
+    const float4 v = node == 1 ? hop0 : hop_load(S.sum, node, h, lane);
+    const float s01 = __fadd_rn(v.x, v.y), s23 = __fadd_rn(v.z, v.w);
     float p[6];
-    p[0] = node == 1 ? hop0 : (lane < (1 << h) ? __ldcg(S.sum + base + lane) : 0.0f);
+    p[0] = wl == 2 ? __fadd_rn(s01, s23) : (wl == 1 ? s01 : v.x);
 #pragma unroll
     for (int k = 1; k <= 5; ++k) p[k] = __fadd_rn(p[k - 1], __shfl_xor_sync(FULL, p[k - 1], 1 << (k - 1)));
     int off = 0;
 #pragma unroll
     for (int k = 4; k >= 0; --k) {
-      if (k < h) {  // left child at this step spans 2^k leaves starting at `off`
+      if (k < hx) {  // left child at this step spans 2^k lanes starting at `off`
         const float left = __shfl_sync(FULL, p[k], off);
         if (!(mass <= left)) {
           mass = __fsub_rn(mass, left);
@@ -209,9 +231,30 @@ __global__ void __launch_bounds__(kSampleWarps * 32)
         }
       }
     }
-    node = base + off;
+    // inside lane `off`
+    const float c0 = __shfl_sync(FULL, v.x, off), c1 = __shfl_sync(FULL, v.y, off);
+    const float c2 = __shfl_sync(FULL, v.z, off), c3 = __shfl_sync(FULL, v.w, off);
+    int sub = 0;
+    if (wl == 2) {
+      const float a = __fadd_rn(c0, c1);  // == s01 of lane `off`
+      float left = c0;
+      if (!(mass <= a)) {
+        mass = __fsub_rn(mass, a);
+        sub = 2, left = c2;
+      }
+      if (!(mass <= left)) {
+        mass = __fsub_rn(mass, left);
+        sub += 1;
+      }
+    } else if (wl == 1) {
+      if (!(mass <= c0)) {
+        mass = __fsub_rn(mass, c0);
+        sub = 1;
+      }
+    }
+    node = base + ((int64_t)off << wl) + sub;
     remaining -= h;
-    if (remaining == 0) leaf_p = __shfl_sync(FULL, p[0], off);
+    if (remaining == 0) leaf_p = sub == 0 ? c0 : (sub == 1 ? c1 : (sub == 2 ? c2 : c3));
   }
   const int64_t leaf = node - S.cap2;
   const int64_t slot = leaf < S.capacity ? leaf : S.capacity - 1;
