@@ -343,3 +343,31 @@ def test_sample_update_captured_in_a_cuda_graph(pdl):
             same_tree(g, o)
     finally:
         _ffi.set_option("pdl", 1)
+
+
+@pytest.mark.parametrize("option,value", [("tree_prefetch", 0), ("host_zero_copy", 0), ("pdl", 0), ("inline_update", 0)])
+def test_options_only_select_among_equal_paths(option, value):
+    """every tunable of the PER path changes how the work is done, never the result: the same program with
+    the option flipped is bit-identical to the oracle (device and host carriers)"""
+    rng = np.random.default_rng(5)
+    cap, batch = 40000, 96
+    shapes, types = [(4,), (1,)], [np.float32, np.int32]
+    _ffi.set_option(option, value)
+    try:
+        for carrier in ("device", "numpy"):
+            g = M.PriorityReplayBuffer(0.6, cap, batch, shapes, types, 3, 4, carrier=carrier)
+            o = O.PriorityBufferOracle(0.6, cap, batch, shapes, types, 3, 4)
+            b = [rng.normal(size=(cap, 4)).astype(np.float32), rng.integers(0, 9, (cap, 1)).astype(np.int32)]
+            g.insert(*([dev(c) for c in b] if carrier == "device" else b))
+            o.insert_batch(b)
+            for _ in range(4):
+                u = rng.random(batch).astype(np.float32)
+                got = g.sample(0.4, uniforms=dev(u) if carrier == "device" else u)
+                want = o.sample(0.4, uniforms=u)
+                same_sample(got, want)
+                pr = (np.abs(rng.normal(size=batch)) + 1e-3).astype(np.float32)
+                g.update_priorities(got[0], dev(pr) if carrier == "device" else pr)
+                o.update_priorities(want[0], pr)
+            same_tree(g, o)
+    finally:
+        _ffi.set_option(option, 1)
