@@ -360,6 +360,81 @@ def bench_per(ctx, name, rows, batch, steps, warmup, primary):
             "algorithmic_bytes_per_sample": 2 * R + 28 * L_1M + 36}
 
 
+def bench_urb(ctx, steps, warmup):
+    """C1: the DQN loop's buffer work -- uniform buffer cap 100k, 40-byte rows, per step insert 1 row + sample 64"""
+    torch, L, ffi = ctx.torch, ctx.L, ctx.ffi
+    cap, batch, rows = 100_000, 64, C2_ROWS
+    R = sum(rows)
+    st = ctx.stream
+    rb = np.asarray(rows, dtype=np.int64)
+    h = C.c_int64(-1)
+    ffi.check(L.mrl_urb_create(cap, len(rows), rb.ctypes.data, None, 5, C.byref(h)))
+    cols = (C.c_void_p * len(rows))()
+    ffi.check(L.mrl_urb_columns(h.value, cols))
+    fill = [torch.randint(0, 256, (cap, r), dtype=torch.uint8, device="cuda") for r in rows]
+    ffi.check(L.mrl_urb_append(h.value, cap, ffi.ptr_table([f.data_ptr() for f in fill]), st))
+    pool = 64
+    new_rows = [torch.randint(0, 256, (pool, r), dtype=torch.uint8, device="cuda") for r in rows]
+    row_tabs = [ffi.ptr_table([c[i].data_ptr() for c in new_rows]) for i in range(pool)]
+    slots = torch.empty(batch, dtype=torch.int64, device="cuda")
+    outs = [torch.empty((batch, r), dtype=torch.uint8, device="cuda") for r in rows]
+    out_tab = ffi.ptr_table([o.data_ptr() for o in outs])
+
+    def step(i):
+        ffi.check(L.mrl_urb_append(h.value, 1, row_tabs[i % pool], st))
+        ffi.check(L.mrl_urb_sample(h.value, batch, slots.data_ptr(), out_tab, st))
+
+    total_ms, launches = ctx.timed(step, steps, warmup)
+    per = total_ms / steps
+    hbm, peak_src = peaks()
+    alg = 2 * R + (2 * R + 8) * batch
+    ach = alg / (per * 1e-3) / 1e9
+    h_rows = [pinned(ctx, (pool, r), torch.uint8) for r in rows]
+    for a, b in zip(h_rows, new_rows):
+        a.copy_(b.cpu())
+    h_row_tabs = [ffi.ptr_table([c[i].data_ptr() for c in h_rows]) for i in range(pool)]
+    h_slots = pinned(ctx, (batch,), torch.int64)
+    h_out = [pinned(ctx, (batch, r), torch.uint8) for r in rows]
+    h_tab = ffi.ptr_table([o.data_ptr() for o in h_out])
+
+    def step_host(i):
+        ffi.check(L.mrl_urb_append_host(h.value, 1, h_row_tabs[i % pool], st))
+        ffi.check(L.mrl_urb_sample_host(h.value, batch, h_slots.data_ptr(), h_tab, st))
+
+    esteps = max(10, min(steps, 1000))
+    e_ms = ctx.timed_host(step_host, esteps, 3)
+    ffi.check(L.mrl_urb_destroy(h.value))
+    return {"workload": "C1 DQN-shaped uniform buffer cap 100k, 40-byte rows: insert 1 + sample 64 per step",
+            "metric": "uniform_insert_sample_samples_per_s", "value": ctx.world * batch * steps / (total_ms * 1e-3),
+            "unit": "samples/s", "ms_per_step": per, "steps": steps, "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": "copy_seg_kernel + urb_sample_fused_kernel", "achieved": ach,
+                         "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg,
+                         "note": "two launches of a few KB each: launch-latency bound, not bandwidth bound"},
+            "e2e": {"value": ctx.world * batch * esteps / (e_ms * 1e-3), "unit": "samples/s",
+                    "h2d_bytes_per_step": R, "d2h_bytes_per_step": batch * (8 + R), "steps": esteps,
+                    "ms_per_step": e_ms / esteps}}
+
+
+def cpu_urb(seconds=2.0):
+    from oracle import oracle as O
+    rng = np.random.default_rng(1)
+    cap, batch = 100_000, 64
+    shapes, types = [(r,) for r in C2_ROWS], [np.uint8] * len(C2_ROWS)
+    b = O.UniformBufferOracle(batch, cap, shapes, types, seed=5)
+    b.insert([rng.integers(0, 256, size=(cap, r), dtype=np.uint8) for r in C2_ROWS])
+    rows = [[rng.integers(0, 256, size=(r,), dtype=np.uint8) for r in C2_ROWS] for _ in range(64)]
+    for i in range(10):
+        b.insert(rows[i]); b.sample()
+    t0 = time.perf_counter()
+    steps = 0
+    while time.perf_counter() - t0 < seconds:
+        b.insert(rows[steps % 64]); b.sample()
+        steps += 1
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, steps, dt
+
+
 def bench_gae(ctx, steps, warmup):
     """C4: 4096 envs x 2048 steps fp32, gamma .99 lambda .95, random done flags"""
     torch, L, ffi = ctx.torch, ctx.L, ctx.ffi
@@ -595,7 +670,7 @@ def main():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--only", default="all", choices=["all", "c2", "c3", "c4"])
+    ap.add_argument("--only", default="all", choices=["all", "c1", "c2", "c3", "c4"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baselines")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -617,6 +692,10 @@ def main():
         r = bench_gae(ctx, max(10, min(args.steps, 50)), args.warmup)
         (also.append(r) if primary else None)
         primary = primary or r
+    if ctx.world == 1 and args.only in ("all", "c1"):
+        r = bench_urb(ctx, max(20, min(args.steps, 500)), args.warmup)
+        (also.append(r) if primary else None)
+        primary = primary or r
     if ctx.world > 1 and args.only == "all":
         r = bench_per(ctx, "C5 sharded PER 1M/rank batch 4096/rank, root-stat all-gather per sample",
                       C2_ROWS, 4096, max(20, min(args.steps, 300)), args.warmup, False)
@@ -633,6 +712,11 @@ def main():
                     "value": v, "unit": "samples/s", "cores": 1, "kind": "port",
                     "sample": f"{n} steps in {dt:.1f}s of sample+update on the oracle, capacity "
                               f"{32768 if wide else 1_000_000}", "host": host_info()}
+            elif primary["workload"].startswith("C1"):
+                v, n, dt = cpu_urb()
+                primary["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": 1, "kind": "port",
+                                           "sample": f"{n} steps of insert 1 + sample 64 in {dt:.1f}s on the oracle",
+                                           "host": host_info()}
             else:
                 g, npl = cpu_gae(2048, 4096)
                 primary["cpu_baseline"] = {"value": g, "unit": "elements/s", "cores": 1, "kind": "port",
@@ -642,6 +726,11 @@ def main():
                     v, n, dt = cpu_per(C3_ROWS, 512, 32768, seconds=6.0)
                     r["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": 1, "kind": "port",
                                          "sample": f"{n} steps in {dt:.1f}s on a 32768-row oracle buffer (1.8 GB of rows)"}
+                elif r["workload"].startswith("C1"):
+                    v, n, dt = cpu_urb()
+                    r["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": 1, "kind": "port",
+                                         "sample": f"{n} steps of insert 1 + sample 64 in {dt:.1f}s on the oracle "
+                                                   "(through its Python wrapper)"}
                 elif r["workload"].startswith("C4"):
                     g, npl = cpu_gae(2048, 4096)
                     r["cpu_baseline"] = {"value": g, "unit": "elements/s", "cores": 1, "kind": "port",
