@@ -276,7 +276,7 @@ class _options:
 
 
 TM_SHAPES = [(1, 16), (5, 16), (64, 32), (65, 48), (127, 80), (128, 64), (300, 4112), (1000, 96), (2048, 128),
-             (513, 36), (77, 4)]
+             (513, 36), (77, 4), (40, 3552), (33, 3696)]
 
 
 @pytest.mark.parametrize("cols,rpu,groups,stages", [(32, 16, 1, 0), (32, 16, 2, 0), (32, 16, 1, 2), (32, 8, 1, 0),
