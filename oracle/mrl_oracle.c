@@ -478,6 +478,16 @@ void orc_fill_rows(void *col, int64_t nrows, int64_t row_bytes, uint64_t seed) {
   }
 }
 
+/* the same rows as orc_fill_rows, but only those listed (full-size buffers are verified row by row) */
+void orc_fill_rows_at(void *out, const int64_t *rows, int64_t n, int64_t row_bytes, uint64_t seed) {
+  uint8_t *p = (uint8_t *)out;
+  for (int64_t k = 0; k < n; ++k) {
+    const int64_t r = rows[k];
+    for (int64_t o = 0; o < row_bytes; ++o) p[k * row_bytes + o] = mrl_fill_byte(seed, r, o);
+    if (row_bytes >= 8) memcpy(p + k * row_bytes, &r, 8);
+  }
+}
+
 double orc_now(void) {
   struct timespec ts;
   clock_gettime(CLOCK_MONOTONIC, &ts);

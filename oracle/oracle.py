@@ -79,6 +79,8 @@ def lib():
         L.orc_mix_seed.restype = u64
         L.orc_mix_seed.argtypes = [u64, u64]
         L.orc_fill_rows.argtypes = [vp, i64, i64, u64]
+        L.orc_fill_rows_at.argtypes = [vp, vp, i64, i64, u64]
+        L.orc_fill_rows_at.restype = None
         L.orc_now.restype = C.c_double
         _lib = L
     return _lib
@@ -394,6 +396,14 @@ def uniform01(seed, ctr):
 def fill_rows(nrows, row_bytes, seed):
     a = np.empty((nrows, row_bytes), dtype=np.uint8)
     lib().orc_fill_rows(a.ctypes.data, nrows, row_bytes, seed)
+    return a
+
+
+def fill_rows_at(rows, row_bytes, seed):
+    """rows `rows` of fill_rows(...) without materialising the others"""
+    rows = np.ascontiguousarray(rows, dtype=np.int64)
+    a = np.empty((len(rows), row_bytes), dtype=np.uint8)
+    lib().orc_fill_rows_at(a.ctypes.data, rows.ctypes.data, len(rows), row_bytes, seed)
     return a
 
 

@@ -371,3 +371,60 @@ def test_options_only_select_among_equal_paths(option, value):
             same_tree(g, o)
     finally:
         _ffi.set_option(option, 1)
+
+
+def test_full_size_c3_indices_weights_rows():
+    """BASELINE config 3 at full size: capacity 1M, two 84x84x4 uint8 columns (2 x 28.2 GB: row offsets
+    need 64 bits) + action / reward / done, batch 512.  Indices and weights bit-exact against an oracle
+    buffer with the same tree (its rows are 1 byte: the tree does not depend on them); every gathered wide
+    row must be the row the fill function defines for that index, whole, and carry its index in bytes 0..7."""
+    free, _ = torch.cuda.mem_get_info()
+    if free < 70 << 30:
+        pytest.skip("needs 70 GB of free device memory")
+    cap, batch = 1_000_000, 512
+    rb = np.asarray([28224, 4, 4, 1, 28224], dtype=np.int64)
+    h = C.c_int64(-1)
+    L = _ffi.lib()
+    _ffi.check(L.mrl_prb_create(cap, 0.6, 5, rb.ctypes.data, 3, 4, C.byref(h)))
+    try:
+        cols = (C.c_void_p * 5)()
+        _ffi.check(L.mrl_prb_columns(h.value, cols))
+        for c in range(5):
+            _ffi.check(L.mrl_fill_rows(cols[c], cap, int(rb[c]), 100 + c, 0))
+        _ffi.check(L.mrl_prb_push_batch(h.value, cap, cols, 0))  # rows onto themselves: ring full, leaves = max priority
+        o = O.PriorityBufferOracle(0.6, cap, batch, [(1,)], [np.uint8], 3, 4)
+        o.insert_batch([np.zeros((cap, 1), np.uint8)])
+        rng = np.random.default_rng(33)
+        pr = (np.abs(rng.normal(size=cap)) + 1e-3).astype(np.float32)
+        d_idx, d_pr = dev(np.arange(cap)), dev(pr)
+        for s in range(0, cap, 65536):
+            e = min(cap, s + 65536)
+            _ffi.check(L.mrl_prb_update(h.value, d_idx[s:e].data_ptr(), d_pr[s:e].data_ptr(), e - s, 0))
+            o.update_priorities(np.arange(s, e), pr[s:e])
+        idx = torch.empty(batch, dtype=torch.int64, device="cuda")
+        w = torch.empty(batch, dtype=torch.float32, device="cuda")
+        outs = [torch.empty((batch, int(r)), dtype=torch.uint8, device="cuda") for r in rb]
+        tab = _ffi.ptr_table([t.data_ptr() for t in outs])
+        seen_high = False
+        for step in range(4):
+            u = rng.random(batch).astype(np.float32)
+            du = dev(u)
+            _ffi.check(L.mrl_prb_sample(h.value, batch, 0.4, du.data_ptr(), idx.data_ptr(), w.data_ptr(), tab, 0))
+            torch.cuda.synchronize()
+            want = o.sample(0.4, uniforms=u)
+            i = idx.cpu().numpy()
+            assert np.array_equal(i, want[0]), "indices differ"
+            assert np.array_equal(w.cpu().numpy().view(np.uint32), want[1].view(np.uint32)), "weights differ"
+            seen_high = seen_high or bool((i * 28224 >= 1 << 32).any())
+            for c in range(5):
+                got = outs[c].cpu().numpy()
+                assert np.array_equal(got, O.fill_rows_at(i, int(rb[c]), 100 + c)), f"column {c} rows differ"
+            assert np.array_equal(outs[0].cpu().numpy()[:, :8].copy().view(np.int64)[:, 0], i)
+            p2 = (np.abs(rng.normal(size=batch)) + 1e-3).astype(np.float32)
+            dp2 = dev(p2)
+            _ffi.check(L.mrl_prb_update(h.value, idx.data_ptr(), dp2.data_ptr(), batch, 0))
+            o.update_priorities(want[0], p2)
+            torch.cuda.synchronize()
+        assert seen_high  # rows beyond the 4 GiB offset were gathered
+    finally:
+        _ffi.check(L.mrl_prb_destroy(h.value))
