@@ -260,12 +260,52 @@ __global__ void __launch_bounds__(kSampleWarps * 32)
   const int64_t slot = leaf < S.capacity ? leaf : S.capacity - 1;
   dbg_mark(S.dbg, 3);
 
-  // start pulling the row in while the weights are computed
-  if (S.gather_mask && lane < tab.ncols && ((S.gather_mask >> lane) & 1u)) {
+  // The row: all 4-byte words of the narrow columns are ONE list, 4 per lane and pass, every load of a pass
+  // in flight before the first store (column by column, each load waited for its predecessor's store -- the
+  // pointers may alias as far as the compiler knows -- 1.5 us for the four columns of a 40-byte row).  The
+  // first pass (512 bytes) is requested here and travels while the weights are computed.
+  uint32_t val[4];
+  uint32_t *dstp[4];
+  auto row_pass_load = [&](int u0) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      int u = u0 + q * 32 + lane;
+      dstp[q] = nullptr, val[q] = 0u;
+      if (u < S.word_units) {
+        int c = 0;
+        for (;; ++c) {
+          if (!((S.gather_mask >> c) & 1u)) continue;
+          const int w = (int)(tab.row_bytes[c] >> 2);
+          if (u < w) break;
+          u -= w;
+        }
+        const int64_t rb = tab.row_bytes[c];
+        val[q] = *reinterpret_cast<const uint32_t *>(tab.col[c] + slot * rb + 4 * u);
+        dstp[q] = reinterpret_cast<uint32_t *>(tab.io[c] + i * rb + 4 * u);
+      }
+    }
+  };
+  auto row_pass_store = [&]() {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (dstp[q]) *dstp[q] = val[q];
+  };
+  if (S.word_units > 0) {
+    row_pass_load(0);
+  } else if (S.gather_mask && lane < tab.ncols && ((S.gather_mask >> lane) & 1u)) {
     const uint8_t *src = tab.col[lane] + slot * tab.row_bytes[lane];
     asm volatile("prefetch.global.L1 [%0];" ::"l"(src));
   }
   if (S.peers) {
+    // (sharded: everything that does not need the peers' statistics goes first -- the longer this rank
+    // takes to get to its mailbox, the more launch skew between the ranks it absorbs)
+    if (S.word_units > 0) {
+      row_pass_store();
+      for (int u0 = 128; u0 < S.word_units; u0 += 128) {
+        row_pass_load(u0);
+        row_pass_store();
+      }
+    }
     // Fused exchange, part 2: by now the descent has hidden the NVLink latency; lane r polls rank r's
     // words in the local mailbox, then the totals are formed in rank order (as the oracle does).
     float ps = 0.0f, pm = FLT_MAX, pz = 0.0f;
@@ -300,32 +340,12 @@ __global__ void __launch_bounds__(kSampleWarps * 32)
   }
   dbg_mark(S.dbg, 4);
   if (S.word_units > 0) {
-    // all 4-byte words of the narrow columns as ONE list, 4 per lane and pass: every load of a pass is in
-    // flight before the first store (column by column, each load waited for its predecessor's store: the
-    // pointers may alias as far as the compiler knows -- 1.5 us for the four columns of a 40-byte row)
-    for (int u0 = 0; u0 < S.word_units; u0 += 128) {
-      uint32_t val[4];
-      uint32_t *dstp[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        int u = u0 + q * 32 + lane;
-        dstp[q] = nullptr, val[q] = 0u;
-        if (u < S.word_units) {
-          int c = 0;
-          for (;; ++c) {
-            if (!((S.gather_mask >> c) & 1u)) continue;
-            const int w = (int)(tab.row_bytes[c] >> 2);
-            if (u < w) break;
-            u -= w;
-          }
-          const int64_t rb = tab.row_bytes[c];
-          val[q] = *reinterpret_cast<const uint32_t *>(tab.col[c] + slot * rb + 4 * u);
-          dstp[q] = reinterpret_cast<uint32_t *>(tab.io[c] + i * rb + 4 * u);
-        }
+    if (!S.peers) {
+      row_pass_store();
+      for (int u0 = 128; u0 < S.word_units; u0 += 128) {
+        row_pass_load(u0);
+        row_pass_store();
       }
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (dstp[q]) *dstp[q] = val[q];
     }
   } else if (S.gather_mask) {
     for (int c = 0; c < tab.ncols; ++c) {
