@@ -73,12 +73,41 @@ __global__ void __launch_bounds__(256)
 // BufferSample for narrow rows in ONE launch: warp j draws its slot and copies the row of every column
 __global__ void __launch_bounds__(256)
     urb_sample_fused_kernel(const __grid_constant__ ColTable tab, int64_t *slots_out, int64_t n,
-                            uint64_t seed, uint64_t ctr, int64_t count) {
+                            uint64_t seed, uint64_t ctr, int64_t count, int word_units) {
   const int lane = threadIdx.x & 31;
   const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (j >= n) return;
   const int64_t slot = mrl_uniform_below(seed, ctr + (uint64_t)j, count);
   if (slots_out && lane == 0) slots_out[j] = slot;
+  if (word_units > 0) {
+    // every column is whole aligned words: the row is ONE list of words, 4 per lane and pass, all loads of
+    // a pass before its stores (column by column each load waits for the previous column's store: the
+    // pointers may alias as far as the compiler knows)
+    for (int u0 = 0; u0 < word_units; u0 += 128) {
+      uint32_t val[4];
+      uint32_t *dstp[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        int u = u0 + q * 32 + lane;
+        dstp[q] = nullptr, val[q] = 0u;
+        if (u < word_units) {
+          int c = 0;
+          for (;; ++c) {
+            const int w = (int)(tab.row_bytes[c] >> 2);
+            if (u < w) break;
+            u -= w;
+          }
+          const int64_t rb = tab.row_bytes[c];
+          val[q] = *reinterpret_cast<const uint32_t *>(tab.col[c] + slot * rb + 4 * u);
+          dstp[q] = reinterpret_cast<uint32_t *>(tab.io[c] + j * rb + 4 * u);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (dstp[q]) *dstp[q] = val[q];
+    }
+    return;
+  }
   for (int c = 0; c < tab.ncols; ++c) {
     const int64_t rb = tab.row_bytes[c];
     const uint8_t *src = tab.col[c] + slot * rb;
@@ -149,8 +178,11 @@ static int urb_sample_impl(UrbBuffer *b, int64_t n, int64_t *slots_out, void *co
   bool narrow = true;
   for (int c = 0; c < b->ncols; ++c) narrow = narrow && b->row_bytes[c] <= 512;
   if (narrow) {
+    int64_t words = 0;
+    bool whole = true;
+    for (int c = 0; c < b->ncols; ++c) whole = whole && ftab.vec[c] >= 4, words += b->row_bytes[c] / 4;
     urb_sample_fused_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(ftab, slots_out, n, b->seed,
-                                                                          b->ctr, b->count);
+                                                                          b->ctr, b->count, whole ? (int)words : 0);
     MRL_LAUNCHED();
     b->ctr += (uint64_t)n;
     return MRL_OK;
