@@ -416,6 +416,48 @@ def bench_urb(ctx, steps, warmup):
                     "ms_per_step": e_ms / esteps}}
 
 
+def bench_insert(ctx, steps, warmup):
+    """bulk insert (BufferAppend / push with a batch dimension): 2048 Atari-shaped rows per step"""
+    torch, L, ffi = ctx.torch, ctx.L, ctx.ffi
+    cap, n, rows = 65536, 2048, C3_ROWS
+    R = sum(rows)
+    st = ctx.stream
+    rb = np.asarray(rows, dtype=np.int64)
+    src = [torch.randint(0, 256, (n, r), dtype=torch.uint8, device="cuda") for r in rows]
+    src_tab = ffi.ptr_table([t.data_ptr() for t in src])
+    hbm, peak_src = peaks()
+    out = {}
+    h = C.c_int64(-1)
+    ffi.check(L.mrl_urb_create(cap, len(rows), rb.ctypes.data, None, 5, C.byref(h)))
+    ms, launches = ctx.timed(lambda i: ffi.check(L.mrl_urb_append(h.value, n, src_tab, st)), steps, warmup)
+    out["uniform_append"] = {"ms": ms / steps, "GBps": 2 * R * n / (ms / steps * 1e-3) / 1e9, "launches": launches}
+    # e2e: the same rows from pinned host arrays (one staged copy + the ring scatter)
+    h_src = [pinned(ctx, (n, r), torch.uint8) for r in rows]
+    for a, b in zip(h_src, src):
+        a.copy_(b.cpu())
+    h_tab = ffi.ptr_table([t.data_ptr() for t in h_src])
+    esteps = max(5, min(steps, 20))
+    e_ms = ctx.timed_host(lambda i: ffi.check(L.mrl_urb_append_host(h.value, n, h_tab, st)), esteps, 3)
+    e2e = {"value": ctx.world * n * esteps / (e_ms * 1e-3), "unit": "rows/s", "h2d_bytes_per_step": R * n,
+           "d2h_bytes_per_step": 0, "steps": esteps, "ms_per_step": e_ms / esteps}
+    ffi.check(L.mrl_urb_destroy(h.value))
+    ffi.check(L.mrl_prb_create(cap, ALPHA, len(rows), rb.ctypes.data, 7, 0, C.byref(h)))
+    ms, launches = ctx.timed(lambda i: ffi.check(L.mrl_prb_push_batch(h.value, n, src_tab, st)), steps, warmup)
+    out["priority_push_batch(rows + leaves + tree rebuild)"] = {
+        "ms": ms / steps, "GBps": 2 * R * n / (ms / steps * 1e-3) / 1e9, "launches": launches}
+    ffi.check(L.mrl_prb_destroy(h.value))
+    for v in out.values():
+        v["frac"] = v["GBps"] / hbm
+    main = out["uniform_append"]
+    return {"workload": f"insert: {n} Atari-shaped rows ({R} bytes each) per step into a {cap}-row ring",
+            "metric": "insert_rows_per_s", "value": ctx.world * n / (main["ms"] * 1e-3), "unit": "rows/s",
+            "ms_per_step": main["ms"], "steps": steps, "gpu_launches": main["launches"],
+            "roofline": {"bound": "hbm", "kernel": "copy_seg_kernel", "achieved": main["GBps"], "peak": hbm,
+                         "unit": "GB/s", "frac": main["frac"], "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": 2 * R * n},
+            "e2e": e2e, "variants": out}
+
+
 def cpu_urb(seconds=2.0):
     from oracle import oracle as O
     rng = np.random.default_rng(1)
@@ -670,7 +712,7 @@ def main():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--only", default="all", choices=["all", "c1", "c2", "c3", "c4"])
+    ap.add_argument("--only", default="all", choices=["all", "c1", "c2", "c3", "c4", "insert"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baselines")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -696,6 +738,10 @@ def main():
         r = bench_urb(ctx, max(20, min(args.steps, 500)), args.warmup)
         (also.append(r) if primary else None)
         primary = primary or r
+    if ctx.world == 1 and args.only in ("all", "insert"):
+        r = bench_insert(ctx, max(10, min(args.steps, 50)), args.warmup)
+        (also.append(r) if primary else None)
+        primary = primary or r
     if ctx.world > 1 and args.only == "all":
         r = bench_per(ctx, "C5 sharded PER 1M/rank batch 4096/rank, root-stat all-gather per sample",
                       C2_ROWS, 4096, max(20, min(args.steps, 300)), args.warmup, False)
@@ -712,6 +758,8 @@ def main():
                     "value": v, "unit": "samples/s", "cores": 1, "kind": "port",
                     "sample": f"{n} steps in {dt:.1f}s of sample+update on the oracle, capacity "
                               f"{32768 if wide else 1_000_000}", "host": host_info()}
+            elif primary["workload"].startswith("insert"):
+                pass
             elif primary["workload"].startswith("C1"):
                 v, n, dt = cpu_urb()
                 primary["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": 1, "kind": "port",

@@ -147,7 +147,9 @@ int gather_rows(const ColTable &tab, const int64_t *slots, int64_t n, int64_t ca
                 cudaStream_t st, uint32_t col_mask = 0xffffffffu);
 int copy_segments(const ColTable &tab, int64_t dst_row, int64_t src_row, int64_t nrows,
                   cudaStream_t st);
-// to_ring = 1: io rows -> ring rows; 0: ring rows -> io rows
+// to_ring = 1: io rows -> ring rows; 0: ring rows -> io rows; 2: io rows are HOST memory -> ring rows (DMA)
+// batches of at least this many bytes go from host arrays straight into the ring (the *_host entry points)
+constexpr size_t kDirectHostBytes = 256 << 10;
 int copy_segments_dir(const ColTable &tab, int64_t ring_row, int64_t io_row, int64_t nrows,
                       int to_ring, cudaStream_t st);
 

@@ -58,6 +58,14 @@ __global__ void __launch_bounds__(256)
 int copy_segments_dir(const ColTable &tab, int64_t ring_row, int64_t io_row, int64_t nrows,
                       int to_ring, cudaStream_t st) {
   if (nrows <= 0) return MRL_OK;
+  if (to_ring == 2) {
+    // io rows are HOST memory: a run of rows is contiguous in the source and in the ring, so the DMA
+    // engine puts it in place directly (no staging copy, no kernel, no second pass over HBM)
+    for (int c = 0; c < tab.ncols; ++c)
+      MRL_CUDA(cudaMemcpyAsync(tab.col[c] + ring_row * tab.row_bytes[c], tab.io[c] + io_row * tab.row_bytes[c],
+                               (size_t)(nrows * tab.row_bytes[c]), cudaMemcpyHostToDevice, st));
+    return MRL_OK;
+  }
   int64_t max_units = 1;
   for (int c = 0; c < tab.ncols; ++c) {
     int64_t u = nrows * tab.row_bytes[c] / tab.vec[c];

@@ -1208,9 +1208,9 @@ static int rebuild_range(PrbBuffer *b, int64_t lo, int64_t hi, cudaStream_t st) 
   return MRL_OK;
 }
 
-static int prb_push_batch_impl(PrbBuffer *b, int64_t nrows, void *const *src, cudaStream_t st) {
+static int prb_push_batch_impl(PrbBuffer *b, int64_t nrows, void *const *src, cudaStream_t st, int dir = 1) {
   const int64_t cap = b->capacity;
-  if (nrows == 1) {
+  if (nrows == 1 && dir == 1) {
     const int64_t slot = (b->head + 1) % cap;
     ColTable tab;
     fill_table(tab, b, src);
@@ -1227,12 +1227,12 @@ static int prb_push_batch_impl(PrbBuffer *b, int64_t nrows, void *const *src, cu
   ColTable tab;
   fill_table(tab, b, src);
   const int64_t run1 = n < cap - first ? n : cap - first;
-  int rc = copy_segments_dir(tab, first, skip, run1, 1, st);
+  int rc = copy_segments_dir(tab, first, skip, run1, dir, st);
   if (rc) return rc;
   rc = rebuild_range(b, first, first + run1, st);
   if (rc) return rc;
   if (n > run1) {
-    rc = copy_segments_dir(tab, 0, skip + run1, n - run1, 1, st);
+    rc = copy_segments_dir(tab, 0, skip + run1, n - run1, dir, st);
     if (rc) return rc;
     rc = rebuild_range(b, 0, n - run1, st);
     if (rc) return rc;
@@ -1460,6 +1460,14 @@ extern "C" int mrl_prb_push_batch_host(int64_t handle, int64_t nrows, const void
   off[0] = 0;
   for (int c = 0; c < b->ncols; ++c)
     off[c + 1] = off[c] + ((size_t)nrows * b->row_bytes[c] + 255) / 256 * 256;
+  if (off[b->ncols] >= kDirectHostBytes) {
+    // large batch: DMA from the caller's arrays straight into the ring rows, then the leaves and the tree;
+    // the arrays are free again when this returns
+    int rc = prb_push_batch_impl(b, nrows, (void *const *)src_cols, st, 2);
+    if (rc) return rc;
+    MRL_CUDA(cudaStreamSynchronize(st));
+    return MRL_OK;
+  }
   int rc = b->stage.wait();
   if (rc) return rc;
   rc = b->stage.ensure(off[b->ncols]);

@@ -258,3 +258,48 @@ def test_buffer_elements_feed_the_scans_without_a_transpose():
     b = M.discounted_reward(ub.buffer[0].reshape(T, env), 0.99, layout="time_major").cpu().numpy()
     tol = 1e-5 * max(1.0, float(np.abs(want).max()))
     assert np.abs(a - want).max() <= tol and np.abs(b.T - want).max() <= tol
+
+
+def test_large_host_batches_go_straight_into_the_ring():
+    """numpy batches of >= 256 KB are DMA'd from the caller's arrays into the ring rows (no staging copy, no
+    kernel): same columns and cursors as the oracle through a fill, a wrap, an over-long batch, the emplace of
+    the reservoir buffer, and the priority buffer's push; the arrays may be overwritten right after the call"""
+    cap = 300
+    shapes, types = [(84, 84, 4), (1,)], [np.uint8, np.int32]
+    g = M.UniformReplayBuffer(16, cap, shapes, types, carrier="numpy")
+    o = O.UniformBufferOracle(16, cap, shapes, types)
+    rng = np.random.default_rng(12)
+    launches = _ffi.launch_count()
+    for n in (200, 170, 40, 650):
+        obs = rng.integers(0, 256, size=(n, 84, 84, 4), dtype=np.uint8)
+        act = rng.integers(0, 18, size=(n, 1)).astype(np.int32)
+        g.insert([obs, act])
+        o.insert([obs.copy(), act.copy()])
+        obs[:] = 0  # the call has finished with the arrays
+        act[:] = 0
+        assert (g.count, g.head) == o.state()
+    assert _ffi.launch_count() == launches  # copies only
+    same_columns(g, o)
+    # emplace at a physical slot (ReservoirReplayBufferPush)
+    L = _ffi.lib()
+    obs = rng.integers(0, 256, size=(20, 84, 84, 4), dtype=np.uint8)
+    act = rng.integers(0, 18, size=(20, 1)).astype(np.int32)
+    _ffi.check(L.mrl_urb_write_at_host(g._handle, 33, 20, _ffi.ptr_table([obs.ctypes.data, act.ctypes.data]), 0))
+    cols = o.columns()
+    cols[0][33:53], cols[1][33:53] = obs, act
+    same_columns(g, o)
+    # priority buffer: rows by DMA, then leaves and tree as always
+    pg = M.PriorityReplayBuffer(0.6, cap, 16, shapes, types, 1, 2, carrier="numpy")
+    po = O.PriorityBufferOracle(0.6, cap, 16, shapes, types, 1, 2)
+    for n in (200, 170):
+        obs = rng.integers(0, 256, size=(n, 84, 84, 4), dtype=np.uint8)
+        act = rng.integers(0, 18, size=(n, 1)).astype(np.int32)
+        pg.insert(obs, act)
+        po.insert_batch([obs.copy(), act.copy()])
+        obs[:] = 0
+    gs, gm = pg.tree()
+    os_, om = po.tree()
+    assert np.array_equal(gs[1:], os_[1:]) and np.array_equal(gm[1:], om[1:]) and pg.info() == po.info()
+    u = rng.random(16).astype(np.float32)
+    got, want = pg.sample(0.4, uniforms=u), po.sample(0.4, uniforms=u)
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[2], want[2]) and np.array_equal(got[3], want[3])
