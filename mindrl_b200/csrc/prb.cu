@@ -772,29 +772,45 @@ __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __gri
       const uint32_t leaf_node = (uint32_t)(U.cap2 + leaf);
       float p = 0.0f;
       float sib_s[kWalkLevels], sib_m[kWalkLevels];
+      // The sibling loads must be IN FLIGHT while p**alpha is evaluated.  Behind a call (prb_pow_fn) the
+      // compiler sinks them to their uses in the walk -- values that live across a call would have to be
+      // spilled first, i.e. waited for -- and the walk becomes nine dependent L2 round trips (measured
+      // 1.5 us for the walk).  So here the loads are volatile and the power is inlined.
 #pragma unroll
       for (int d = 0; d < kWalkLevels; ++d) {
         sib_s[d] = 0.0f, sib_m[d] = FLT_MAX;
         if (on && d < nlev) {
           const uint32_t sn = (leaf_node >> d) ^ 1u;
-          sib_s[d] = __ldcg(U.sum + sn);
-          sib_m[d] = __ldcg(U.mn + sn);
+          asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(sib_s[d]) : "l"(U.sum + sn) : "memory");
+          asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(sib_m[d]) : "l"(U.mn + sn) : "memory");
         }
       }
       if (on) {
-        p = prb_pow_fn(ld_pr(k), U.alpha);
+        p = mrl_priority_pow(ld_pr(k), U.alpha);
         local_max = p > local_max ? p : local_max;
       }
-      // Partners are found by comparing against the share's m <= 32 entries one shuffle at a time: m is 2
-      // on average (256 entries over 128 CTAs).  (match.any did this in one instruction per level, but it
-      // costs ~0.3 us when all 32 keys differ: 5.5 of the kernel's 10 us were spent in the ten of them.)
+      // Who meets whom depends on the leaf numbers alone, so it is worked out from ONE pass over the share's
+      // m <= 32 entries (m is 2 on average: 256 entries over 128 CTAs), before any value is needed: the
+      // paths of two leaves are siblings exactly at the level of the highest bit in which the leaf numbers
+      // differ; equal leaves are duplicates, of which the highest batch position provides the value.
+      // partner lane + 32 of level d sits in bits 6d..6d+5 of `meet`.  (match.any did the search in one
+      // instruction per level, but costs ~0.3 us when all 32 keys differ; a shuffle loop per level still
+      // cost 0.16 us per level.)
       const int m = total_mine;
-      // leaf level: among the entries of one leaf the highest batch position provides the value
       int win_k = k, win_lane = tid;
+      unsigned long long meet = 0ull;
       for (int j = 0; j < m; ++j) {
         const uint32_t lj = __shfl_sync(FULL, leaf_node, j);
         const int kj = __shfl_sync(FULL, k, j);
-        if (on && lj == leaf_node && kj > win_k) win_k = kj, win_lane = j;
+        const uint32_t x = lj ^ leaf_node;
+        if (on) {
+          if (x == 0u) {
+            if (kj > win_k) win_k = kj, win_lane = j;
+          } else {
+            const int hb = 31 - __clz(x);
+            if (hb < nlev) meet = (meet & ~(63ull << (6 * hb))) | ((unsigned long long)(32 | j) << (6 * hb));
+          }
+        }
       }
       float vs = __shfl_sync(FULL, p, win_lane), vm = vs;
       if (on && k == win_k) {
@@ -802,30 +818,32 @@ __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __gri
         __stcg(U.mn + leaf_node, vm);
       }
       if (blockIdx.x == 0) dbg_mark_gt(U.dbg, 10);
+      // the walk itself is branch-free register work (two shuffles, an add and a min per level); the
+      // nodes are stored afterwards, all at once
+      float lv_s[kWalkLevels + 1], lv_m[kWalkLevels + 1];
 #pragma unroll
       for (int d = 0; d < kWalkLevels; ++d) {
+        lv_s[d] = vs, lv_m[d] = vm;  // value of the path's node at level d (d = 0: the leaf)
         if (d < nlev) {
-          const uint32_t node = on ? leaf_node >> d : 0u;  // (0 is never a sibling: the root's index is 1)
-          if (d > 0 && on) {
-            __stcg(U.sum + node, vs);
-            __stcg(U.mn + node, vm);
-          }
           // entries whose paths have merged carry identical values: any lane holding the sibling will do
-          int src = -1;
-          for (int j = 0; j < m; ++j) {
-            const uint32_t nj = __shfl_sync(FULL, node, j);
-            if (nj == (node ^ 1u)) src = j;
-          }
-          const float o_s = __shfl_sync(FULL, vs, src < 0 ? tid : src), o_m = __shfl_sync(FULL, vm, src < 0 ? tid : src);
-          const float os = src >= 0 ? o_s : sib_s[d], om = src >= 0 ? o_m : sib_m[d];
+          const int e = (int)(meet >> (6 * d)) & 63;
+          const int src = e & 32 ? e & 31 : tid;
+          const float o_s = __shfl_sync(FULL, vs, src), o_m = __shfl_sync(FULL, vm, src);
+          const float os = e & 32 ? o_s : sib_s[d], om = e & 32 ? o_m : sib_m[d];
           vs = __fadd_rn(vs, os);
           vm = om < vm ? om : vm;
         }
       }
-      if (on && nlev > 0) {
-        const uint32_t node = leaf_node >> nlev;
-        __stcg(U.sum + node, vs);
-        __stcg(U.mn + node, vm);
+      lv_s[kWalkLevels] = vs, lv_m[kWalkLevels] = vm;
+      if (on) {
+#pragma unroll
+        for (int d = 1; d <= kWalkLevels; ++d) {
+          if (d <= nlev) {
+            const uint32_t node = leaf_node >> d;
+            __stcg(U.sum + node, lv_s[d]);
+            __stcg(U.mn + node, lv_m[d]);
+          }
+        }
       }
     }
   } else if (dense) {
@@ -989,14 +1007,20 @@ __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __gri
 
   if (blockIdx.x == 0) dbg_mark_gt(U.dbg, 11);
   // ---- the last CTA to get here rebuilds the top levels ------------------------------------------
-  __threadfence();
+  // every thread's tree stores happen-before the block barrier; thread 0's acq_rel ticket at gpu scope then
+  // publishes them (release, cumulative over the barrier) and, in the last CTA, acquires the other CTAs'.
+  // One fence in one thread instead of __threadfence() in all 512 (0.45 us).
   __syncthreads();
-  if (tid == 0) s_last = atomicAdd(&U.state->done_ctas, 1u) == gridDim.x - 1 ? 1u : 0u;
+  if (tid == 0) {
+    unsigned int ticket;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(ticket) : "l"(&U.state->done_ctas) : "memory");
+    s_last = ticket == gridDim.x - 1 ? 1u : 0u;
+  }
   __syncthreads();
   if (blockIdx.x == 0) dbg_mark_gt(U.dbg, 12);
   if (!s_last) return;
   dbg_mark_gt(U.dbg, 13);
-  __threadfence();
+  // (thread 0 acquired with its ticket, the barrier hands that to the CTA, and the loads below bypass L1)
   if (__builtin_expect(width == 4 * kSubThreads && nthr == kSubThreads, 1)) {
     // 2048 level-11 nodes, 4 per thread: two levels in registers, five by warp shuffles, the last
     // four by one warp -- one block barrier instead of eleven, no shared-memory tree
