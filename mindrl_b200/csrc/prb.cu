@@ -6,25 +6,34 @@
 //                  as in the reference)
 //   sum[2*cap2], mn[2*cap2]   fp32 segment tree in heap order (root = 1, children 2i / 2i+1,
 //                  leaves at cap2 + slot, cap2 = capacity rounded up to a power of two), stored as
-//                  two arrays: the descent reads only `sum`, so a 32-descendant hop is one 128-byte
-//                  line.
-//   tag[cap2]      uint64 (call epoch << 32 | batch position): last-writer-wins arbiter of update
-//   state          {max_priority}
+//                  two arrays: the descent reads only `sum`, so the 128 descendants seven levels below
+//                  a node are four consecutive 128-byte lines.
+//   tag[cap2]      uint64 (call epoch << 32 | batch position): last-writer-wins arbiter of the one-CTA
+//                  update kernel
+//   state          {max_priority, done_ctas}
 //
-// Kernels
-//   prb_sample_kernel   warp per sample.  Top <=10 levels of `sum` staged in shared memory per CTA;
-//                       below that the warp hops 5 levels per step: one coalesced 128-byte load of
-//                       the 32 descendants, pairwise sums rebuilt with shuffles (bit-identical to the
-//                       stored inner nodes because every parent is fl(left+right)), then five
-//                       shuffle-compare steps.  4 dependent L2 loads instead of 20 for 2^20 leaves.
-//                       Importance weights and small-row gather are fused behind the descent.
-//   prb_update_kernel   one CTA.  atomicMax tag arbitration -> winners write leaves -> level-synchronous
-//                       parent recompute for the lower levels -> top 10 levels recomputed in shared
-//                       memory.  Parents are always recomputed from both children (never delta
-//                       atomics), so the tree equals the sequential oracle's bit for bit.
-//   prb_push_kernel     one warp: row write, leaf <- max_priority, 20 sibling loads in parallel, path
-//                       recomputed through shuffles.
-//   prb_rebuild_kernel  range rebuild after a batched push.
+// Kernels (the defaults; DESIGN.md section 5 has the measurements)
+//   prb_sample_kernel      warp per sample.  From the root the warp hops 7 levels per dependent load:
+//                          float4 per lane (the 128 descendants), two levels rebuilt inside the lane and
+//                          five with shuffles (bit-identical to the stored inner nodes because every
+//                          parent is fl(left+right)), five shuffle-compare steps to the lane and two
+//                          inside its quad: 3 dependent loads for 2^20 leaves.  Importance weights (two
+//                          pows side by side on two lanes) and the narrow columns (one list of words,
+//                          requested before the weights are computed) are fused behind the descent; in
+//                          the sharded buffer the kernel also exchanges the ranks' root statistics
+//                          through peer mailboxes.
+//   prb_update_sub_kernel  128..512 CTAs own the subtrees below level 11.  Normal case (a share of <= 32
+//                          entries): one warp -- all path siblings in one round trip, who-meets-whom from
+//                          one shuffle pass (highest differing bit of two leaf numbers), branch-free
+//                          register walk, node stores afterwards.  Larger shares: thread per entry with a
+//                          shared-memory list, or whole subtrees rebuilt in shared memory.  The last CTA
+//                          (acq_rel ticket) rebuilds the top 11 levels.  Parents are always recomputed
+//                          from both children (never delta atomics), so the tree equals the sequential
+//                          oracle's bit for bit.
+//   prb_update_kernel, prb_update_walk_kernel   one-CTA variants (small trees / MRL_UPDATE_PATH).
+//   prb_push_kernel        one warp: row write, leaf <- max_priority, sibling loads in parallel, path
+//                          recomputed through shuffles.
+//   prb_rebuild_kernel     range rebuild after a batched push.
 #include <float.h>
 #include <stdlib.h>
 #include <string.h>
@@ -674,9 +683,9 @@ __global__ void __launch_bounds__(kWalkThreads)
 // the batch is spread over kSubCtas CTAs by ownership of the subtrees below level kTopLevels: the
 // lower levels of different subtrees never meet, every CTA scans the index list, keeps the entries
 // that fall into its subtrees, loads all siblings of its paths in one round trip and walks the paths
-// up in registers, exchanging values between paths that merge through a small shared-memory list
-// (typically 2..32 entries per CTA: a linear scan).  The last CTA to finish (atomic ticket after a
-// __threadfence) rebuilds the top levels in shared memory.  Parents are fl(left+right)/min of their
+// up in registers; paths that merge exchange values by shuffles (shares of <= 32 entries: one warp) or
+// through a small shared-memory list.  The last CTA to finish (acq_rel ticket behind the block
+// barrier) rebuilds the top levels.  Parents are fl(left+right)/min of their
 // children exactly as in the sequential oracle; duplicates of a leaf resolve to the highest batch
 // position; max_priority takes every processed priority.
 constexpr int kSubCtas = 128;
