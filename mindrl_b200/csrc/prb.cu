@@ -711,6 +711,10 @@ __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __gri
   __shared__ int s_cnt;
   __shared__ unsigned int s_dirty;  // bit j: owned subtree blockIdx.x + j*gridDim.x has an entry
   __shared__ unsigned int s_last;
+  // one list per owned subtree = per warp (width / gridDim <= 16 subtrees): subtrees never meet below the
+  // split, so every warp walks its own subtree's entries independently
+  __shared__ int s_cw[kSubThreads / 32];
+  __shared__ int s_kw[kSubThreads / 32][32];
   int *s_k = s_raw;                                                 // batch position of each entry
   uint32_t *s_node = reinterpret_cast<uint32_t *>(s_raw + kSubMaxLocal);
   float2 *s_val = reinterpret_cast<float2 *>(s_raw + 2 * kSubMaxLocal);
@@ -746,9 +750,11 @@ __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __gri
   // this CTA owns the subtrees (level-`split` nodes) congruent to blockIdx.x mod gridDim.x: a
   // contiguous run of leaves is spread over many CTAs
   if (tid == 0) s_cnt = 0, s_dirty = 0u;
+  if (tid < kSubThreads / 32) s_cw[tid] = 0;
   __syncthreads();
+  const bool per_warp = width % G == 0 && width / G <= nthr / 32 && nthr == kSubThreads;
   {
-    // one scan: count this CTA's share, note its dirty subtrees, and optimistically build the entry list
+    // one scan: count this CTA's share, note its dirty subtrees, and optimistically build the entry lists
     unsigned int dirty = 0u;
     for (int64_t k = tid; k < U.n; k += nthr) {
       const int top = (int)(ld_idx(k) >> nlev);
@@ -756,27 +762,42 @@ __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __gri
         dirty |= 1u << ((top / G) & 31);
         const int pos = atomicAdd(&s_cnt, 1);
         if (pos < kSubMaxLocal) s_k[pos] = (int)k;
+        if (per_warp) {
+          const int w = (top / G) & (kSubThreads / 32 - 1);
+          const int pw = atomicAdd(&s_cw[w], 1);
+          if (pw < 32) s_kw[w][pw] = (int)k;
+        }
       }
     }
     if (dirty) atomicOr(&s_dirty, dirty);
   }
   __syncthreads();
+  // a subtree with more than 32 entries sends the whole CTA down the general paths (the counts are read
+  // AFTER the barrier: a __syncthreads_or would evaluate its predicate before the other threads' atomics)
+  bool crowded = false;
+#pragma unroll
+  for (int w = 0; w < kSubThreads / 32; ++w) crowded = crowded || s_cw[w] > 32;
   const int total_mine = s_cnt;
   const unsigned int dirty_mask = s_dirty;
+  const bool warp_mode = per_warp && !crowded && total_mine > 0;
+  const int wid = tid >> 5, lane = tid & 31;
+  const int *my_list = warp_mode ? s_kw[wid] : s_k;
+  const int my_m = warp_mode ? s_cw[wid] : (wid == 0 && total_mine <= 32 ? total_mine : 0);
   __syncthreads();
   if (blockIdx.x == 0) dbg_mark_gt(U.dbg, 9);
 
   const int S = 1 << nlev;  // leaves per subtree
   const bool dense = total_mine > kSubDenseAt && 2 * S <= (2 << kTopLevels) && S <= 4 * kSubMaxLocal &&
                      (width + G - 1) / G <= 32;
-  if (__builtin_expect(total_mine > 0 && total_mine <= 32, 1)) {  // (never dense: that needs > 128 entries)
-    // ---- small share (the normal case): one warp, no barriers, no shared-memory exchange ----------
-    // Lanes whose path nodes are siblings find each other by comparing against every entry of the share
+  if (__builtin_expect(warp_mode || (total_mine > 0 && total_mine <= 32), 1)) {
+    // ---- the normal case: a warp per owned subtree (or one warp for the whole share when the CTA owns
+    // more subtrees than it has warps), no barriers, no shared-memory exchange -------------------------
+    // Lanes whose path nodes are siblings find each other by comparing against every entry of the list
     // (shuffles); duplicates of a leaf resolve to the highest batch position the same way.
-    if (tid < 32) {
+    if (my_m > 0) {
       constexpr unsigned FULL = 0xffffffffu;
-      const bool on = tid < total_mine;
-      const int k = on ? s_k[tid] : -1;
+      const bool on = lane < my_m;
+      const int k = on ? my_list[lane] : -1;
       const int64_t leaf = on ? ld_idx(k) : 0;
       const uint32_t leaf_node = (uint32_t)(U.cap2 + leaf);
       float p = 0.0f;
@@ -798,15 +819,15 @@ __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __gri
         p = mrl_priority_pow(ld_pr(k), U.alpha);
         local_max = p > local_max ? p : local_max;
       }
-      // Who meets whom depends on the leaf numbers alone, so it is worked out from ONE pass over the share's
-      // m <= 32 entries (m is 2 on average: 256 entries over 128 CTAs), before any value is needed: the
+      // Who meets whom depends on the leaf numbers alone, so it is worked out from ONE pass over the list's
+      // m <= 32 entries (a handful: n entries over 2048 subtrees), before any value is needed: the
       // paths of two leaves are siblings exactly at the level of the highest bit in which the leaf numbers
       // differ; equal leaves are duplicates, of which the highest batch position provides the value.
       // partner lane + 32 of level d sits in bits 6d..6d+5 of `meet`.  (match.any did the search in one
       // instruction per level, but costs ~0.3 us when all 32 keys differ; a shuffle loop per level still
       // cost 0.16 us per level.)
-      const int m = total_mine;
-      int win_k = k, win_lane = tid;
+      const int m = my_m;
+      int win_k = k, win_lane = lane;
       unsigned long long meet = 0ull;
       for (int j = 0; j < m; ++j) {
         const uint32_t lj = __shfl_sync(FULL, leaf_node, j);
@@ -836,7 +857,7 @@ __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __gri
         if (d < nlev) {
           // entries whose paths have merged carry identical values: any lane holding the sibling will do
           const int e = (int)(meet >> (6 * d)) & 63;
-          const int src = e & 32 ? e & 31 : tid;
+          const int src = e & 32 ? e & 31 : lane;
           const float o_s = __shfl_sync(FULL, vs, src), o_m = __shfl_sync(FULL, vm, src);
           const float os = e & 32 ? o_s : sib_s[d], om = e & 32 ? o_m : sib_m[d];
           vs = __fadd_rn(vs, os);
@@ -1361,8 +1382,13 @@ static int prb_update_impl(PrbBuffer *b, const int64_t *indices, const float *pr
     prb_update_walk_kernel<<<1, threads, smem, st>>>(U, bits);
   } else if (g_update_path == 0 && b->levels - kTopLevels <= kWalkLevels && b->levels > kTopLevels &&
              n < (1LL << 31)) {
-    int ctas = kSubCtas;  // 128..512 so that a CTA's share stays within one warp (~n/ctas entries)
-    while (ctas < 512 && n > 8 * (int64_t)ctas) ctas <<= 1;
+    // 128 CTAs x 16 warps = one warp per level-11 subtree (n / 2048 entries each).  More CTAs (with their
+    // launch ramp: 512 x 512 threads put up to four CTAs on an SM one after the other, and the last CTA of
+    // the grid finished at 12.4 us where the first finished at 5.8) only for batches whose subtrees overflow
+    // a warp anyway.
+    int ctas = kSubCtas;
+    if (n > 32768)
+      while (ctas < 512 && n > 8 * (int64_t)ctas) ctas <<= 1;
     static const InlineBatch none = {};
     if (inl) MRL_CUDA(launch_pdl(prb_update_sub_kernel<true>, dim3(ctas), dim3(kSubThreads), 0, st, U, *inl));
     else MRL_CUDA(launch_pdl(prb_update_sub_kernel<false>, dim3(ctas), dim3(kSubThreads), 0, st, U, none));

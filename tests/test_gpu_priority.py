@@ -428,3 +428,30 @@ def test_full_size_c3_indices_weights_rows():
         assert seen_high  # rows beyond the 4 GiB offset were gathered
     finally:
         _ffi.check(L.mrl_prb_destroy(h.value))
+
+
+@pytest.mark.parametrize("pattern", ["one_subtree", "two_subtrees_one_cta", "mixed"])
+def test_update_shares_that_overflow_a_warp(pattern):
+    """the update kernel gives each level-11 subtree to a warp (<= 32 entries); a crowded subtree must send the
+    CTA down the general paths -- every time (the decision once raced with the counting)"""
+    rng = np.random.default_rng(21)
+    cap, batch = 1 << 20, 256
+    shapes, types = [(1,)], [np.int32]
+    g = M.PriorityReplayBuffer(0.6, cap, batch, shapes, types, 0, 1)
+    o = O.PriorityBufferOracle(0.6, cap, batch, shapes, types, 0, 1)
+    b = [np.arange(cap, dtype=np.int32)[:, None]]
+    g.insert(*[dev(c) for c in b])
+    o.insert_batch(b)
+    for rep in range(20):
+        if pattern == "one_subtree":          # 512 leaves per subtree: 200 entries in one of them
+            idx = rng.integers(0, 512, size=200) + 512 * int(rng.integers(0, 2048))
+        elif pattern == "two_subtrees_one_cta":  # subtrees t and t + 128 belong to the same CTA, different warps
+            t = int(rng.integers(0, 128))
+            idx = np.concatenate([rng.integers(0, 512, size=40) + 512 * t, rng.integers(0, 512, size=20) + 512 * (t + 128)])
+        else:
+            idx = np.concatenate([rng.integers(0, cap, size=150), rng.integers(0, 512, size=33) + 512 * 7])
+        idx = idx[idx < cap].astype(np.int64)
+        pr = (np.abs(rng.normal(size=idx.size)) + 1e-3).astype(np.float32)
+        g.update_priorities(dev(idx), dev(pr))
+        o.update_priorities(idx, pr)
+        same_tree(g, o)
