@@ -702,7 +702,9 @@ struct InlineBatch {
   float pr[kInlineMax];
 };
 
-template <bool INL>
+// PW: a warp per owned subtree (batches above 1024 entries; compiled apart so that the learner-sized
+// batches keep the leaner kernel: 6.6 against 6.9 us at 256 entries)
+template <bool INL, bool PW>
 __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __grid_constant__ UpdateArgs U,
                                                                      const __grid_constant__ InlineBatch IB) {
   __shared__ float ssum[2 << kTopLevels];
@@ -713,8 +715,8 @@ __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __gri
   __shared__ unsigned int s_last;
   // one list per owned subtree = per warp (width / gridDim <= 16 subtrees): subtrees never meet below the
   // split, so every warp walks its own subtree's entries independently
-  __shared__ int s_cw[kSubThreads / 32];
-  __shared__ int s_kw[kSubThreads / 32][32];
+  __shared__ int s_cw[PW ? kSubThreads / 32 : 1];
+  __shared__ int s_kw[PW ? kSubThreads / 32 : 1][32];
   int *s_k = s_raw;                                                 // batch position of each entry
   uint32_t *s_node = reinterpret_cast<uint32_t *>(s_raw + kSubMaxLocal);
   float2 *s_val = reinterpret_cast<float2 *>(s_raw + 2 * kSubMaxLocal);
@@ -750,9 +752,9 @@ __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __gri
   // this CTA owns the subtrees (level-`split` nodes) congruent to blockIdx.x mod gridDim.x: a
   // contiguous run of leaves is spread over many CTAs
   if (tid == 0) s_cnt = 0, s_dirty = 0u;
-  if (tid < kSubThreads / 32) s_cw[tid] = 0;
+  if (PW && tid < kSubThreads / 32) s_cw[tid] = 0;
   __syncthreads();
-  const bool per_warp = width % G == 0 && width / G <= nthr / 32 && nthr == kSubThreads;
+  const bool per_warp = PW && width % G == 0 && width / G <= nthr / 32 && nthr == kSubThreads;
   {
     // one scan: count this CTA's share, note its dirty subtrees, and optimistically build the entry lists
     unsigned int dirty = 0u;
@@ -762,7 +764,7 @@ __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __gri
         dirty |= 1u << ((top / G) & 31);
         const int pos = atomicAdd(&s_cnt, 1);
         if (pos < kSubMaxLocal) s_k[pos] = (int)k;
-        if (per_warp) {
+        if (PW && per_warp) {
           const int w = (top / G) & (kSubThreads / 32 - 1);
           const int pw = atomicAdd(&s_cw[w], 1);
           if (pw < 32) s_kw[w][pw] = (int)k;
@@ -775,14 +777,16 @@ __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __gri
   // a subtree with more than 32 entries sends the whole CTA down the general paths (the counts are read
   // AFTER the barrier: a __syncthreads_or would evaluate its predicate before the other threads' atomics)
   bool crowded = false;
+  if (PW && per_warp) {
 #pragma unroll
-  for (int w = 0; w < kSubThreads / 32; ++w) crowded = crowded || s_cw[w] > 32;
+    for (int w = 0; w < kSubThreads / 32; ++w) crowded = crowded || s_cw[w] > 32;
+  }
   const int total_mine = s_cnt;
   const unsigned int dirty_mask = s_dirty;
   const bool warp_mode = per_warp && !crowded && total_mine > 0;
   const int wid = tid >> 5, lane = tid & 31;
-  const int *my_list = warp_mode ? s_kw[wid] : s_k;
-  const int my_m = warp_mode ? s_cw[wid] : (wid == 0 && total_mine <= 32 ? total_mine : 0);
+  const int *my_list = PW && warp_mode ? s_kw[wid] : s_k;
+  const int my_m = PW && warp_mode ? s_cw[wid] : (wid == 0 && total_mine <= 32 ? total_mine : 0);
   __syncthreads();
   if (blockIdx.x == 0) dbg_mark_gt(U.dbg, 9);
 
@@ -1390,8 +1394,10 @@ static int prb_update_impl(PrbBuffer *b, const int64_t *indices, const float *pr
     if (n > 32768)
       while (ctas < 512 && n > 8 * (int64_t)ctas) ctas <<= 1;
     static const InlineBatch none = {};
-    if (inl) MRL_CUDA(launch_pdl(prb_update_sub_kernel<true>, dim3(ctas), dim3(kSubThreads), 0, st, U, *inl));
-    else MRL_CUDA(launch_pdl(prb_update_sub_kernel<false>, dim3(ctas), dim3(kSubThreads), 0, st, U, none));
+    if (inl) MRL_CUDA(launch_pdl(prb_update_sub_kernel<true, false>, dim3(ctas), dim3(kSubThreads), 0, st, U, *inl));
+    else if (n > 1024)
+      MRL_CUDA(launch_pdl(prb_update_sub_kernel<false, true>, dim3(ctas), dim3(kSubThreads), 0, st, U, none));
+    else MRL_CUDA(launch_pdl(prb_update_sub_kernel<false, false>, dim3(ctas), dim3(kSubThreads), 0, st, U, none));
   } else {
     prb_update_kernel<<<1, 1024, 0, st>>>(U);
   }

@@ -450,6 +450,8 @@ def test_update_shares_that_overflow_a_warp(pattern):
             idx = np.concatenate([rng.integers(0, 512, size=40) + 512 * t, rng.integers(0, 512, size=20) + 512 * (t + 128)])
         else:
             idx = np.concatenate([rng.integers(0, cap, size=150), rng.integers(0, 512, size=33) + 512 * 7])
+        if rep % 2:  # batches above 1024 entries use a warp per subtree: crowd one while the rest is sparse
+            idx = np.concatenate([idx, rng.integers(0, cap, size=1500)])
         idx = idx[idx < cap].astype(np.int64)
         pr = (np.abs(rng.normal(size=idx.size)) + 1e-3).astype(np.float32)
         g.update_priorities(dev(idx), dev(pr))
