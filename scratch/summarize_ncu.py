@@ -58,15 +58,15 @@ if __name__ == "__main__":
                      ("prof_c4_r1.ncu-rep", "r1_ncu_full_c4_scan_kernels"),
                      ("prof_c4_r1b.ncu-rep", "r1_ncu_full_c4_tma_scan_kernels"),
                      ("prof_c2_r1b.ncu-rep", "r1_ncu_full_c2_per_kernels_pdl"), ("prof_c3_r1b.ncu-rep", "r1_ncu_full_c3_per_kernels_pdl"), ("prof_scan_r1e.ncu-rep", "r1_ncu_full_wtile_before_fastpath"),
-                     ("prof_c2_s6.ncu-rep", "r1_ncu_full_c2_per_kernels_s6"), ("prof_c3_s6.ncu-rep", "r1_ncu_full_c3_per_kernels_s6"),
-                     ("prof_c4_s6.ncu-rep", "r1_ncu_full_c4_tma_scan_kernels_s6")]:
+                     ("prof_c2_s7.ncu-rep", "r1_ncu_full_c2_per_kernels_s7"), ("prof_c3_s7.ncu-rep", "r1_ncu_full_c3_per_kernels_s7"),
+                     ("prof_c4_s7.ncu-rep", "r1_ncu_full_c4_tma_scan_kernels_s7")]:
         p = os.path.join(g, rep)
         if os.path.exists(p):
             for d in report(p, tag):
                 print(tag, d["kernel"][:60], d["gpu__time_duration.sum"], d.get("gpu__time_duration.sum_unit"), round(d["dram_traffic_bytes"] / 1e6, 2), "MB")
     # per-launch traffic of the TMA scan kernels -> profiles/r1_traffic.json (bench.py's roofline.traffic)
     tp = os.path.join(OUT, "r1_traffic.json")
-    tj = os.path.join(OUT, "r1_ncu_full_c4_tma_scan_kernels_s6.json")
+    tj = os.path.join(OUT, "r1_ncu_full_c4_tma_scan_kernels_s7.json")
     if os.path.exists(tp) and os.path.exists(tj):
         t = json.load(open(tp))
         for d in json.load(open(tj)):
@@ -75,9 +75,9 @@ if __name__ == "__main__":
                                "dram_traffic_bytes": int(d["dram_traffic_bytes"]),
                                "dram_read_bytes": int(d["dram__bytes_read.sum"]),
                                "dram_write_bytes": int(d["dram__bytes_write.sum"]), "launches_captured": 1,
-                               "source": "profiles/r1_ncu_full_c4_tma_scan_kernels_s6.json (ncu --set full --clock-control none; cold caches, serialised)"}
+                               "source": "profiles/r1_ncu_full_c4_tma_scan_kernels_s7.json (ncu --set full --clock-control none; cold caches, serialised)"}
         json.dump(t, open(tp, "w"), indent=1)
-    for cfg, tag in (("c2", "r1_ncu_full_c2_per_kernels_s6"), ("c3", "r1_ncu_full_c3_per_kernels_s6")):
+    for cfg, tag in (("c2", "r1_ncu_full_c2_per_kernels_s7"), ("c3", "r1_ncu_full_c3_per_kernels_s7")):
         tj = os.path.join(OUT, tag + ".json")
         if os.path.exists(tp) and os.path.exists(tj):
             t = json.load(open(tp))
@@ -95,8 +95,8 @@ if __name__ == "__main__":
                                       "launches_captured": n,
                                       "source": f"profiles/{tag}.json (ncu --set full --clock-control none; cold caches, serialised)"}
             json.dump(t, open(tp, "w"), indent=1)
-    if os.path.exists(os.path.join(g, "launches_s6.csv")):
-        launches(os.path.join(g, "launches_s6.csv"), "r1_launch_list_bench_steps20_s6")
+    if os.path.exists(os.path.join(g, "launches_s7.csv")):
+        launches(os.path.join(g, "launches_s7.csv"), "r1_launch_list_bench_steps20_s7")
     if os.path.exists(os.path.join(g, "launches_r1b.csv")):
         launches(os.path.join(g, "launches_r1b.csv"), "r1_launch_list_bench_steps20_final")
     if os.path.exists(os.path.join(g, "launches_r1.csv")):
