@@ -994,6 +994,19 @@ static int launch_scan_hd(ScanArgs A, int32_t layout, int32_t mode, cudaStream_t
       const size_t tiles = (size_t)nch * n_wgroups;
       const size_t agg_bytes = tiles * 32 * sizeof(uint4);
       const size_t need = 256 + agg_bytes + tiles * 32 * sizeof(uint2);
+      {
+        // This path keeps its ticket base and flag epoch on the HOST (they travel as launch parameters): a
+        // replayed capture would reuse the capture's values and its consumers would wait for flags that never
+        // come (a captured replay hung in testing).  Refuse instead.
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        const cudaError_t ce = cudaStreamIsCapturing(st, &cap);
+        if (ce != cudaSuccess || cap != cudaStreamCaptureStatusNone) {
+          if (ce != cudaSuccess) cudaGetLastError();
+          set_error("this scan shape runs the look-back kernels, which cannot be captured in a CUDA graph "
+                    "(host-side epoch); launch it on a stream that is not capturing");
+          return MRL_ERR_STATE;
+        }
+      }
       // flag-in-payload workspace: zeroed once when (re)allocated, then validated by the launch epoch
       static uint8_t *ll_ws = nullptr;
       static size_t ll_bytes = 0;
