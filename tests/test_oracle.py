@@ -340,3 +340,15 @@ def test_reservoir_oracle_keeps_an_unbiased_sample():
     slots, cols = o.sample()
     assert len(slots) == 8 and len(set(slots.tolist())) == 8
     assert np.array_equal(cols[0], o.cols[0][slots])
+
+
+def test_fill_rows_at_is_a_row_subset_of_fill_rows():
+    """the full-size buffer tests verify gathered rows one by one: the per-row filler must agree with the bulk one"""
+    for rb in (1, 3, 8, 37, 28224):
+        full = O.fill_rows(300, rb, 100 + rb)
+        rows = np.array([0, 299, 17, 17, 123], dtype=np.int64)
+        assert np.array_equal(O.fill_rows_at(rows, rb, 100 + rb), full[rows])
+        if rb >= 8:
+            assert np.array_equal(full[:, :8].copy().view(np.int64)[:, 0], np.arange(300))
+    big = O.fill_rows_at(np.array([999_999, 1 << 33], dtype=np.int64), 16, 5)  # row numbers beyond any test buffer
+    assert big[:, :8].copy().view(np.int64)[:, 0].tolist() == [999_999, 1 << 33]
