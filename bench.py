@@ -52,6 +52,17 @@ def ncu_traffic(key):
         return None
 
 
+def ncu_latency_evidence(key):
+    """what SURVEY 8(d) asks for the latency-bound kernels instead of a %-of-peak target: L2 hit rate and warp
+    stall reasons of the committed ncu capture (profiles/r1_traffic.json; cold caches, serialised launches)"""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))[key]
+        return {k: t[k] for k in ("ncu_duration_us", "l2_hit_rate_pct", "warps_active_pct", "issue_active_pct",
+                                  "stalls_per_issue", "source") if k in t}
+    except Exception:
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -325,6 +336,8 @@ def bench_per(ctx, name, rows, batch, steps, warmup, primary):
                 "frac": ach / hbm, "traffic": ncu_traffic(tkey), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": kern[dom]["bytes"],
                 "kernel_ms": {k: v["ms"] for k, v in kern.items()},
+                "ncu": {k: ncu_latency_evidence(("c3:" if R > 512 else "c2:") + k)
+                        for k in ("prb_sample_kernel", "prb_update_sub_kernel")},
                 "note": ("tree kernels are dependent-load latency bound (L2/HBM round trips), "
                          "not bandwidth bound" if R <= 512 else "row gather is HBM-bandwidth bound")}
 

@@ -94,6 +94,13 @@ if __name__ == "__main__":
                                       "dram_write_bytes": int(sum(d["dram__bytes_write.sum"] for d in ds) / n),
                                       "launches_captured": n,
                                       "source": f"profiles/{tag}.json (ncu --set full --clock-control none; cold caches, serialised)"}
+                avg = lambda k: round(sum(d.get(k, 0) for d in ds) / n, 3)  # noqa: E731
+                t[f"{cfg}:{name}"].update({
+                    "l2_hit_rate_pct": avg("lts__t_sector_hit_rate.pct"),
+                    "warps_active_pct": avg("sm__warps_active.avg.pct_of_peak_sustained_active"),
+                    "issue_active_pct": avg("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                    "stalls_per_issue": {r: avg(f"smsp__average_warps_issue_stalled_{r}_per_issue_active.ratio")
+                                         for r in ("long_scoreboard", "short_scoreboard", "wait", "barrier", "membar")}})
             json.dump(t, open(tp, "w"), indent=1)
     if os.path.exists(os.path.join(g, "launches_s7.csv")):
         launches(os.path.join(g, "launches_s7.csv"), "r1_launch_list_bench_steps20_s7")
