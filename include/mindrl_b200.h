@@ -33,6 +33,11 @@
  *   - calls on one handle must be issued from one thread at a time and are
  *     stream-ordered; different handles are independent (same contract as the
  *     reference registry, which has no locking);
+ *   - the scans keep their workspaces (look-back words, moment partials, scratch)
+ *     per (device, stream): calls on different streams or devices may run
+ *     concurrently; every scan entry point can be captured in a CUDA graph once
+ *     it has run on that stream for the same or a larger shape (workspace
+ *     allocation is not a stream operation);
  *   - no exceptions, no exit(): errors are the return code, text through
  *     mrl_last_error().
  *   - there is NO CPU fallback: without a CUDA device every compute entry
@@ -89,6 +94,7 @@ int64_t mrl_launch_count(void);
  *   "bm_kernel" [0]: batch-major scans: 0 auto, 1 warp-per-row register kernel, 2 TMA rows whenever aligned;
  *       "row_ctas_per_sm" [4], "row_stages" [0 = from row_ctas_per_sm]
  *   "host_scan_chunks" [0 = ~16 MB of input per piece]: pieces of the *_host scans (1 = no pipelining)
+ *   "shard_timeout_ms" [10000]: how long a sharded sample kernel polls for a peer's root statistics
  *   "debug_timers": device pointer to >= 32 int64 phase marks of the tree kernels (0 = off) */
 int mrl_set_option(const char *key, int64_t value);
 
@@ -167,13 +173,16 @@ int mrl_prb_push_batch_host(int64_t handle, int64_t nrows, const void *const *sr
  * uniforms: n floats in [0,1) to use as the per-stratum draws (parity / reproducibility), or
  * NULL to draw them from the buffer's counter-based generator.
  * out: indices int64[n], weights float[n], out_cols[i] = n*row_bytes[i] bytes (out_cols may be
- * NULL to skip the row gather). */
+ * NULL to skip the row gather).  Every index is < size (a mass that rounds past the total returns
+ * the newest row).  MRL_ERR_STATE when the buffer is empty. */
 int mrl_prb_sample(int64_t handle, int64_t n, float beta, const float *uniforms,
                    int64_t *indices, float *weights, void *const *out_cols, void *stream);
 int mrl_prb_sample_host(int64_t handle, int64_t n, float beta, const float *uniforms,
                         int64_t *indices, float *weights, void *const *out_cols, void *stream);
 /* PriorityReplayBufferUpdate (:120): leaf[indices[k]] <- priorities[k]^alpha in order k=0..n-1
- * (duplicates: last occurrence wins), ancestors recomputed, max_priority tracked. */
+ * (duplicates: last occurrence wins), ancestors recomputed, max_priority tracked.  As in the
+ * reference (:113) the caller guarantees 0 <= indices[k] < capacity for device arrays; the
+ * _host variant checks them (MRL_ERR_INVALID). */
 int mrl_prb_update(int64_t handle, const int64_t *indices, const float *priorities, int64_t n,
                    void *stream);
 int mrl_prb_update_host(int64_t handle, const int64_t *indices, const float *priorities,
@@ -206,22 +215,39 @@ int mrl_prb_sample_sharded(int64_t handle, int64_t n, float beta, const float *u
                            const float *gstats, int32_t world, int64_t *indices, float *weights,
                            void *const *out_cols, void *stream);
 
-/* Fused exchange for ranks on ONE node (one process per GPU): the root statistics travel as peer
- * stores over NVLink issued by the sample kernel itself, overlapped with the tree descent; no NCCL
- * call, no extra launch.
- *   1. mrl_prb_shard_init   allocates this rank's mailbox, returns its 64-byte CUDA IPC handle
- *   2. ranks all-gather the handles (any transport) into world*64 bytes, rank order
- *   3. mrl_prb_shard_connect maps the peers' mailboxes
- *   4. mrl_prb_sample_sharded_p2p: same results as mrl_prb_root_stats + all-gather +
- *      mrl_prb_sample_sharded.  Collective: every rank must call it the same number of times. */
+/* Fused exchange for ranks on ONE node (one process per GPU): the root statistics travel as peer stores
+ * over NVLink issued by the buffer's own kernels; no NCCL call, no extra launch in the learner loop.
+ *   1. mrl_prb_shard_init     allocates this rank's mailbox, returns its 64-byte CUDA IPC handle
+ *   2. (optional) mrl_prb_shard_set_mode
+ *        1 = publish on mutation (default): the kernel that changes the tree (update_priorities' last CTA,
+ *            push, the tail of a batched push / set_state) stores {root_sum, root_min, size}, tagged with the
+ *            rank's mutation count, into every peer's mailbox; sample #j uses, for every peer, the
+ *            statistics that peer had at ITS sample #j -- which landed a whole step earlier, so the sample
+ *            step does not wait for the slowest rank unless that rank is more than a step behind.
+ *        0 = publish on sample (round 1): the sample kernel stores the statistics itself and waits for the
+ *            matching words of all peers.
+ *      Same results in both modes and as mrl_prb_root_stats + all-gather + mrl_prb_sample_sharded, PROVIDED
+ *      every rank issues the same sequence of sample / mutating calls on the handle (SPMD) and all of them
+ *      on one stream.  Programs whose ranks mutate their shards at different rates use the all-gather path.
+ *   3. ranks all-gather the handles (any transport) into world*64 bytes, rank order
+ *   4. mrl_prb_shard_connect  maps the peers' mailboxes (MRL_ERR_CUDA when a peer is not reachable through
+ *      CUDA IPC, e.g. on another node: fall back to the all-gather path) and publishes the current state
+ *   5. mrl_prb_sample_sharded_p2p.  A kernel that sees no word from a peer for "shard_timeout_ms" gives up
+ *      (weights NaN) and raises the link's error word: the *_host variant and every later call on the handle
+ *      return MRL_ERR_STATE instead of hanging the GPU.
+ * mrl_prb_shard_diag reads (and optionally resets) the exchange counters: SM cycles warp 0 spent polling,
+ * calls that polled, calls whose first look missed a word, timeouts.  Synchronises `stream`. */
 int mrl_prb_shard_init(int64_t handle, int32_t rank, int32_t world, void *ipc_handle_out);
-int mrl_prb_shard_connect(int64_t handle, const void *all_ipc_handles);
+int mrl_prb_shard_set_mode(int64_t handle, int32_t mode);
+int mrl_prb_shard_connect(int64_t handle, const void *all_ipc_handles, void *stream);
 int mrl_prb_sample_sharded_p2p(int64_t handle, int64_t n, float beta, const float *uniforms,
                                int64_t *indices, float *weights, void *const *out_cols,
                                void *stream);
 int mrl_prb_sample_sharded_p2p_host(int64_t handle, int64_t n, float beta, const float *uniforms,
                                     int64_t *indices, float *weights, void *const *out_cols,
                                     void *stream);
+int mrl_prb_shard_diag(int64_t handle, int64_t *wait_cycles, int64_t *polled_calls, int64_t *waited_calls,
+                       int64_t *timeouts, int32_t reset, void *stream);
 
 /* ---- reverse scans ----------------------------------------------------- */
 /* DiscountedReturn (discounted_return.py:84-92):
@@ -253,6 +279,43 @@ int mrl_gae_host(const float *reward, const float *value, const float *next_valu
  *   out = (x - mean(x)) / (sqrt(var(x)) + eps), mean and population variance over all n elements,
  * accumulated in float64 in a fixed order (deterministic).  out may alias x. */
 int mrl_normalize(const float *x, float *out, int64_t n, float eps, void *stream);
+
+/* The scan and the normalisation that follows it in the learners as ONE operation:
+ *   PPO  (ppo.py:353-368): advantage = gae(...); (advantage - mean) / (sqrt(var) + eps)
+ *   A2C  (a2c.py:189-192): returns = discount_return(...); (returns - mean) / (sqrt(var) + eps)
+ * The moments are accumulated by the scan kernel while it stores its results (float64, fixed order: one
+ * partial per CTA), so normalising costs one more pass instead of three.  adv / out receive the
+ * NORMALISED values (ret of GAE stays un-normalised, as in PPO).  Shapes without a moment-producing
+ * kernel (short, narrow or unaligned ones, MRL_SCAN_SEQUENTIAL) take the moments in a separate pass:
+ * same results. */
+int mrl_gae_normalized(const float *reward, const float *value, const float *next_value,
+                       const float *last_value, const uint8_t *done, float *adv, float *ret, int64_t T,
+                       int64_t B, float gamma, float lambda, float eps, int32_t layout, int32_t mode,
+                       void *stream);
+int mrl_discounted_return_normalized(const float *reward, const uint8_t *done, const float *last_value,
+                                     float *out, int64_t T, int64_t B, int64_t E, float gamma, float eps,
+                                     int32_t layout, int32_t mode, void *stream);
+
+/* V-trace targets of IMPALA (algorithm/impala/vtrace.py:48-108, get_vs_and_advantages), time-major [T,B]
+ * float arrays, bootstrap_value [B]; masks may be NULL (= 1); a clip threshold of +infinity disables that
+ * clip.  Writes vs and pg_advantages.  MRL_SCAN_SEQUENTIAL: one kernel in the reference's operation order
+ * (only exp() differs from a CPU libm by its last bit); MRL_SCAN_PARALLEL: prep, parallel scan, post;
+ * MRL_SCAN_AUTO picks by shape. */
+int mrl_vtrace(const float *log_rhos, const float *discounts, const float *rewards, const float *values,
+               const float *bootstrap_value, const float *masks, float clip_rho_threshold,
+               float clip_pg_threshold, float clip_cs_threshold, float *vs, float *pg_advantages, int64_t T,
+               int64_t B, int32_t mode, void *stream);
+
+/* TD(lambda) targets of COMA (algorithm/coma/coma.py:489-501, build_td_lambda_targets), batch-major:
+ *   ret[:, t] = lambda_gamma * ret[:, t+1]
+ *               + mask[:, t] * (rewards[:, t] + bootstrap_gamma * target_qs[:, t+1] * (1 - terminated[:, t]))
+ * for t = max_t-1 .. 0, ret[:, t >= max_t] = 0.  target_qs / ret [B, Tq, A]; rewards, terminated, mask
+ * [B, Tr, RA], RA = 1 (broadcast over agents) or A.  lambda_gamma = (float)(td_lambda * gamma) and
+ * bootstrap_gamma = (float)((1 - td_lambda) * gamma), formed in double as the reference's Python scalars
+ * are.  Same operation order as the reference loop: bit-identical. */
+int mrl_td_lambda(const float *rewards, const float *terminated, const float *mask, const float *target_qs,
+                  float *ret, int64_t B, int64_t Tq, int64_t Tr, int64_t A, int64_t RA, int64_t max_t,
+                  float lambda_gamma, float bootstrap_gamma, void *stream);
 
 /* generic first-order reverse recurrence x[t] = a[t] + b[t] * x[t+1], x[T] = x_last (NULL = 0):
  * V-trace (vtrace.py:88-93, b = discount*c*mask) and TD(lambda) (coma.py:489-501). */

@@ -70,7 +70,9 @@ SIGNATURES = {
     "mrl_prb_root_stats": [i64, vp, vp],
     "mrl_prb_sample_sharded": [i64, i64, f32, vp, vp, i32, vp, vp, vp, vp],
     "mrl_prb_shard_init": [i64, i32, i32, vp],
-    "mrl_prb_shard_connect": [i64, vp],
+    "mrl_prb_shard_set_mode": [i64, i32],
+    "mrl_prb_shard_connect": [i64, vp, vp],
+    "mrl_prb_shard_diag": [i64, vp, vp, vp, vp, i32, vp],
     "mrl_prb_sample_sharded_p2p": [i64, i64, f32, vp, vp, vp, vp, vp],
     "mrl_prb_sample_sharded_p2p_host": [i64, i64, f32, vp, vp, vp, vp, vp],
     "mrl_discounted_return": [vp, vp, vp, vp, i64, i64, i64, f32, i32, i32, vp],
@@ -78,6 +80,10 @@ SIGNATURES = {
     "mrl_gae": [vp, vp, vp, vp, vp, vp, vp, i64, i64, f32, f32, i32, i32, vp],
     "mrl_gae_host": [vp, vp, vp, vp, vp, vp, vp, i64, i64, f32, f32, i32, i32, vp],
     "mrl_normalize": [vp, vp, i64, f32, vp],
+    "mrl_gae_normalized": [vp, vp, vp, vp, vp, vp, vp, i64, i64, f32, f32, f32, i32, i32, vp],
+    "mrl_discounted_return_normalized": [vp, vp, vp, vp, i64, i64, i64, f32, f32, i32, i32, vp],
+    "mrl_td_lambda": [vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, f32, f32, vp],
+    "mrl_vtrace": [vp, vp, vp, vp, vp, vp, f32, f32, f32, vp, vp, i64, i64, i32, vp],
     "mrl_affine_scan": [vp, vp, vp, vp, i64, i64, i32, i32, vp],
 }
 _RESTYPES = {"mrl_last_error": C.c_char_p, "mrl_launch_count": i64}

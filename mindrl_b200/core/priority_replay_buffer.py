@@ -188,16 +188,29 @@ class PriorityReplayBuffer:
                                        int(state["rng_counter"]), float(state["max_priority"]),
                                        s.ctypes.data, m.ctypes.data, st))
 
-    def shard_init(self, rank, world):
-        """allocates this rank's peer mailbox; returns its 64-byte CUDA IPC handle"""
+    def shard_init(self, rank, world, publish="mutation"):
+        """allocates this rank's peer mailbox; returns its 64-byte CUDA IPC handle.
+        publish: 'mutation' (default) -- update_priorities / insert publish the root statistics to the peers,
+        sample reads what landed a step earlier; 'sample' -- the sample kernel exchanges them itself."""
         buf = C.create_string_buffer(64)
         _ffi.check(_ffi.lib().mrl_prb_shard_init(self._handle, int(rank), int(world), buf))
+        _ffi.check(_ffi.lib().mrl_prb_shard_set_mode(self._handle, {"sample": 0, "mutation": 1}[publish]))
         return buf.raw
 
     def shard_connect(self, all_handles):
-        """maps every rank's mailbox; all_handles = world*64 bytes in rank order"""
+        """maps every rank's mailbox; all_handles = world*64 bytes in rank order.  Raises MindRLError
+        (MRL_ERR_CUDA) when a peer is not reachable through CUDA IPC (another node)."""
         buf = C.create_string_buffer(bytes(all_handles), len(all_handles))
-        _ffi.check(_ffi.lib().mrl_prb_shard_connect(self._handle, buf))
+        _ffi.check(_ffi.lib().mrl_prb_shard_connect(self._handle, buf, K.current_stream()))
+
+    def shard_diag(self, reset=False):
+        """exchange counters of the sharded sample: SM cycles warp 0 spent polling its mailbox, calls that
+        polled, calls whose first look missed a peer's word, timeouts (synchronises the stream)"""
+        v = [C.c_int64() for _ in range(4)]
+        _ffi.check(_ffi.lib().mrl_prb_shard_diag(self._handle, *[C.byref(x) for x in v], int(bool(reset)),
+                                                 K.current_stream()))
+        return {"wait_cycles": v[0].value, "polled_calls": v[1].value, "waited_calls": v[2].value,
+                "timeouts": v[3].value}
 
     def root_stats(self):
         """device array {root_sum, root_min, size, max_priority} for the sharded exchange"""

@@ -41,28 +41,65 @@ def owner_of(global_indices, local_capacity):
 
 class ShardedPriorityReplayBuffer:
     """`local` is this rank's buffer: mindrl_b200.core.PriorityReplayBuffer on a GPU box.  It
-    must provide root_stats(), sample(beta, uniforms=, gstats=), update_priorities(), insert()."""
+    must provide root_stats(), sample(beta, uniforms=, gstats=), update_priorities(), insert().
+
+    Semantics of sample #j on every rank: strata are drawn from the rank's OWN tree; the importance
+    weights use, for every rank q, the root statistics q's tree had at q's own sample #j.  With the
+    peer-memory exchanges this needs every rank to issue the same sequence of sample / insert /
+    update_priorities calls (SPMD learners) on one stream; programs whose ranks mutate their shards at
+    different rates use exchange='nccl' (statistics gathered at the call)."""
 
     def __init__(self, local, local_capacity, group=None, exchange="auto"):
-        """exchange: 'p2p' = peer-memory mailboxes written by the sample kernel itself (ranks on one
-        node), 'nccl' = all-gather of the 16-byte root statistics, 'auto' = p2p when the local buffer
-        supports it."""
+        """exchange:
+        'p2p'        peer mailboxes, statistics published by the MUTATING kernels (update_priorities, insert):
+                     the sample step reads words that landed a step earlier and does not wait for the slowest rank
+        'p2p_sample' peer mailboxes, statistics exchanged by the sample kernel itself (round-1 protocol)
+        'nccl'       all-gather of the 16-byte root statistics
+        'auto'       'p2p' when every rank is on this node and every mailbox could be mapped (checked
+                     collectively), else 'nccl'."""
         if dist is None or not dist.is_initialized():
             raise RuntimeError("torch.distributed must be initialised (one process per GPU)")
+        if exchange not in ("auto", "p2p", "p2p_sample", "nccl"):
+            raise ValueError(f"unknown exchange {exchange!r}")
         self.local = local
         self.local_capacity = int(local_capacity)
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.p2p = False
-        if exchange in ("auto", "p2p") and hasattr(local, "shard_init") and self.world <= 32:
-            mine = local.shard_init(self.rank, self.world)
-            parts = [None] * self.world
-            dist.all_gather_object(parts, mine, group=group)
-            local.shard_connect(b"".join(parts))
-            self.p2p = True
-        elif exchange == "p2p":
+        self.exchange = "nccl"
+        if exchange == "nccl":
+            return
+        able = hasattr(local, "shard_init") and self.world <= 32
+        if not able and exchange != "auto":
             raise RuntimeError("peer-memory exchange is not available for this buffer")
+        # every rank must take the same branch: agree on (a) capability, (b) one node, (c) mapping succeeded
+        import socket
+        info = [None] * self.world
+        mine = None
+        if able:
+            mine = local.shard_init(self.rank, self.world,
+                                    publish="sample" if exchange == "p2p_sample" else "mutation")
+        dist.all_gather_object(info, (socket.gethostname(), mine), group=group)
+        one_node = len({h for h, _ in info}) == 1
+        all_able = all(m is not None for _, m in info)
+        ok = False
+        err = None
+        if one_node and all_able:
+            try:
+                local.shard_connect(b"".join(m for _, m in info))
+                ok = True
+            except Exception as e:  # a peer could not be mapped (no peer access between the GPUs)
+                err = e
+        flags = [None] * self.world
+        dist.all_gather_object(flags, ok, group=group)
+        if all(flags):
+            self.p2p = True
+            self.exchange = "p2p_sample" if exchange == "p2p_sample" else "p2p"
+        elif exchange != "auto":
+            raise RuntimeError(f"peer-memory exchange could not be set up on every rank "
+                               f"(one node: {one_node}, mapped here: {ok}): {err}")
+        # (a rank whose mapping succeeded while another's failed simply never uses its mailbox)
 
     def insert(self, *transition):
         return self.local.insert(*transition)
@@ -88,3 +125,7 @@ class ShardedPriorityReplayBuffer:
     def update_priorities(self, indices, priorities):
         return self.local.update_priorities(to_local(indices, self.rank, self.local_capacity),
                                             priorities)
+
+    def exchange_diag(self, reset=False):
+        """counters of the peer-memory exchange (see PriorityReplayBuffer.shard_diag); None for 'nccl'"""
+        return self.local.shard_diag(reset) if self.p2p else None

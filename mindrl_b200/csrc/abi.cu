@@ -15,6 +15,32 @@ void set_error(const char *fmt, ...) {
   va_end(ap);
 }
 
+int sm_count() {
+  static std::mutex mu;
+  static int cached[64];  // 0 = not queried yet
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  std::lock_guard<std::mutex> g(mu);
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+bool first_use_on_device(const void *kernel) {
+  static std::mutex mu;
+  static std::unordered_map<const void *, uint64_t> seen;  // bit d: configured on device d
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+  std::lock_guard<std::mutex> g(mu);
+  uint64_t &m = seen[kernel];
+  if (m & (1ull << dev)) return false;
+  m |= 1ull << dev;
+  return true;
+}
+
 int stream_wait_spin(cudaStream_t st) {
   static thread_local cudaEvent_t ev = nullptr;
   if (!ev) MRL_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));

@@ -15,7 +15,11 @@
 
 namespace mrl {
 
-constexpr int kNumSM = 148;  // B200: 2 dies x 74 SMs
+// SMs of the current device (cudaDevAttrMultiProcessorCount, cached per device; 148 on a B200).  Grids are
+// sized from this, never from a constant.
+int sm_count();
+// true exactly once per (kernel, device): guards cudaFuncSetAttribute, which is a per-device setting
+bool first_use_on_device(const void *kernel);
 
 void set_error(const char *fmt, ...);
 extern std::atomic<int64_t> g_launches;

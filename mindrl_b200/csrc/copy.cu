@@ -73,7 +73,7 @@ int copy_segments_dir(const ColTable &tab, int64_t ring_row, int64_t io_row, int
   }
   int64_t blocks = (max_units + 256 * 4 - 1) / (256 * 4);
   if (blocks < 1) blocks = 1;
-  if (blocks > kNumSM * 8) blocks = kNumSM * 8;
+  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
   dim3 grid((unsigned)blocks, (unsigned)tab.ncols);
   copy_seg_kernel<<<grid, 256, 0, st>>>(tab, ring_row, io_row, nrows, to_ring);
   MRL_LAUNCHED();
@@ -309,6 +309,7 @@ static int64_t g_bulk_stages = env_i64("MRL_BULK_STAGES", 4);
 extern long long *g_debug_timers;  // prb.cu
 extern bool g_no_inline_update;    // prb.cu
 extern bool g_host_zero_copy;      // prb.cu
+extern long long g_shard_timeout_ns;  // prb.cu
 bool g_pdl = true;                 // programmatic dependent launch of the PER-path kernels
 bool g_tree_prefetch = true;       // tree kernels pull the lines of their later round trips into L2 first
 
@@ -330,6 +331,10 @@ int set_copy_option(const char *key, int64_t value) {
     g_host_zero_copy = value == 1;
     return MRL_OK;
   }
+  if (k == "shard_timeout_ms" && value >= 1 && value <= 3600000) {
+    g_shard_timeout_ns = value * 1000000ll;
+    return MRL_OK;
+  }
   if (k == "tree_prefetch" && (value == 0 || value == 1)) {
     g_tree_prefetch = value == 1;
     return MRL_OK;
@@ -347,11 +352,10 @@ template <int STAGES>
 static int launch_bulk(const ColTable &tab, const BulkPlan &plan, const int64_t *slots, int64_t capacity,
                        int32_t stage_bytes, int64_t blocks, cudaStream_t st) {
   const size_t smem = (size_t)stage_bytes * STAGES;
-  static size_t configured = 0;
-  if (smem > configured) {
-    MRL_CUDA(cudaFuncSetAttribute(gather_bulk_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  // (per device: the limit is a property of the function ON a device; always the most a CTA may take, so
+  // one setting serves every stage size)
+  if (first_use_on_device((const void *)gather_bulk_kernel<STAGES>))
+    MRL_CUDA(cudaFuncSetAttribute(gather_bulk_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   MRL_CUDA(launch_pdl(gather_bulk_kernel<STAGES>, dim3((unsigned)blocks), dim3(32), smem, st, tab, plan, slots,
                       capacity, stage_bytes));
   return MRL_OK;
@@ -388,7 +392,7 @@ int gather_rows(const ColTable &tab, const int64_t *slots, int64_t n, int64_t ca
   }
   if (plan.ncols > 0) {
     const int64_t total = plan.item_begin[plan.ncols];
-    int64_t blocks = kNumSM * bulk_ctas_per_sm;
+    int64_t blocks = sm_count() * bulk_ctas_per_sm;
     if (blocks > total) blocks = total;
     stage_bytes = (stage_bytes + 127) / 128 * 128;
     int stages = (int)g_bulk_stages;
@@ -410,7 +414,7 @@ int gather_rows(const ColTable &tab, const int64_t *slots, int64_t n, int64_t ca
         if (u > max_units) max_units = u;
       }
     int64_t blocks = (max_units + 256 * 4 - 1) / (256 * 4);
-    if (blocks > kNumSM * 8) blocks = kNumSM * 8;
+    if (blocks > sm_count() * 8) blocks = sm_count() * 8;
     dim3 grid((unsigned)blocks, (unsigned)ncols);
     gather_ldg_kernel<<<grid, 256, 0, st>>>(tab, slots, n, capacity, ldg_mask);
     MRL_LAUNCHED();
@@ -482,14 +486,14 @@ __global__ void __launch_bounds__(256) transpose_rows_kernel(const V *__restrict
 template <typename T>
 static void launch_tile(const void *in, void *out, int64_t A, int64_t B, cudaStream_t st) {
   const int64_t n_tiles = ((A + 31) / 32) * ((B + 31) / 32);
-  const int64_t grid = n_tiles < (int64_t)kNumSM * 8 ? n_tiles : (int64_t)kNumSM * 8;
+  const int64_t grid = n_tiles < (int64_t)sm_count() * 8 ? n_tiles : (int64_t)sm_count() * 8;
   transpose_tile_kernel<T><<<(unsigned)grid, 256, 0, st>>>((const T *)in, (T *)out, A, B);
 }
 template <typename V>
 static void launch_rows(const void *in, void *out, int64_t A, int64_t B, int64_t row_bytes, cudaStream_t st) {
   const int64_t U = row_bytes / (int64_t)sizeof(V);
   const int64_t blocks = (A * B * U + 255) / 256;
-  const int64_t grid = blocks < (int64_t)kNumSM * 16 ? blocks : (int64_t)kNumSM * 16;
+  const int64_t grid = blocks < (int64_t)sm_count() * 16 ? blocks : (int64_t)sm_count() * 16;
   transpose_rows_kernel<V><<<(unsigned)grid, 256, 0, st>>>((const V *)in, (V *)out, A, B, U);
 }
 
@@ -527,7 +531,7 @@ extern "C" int mrl_fill_rows(void *col, int64_t nrows, int64_t row_bytes, uint64
                              void *stream) {
   MRL_REQUIRE(col && nrows >= 0 && row_bytes > 0, "mrl_fill_rows: bad arguments");
   if (nrows == 0) return MRL_OK;
-  mrl::fill_rows_kernel<<<mrl::kNumSM * 8, 256, 0, mrl::as_stream(stream)>>>(
+  mrl::fill_rows_kernel<<<mrl::sm_count() * 8, 256, 0, mrl::as_stream(stream)>>>(
       (uint8_t *)col, nrows, row_bytes, seed);
   MRL_LAUNCHED();
   return MRL_OK;

@@ -50,17 +50,66 @@ struct PrbState {
   float pad[2];
 };
 
-// peer-memory mailbox of the sharded buffer: every rank owns [2][world][4] flag-in-payload words
-// {value bits, epoch}; ranks write their root statistics straight into every peer's mailbox (NVLink
-// peer stores issued by the sample kernel itself) and poll their own copy
+// Peer-memory mailboxes of the sharded buffer.  Every rank owns [2][world][4] flag-in-payload words
+// {value bits, tag} (8-byte accesses are single-copy atomic: a reader that sees the tag sees the value) and
+// has every peer's mailbox mapped (CUDA IPC).  Two protocols share the words:
+//   kPublishOnMutation (default): whoever CHANGES a rank's tree -- the last CTA of the update kernel, the
+//       push kernel, the tail of a batched push / set_state -- stores that rank's {root_sum, root_min, size}
+//       straight into all peers' mailboxes, tag = the rank's mutation count.  sample #j reads slot (j-1)&1 and
+//       expects tag == its own mutation count: ranks run the same program (SPMD), so a peer's statistics "as of
+//       its own sample #j" are exactly its publication number <own mutation count>, and they landed a whole
+//       step before they are needed -- no wait in the sample step unless a peer is more than a step behind.
+//       Mutations issued after sample #j go to slot j&1, so a peer that runs ahead never overwrites what a
+//       slower rank has yet to read (it cannot pass ITS sample #j+1 before the slower rank has published the
+//       mutations that follow its sample #j, which are stream-ordered behind that sample).
+//   kPublishOnSample (round 1): the sample kernel itself stores the statistics, tag = sample call number, and
+//       waits for all peers' words of the same call: every step ends when the slowest rank has got there.
+// Contract of both: all calls on a sharded handle go to ONE stream, every rank issues the same sequence of
+// sample / mutating calls.  A poll that sees nothing for `shard_timeout_ms` gives up, raises the link's error
+// word (mapped host memory) and the next call on the handle returns MRL_ERR_STATE.
 constexpr int kMaxWorld = 32;
+constexpr int kPublishOnSample = 0, kPublishOnMutation = 1;
+struct ShardDiag {                    // device memory, read back by mrl_prb_shard_diag
+  unsigned long long wait_cycles;     // SM cycles warp 0 of CTA 0 spent in the poll, summed over calls
+  unsigned long long polled_calls;    // sample calls that polled
+  unsigned long long waited_calls;    // ... whose first look did not find every peer's word
+  unsigned long long timeouts;
+};
 struct ShardLink {
-  int rank = -1, world = 0;
+  int rank = -1, world = 0, mode = kPublishOnMutation;
   uint2 *mailbox = nullptr;     // this rank's mailbox (cudaMalloc, exported through CUDA IPC)
   uint2 *peer[kMaxWorld] = {};  // mapped mailboxes of all ranks (peer[rank] == mailbox)
   uint2 **peer_dev = nullptr;   // the same table in device memory
   uint32_t epoch = 0;           // sharded sample calls so far (identical on every rank)
+  uint32_t version = 0;         // publications so far = mutating calls since connect + 1 (identical on every rank)
+  uint32_t published_epoch = 0; // `epoch` at the last publication: a sample without a mutation since the last
+                                // sample re-publishes into its own slot first
+  ShardDiag *diag = nullptr;
+  int *err_host = nullptr;      // pinned + mapped: raised by a kernel whose poll timed out
+  int *err_dev = nullptr;
 };
+long long g_shard_timeout_ns = 10000000000ll;  // option "shard_timeout_ms" [10000]
+
+// what a kernel needs to publish the root statistics (all zero = not sharded / not this protocol)
+struct PublishArgs {
+  uint2 *const *peers = nullptr;
+  int32_t rank = 0, world = 0;
+  uint32_t slot = 0, tag = 0;
+  float size = 0.0f;
+};
+// lanes 0..world-1 of ONE warp: lane q stores this rank's three words into rank q's mailbox (NVLink peer
+// stores; relaxed, system scope -- the words validate themselves)
+__device__ __forceinline__ void publish_root(const PublishArgs &P, int lane, float root_sum, float root_min) {
+  if (P.peers && lane < P.world) {
+    uint2 *dst = P.peers[lane] + ((size_t)P.slot * P.world + P.rank) * 4;
+    const float vals[3] = {root_sum, root_min, P.size};
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+      asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1,%2};" ::"l"(dst + q), "r"(__float_as_uint(vals[q])),
+                   "r"(P.tag)
+                   : "memory");
+  }
+}
 
 struct PrbBuffer {
   int64_t capacity = 0, cap2 = 1;
@@ -131,10 +180,14 @@ struct SampleArgs {
   uint64_t seed, ctr;
   uint32_t gather_mask;  // columns whose rows this kernel copies itself (narrow rows)
   long long *dbg;
-  uint2 *const *peers;  // sharded, peer-memory exchange: mailboxes of all ranks (else NULL)
-  const uint2 *mailbox;
-  int32_t rank;
-  uint32_t epoch;
+  // sharded, peer-memory exchange (mailbox == NULL: off)
+  PublishArgs pub;       // kPublishOnSample: this kernel stores the rank's statistics itself (pub.peers != NULL)
+  const uint2 *mailbox;  // this rank's mailbox
+  uint32_t slot, expect; // words to read: slot, and the tag they must carry
+  ShardDiag *diag;
+  int *err;              // raised when the poll times out
+  long long timeout_ns;
+  const float *beta_dev; // != NULL: beta is read from device memory (AOT shim: beta arrives as a tensor)
   int32_t prefetch;  // option "tree_prefetch"
   int32_t word_units;  // > 0: every fused column is made of aligned 4-byte words; their total per row
 };
@@ -182,17 +235,9 @@ __global__ void __launch_bounds__(kSampleWarps * 32)
   float w_min = __ldcg(S.mn + 1);
   float4 hop0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
   if (S.levels > 0) hop0 = hop_load(S.sum, 1, S.levels < kHop ? S.levels : kHop, lane);
-  if (S.peers && blockIdx.x == 0 && threadIdx.x < S.world) {
-    // Fused exchange, part 1: this rank's root statistics go straight into every rank's mailbox
-    // (peer stores over NVLink).  The words are self-validating {value, epoch}: no fence, no flag.
-    uint2 *dst = S.peers[threadIdx.x] + ((size_t)(S.epoch & 1u) * S.world + S.rank) * 4;
-    const float vals[3] = {root_sum, w_min, (float)S.size};
-#pragma unroll
-    for (int q = 0; q < 3; ++q)
-      asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1,%2};" ::"l"(dst + q),
-                   "r"(__float_as_uint(vals[q])), "r"(S.epoch)
-                   : "memory");
-  }
+  // kPublishOnSample: this rank's root statistics go straight into every rank's mailbox now, so that the
+  // NVLink latency hides behind the descent
+  if (blockIdx.x == 0 && threadIdx.x < 32) publish_root(S.pub, threadIdx.x, root_sum, w_min);
   const float u = S.uniforms ? __ldg(S.uniforms + i) : mrl_uniform01(S.seed, S.ctr + (uint64_t)i);
   float w_sum = root_sum, w_size = (float)S.size;
   if (S.gstats) {
@@ -265,8 +310,15 @@ __global__ void __launch_bounds__(kSampleWarps * 32)
     remaining -= h;
     if (remaining == 0) leaf_p = sub == 0 ? c0 : (sub == 1 ? c1 : (sub == 2 ? c2 : c3));
   }
-  const int64_t leaf = node - S.cap2;
-  const int64_t slot = leaf < S.capacity ? leaf : S.capacity - 1;
+  // A mass that rounds past the total walks into the empty part of the tree (leaves >= size, priority 0):
+  // the newest valid leaf is returned instead, so that index, weight and row always belong together and
+  // the index is safe to hand back to update_priorities (a decision of the parity checker too).
+  int64_t leaf = node - S.cap2;
+  if (leaf >= S.size) {
+    leaf = S.size - 1;
+    leaf_p = __ldcg(S.sum + S.cap2 + leaf);
+  }
+  const int64_t slot = leaf;
   dbg_mark(S.dbg, 3);
 
   // The row: all 4-byte words of the narrow columns are ONE list, 4 per lane and pass, every load of a pass
@@ -305,9 +357,9 @@ __global__ void __launch_bounds__(kSampleWarps * 32)
     const uint8_t *src = tab.col[lane] + slot * tab.row_bytes[lane];
     asm volatile("prefetch.global.L1 [%0];" ::"l"(src));
   }
-  if (S.peers) {
+  if (S.mailbox) {
     // (sharded: everything that does not need the peers' statistics goes first -- the longer this rank
-    // takes to get to its mailbox, the more launch skew between the ranks it absorbs)
+    // takes to get to its mailbox, the more skew between the ranks it absorbs)
     if (S.word_units > 0) {
       row_pass_store();
       for (int u0 = 128; u0 < S.word_units; u0 += 128) {
@@ -315,18 +367,48 @@ __global__ void __launch_bounds__(kSampleWarps * 32)
         row_pass_store();
       }
     }
-    // Fused exchange, part 2: by now the descent has hidden the NVLink latency; lane r polls rank r's
-    // words in the local mailbox, then the totals are formed in rank order (as the oracle does).
-    float ps = 0.0f, pm = FLT_MAX, pz = 0.0f;
-    if (lane < S.world) {
-      const uint2 *src = S.mailbox + ((size_t)(S.epoch & 1u) * S.world + lane) * 4;
+    // Lane r polls rank r's three words in the LOCAL mailbox until they carry the expected tag (kPublishOn-
+    // Mutation: they were stored by the peer's previous mutating kernel, a whole step ago; kPublishOnSample: by
+    // the peer's matching sample kernel); this rank's own entry comes from its tree.  Then the totals are
+    // formed in rank order (as the oracle does).  The poll is bounded: ADVICE r1 -- a rank that never makes
+    // the matching call must not hang its peers' GPUs.
+    float ps = root_sum, pm = w_min, pz = (float)S.size;
+    const bool timing = S.diag && blockIdx.x == 0 && threadIdx.x == 0;
+    long long c0 = 0;
+    if (timing) c0 = clock64();
+    bool first_miss = false;
+    if (lane < S.world && lane != S.pub.rank) {
+      const uint2 *src = S.mailbox + ((size_t)S.slot * S.world + lane) * 4;
       uint2 a, b, c;
-      do {
+      long long t0 = 0;
+      unsigned int spins = 0;
+      while (true) {
         asm volatile("ld.relaxed.sys.global.v2.u32 {%0,%1}, [%2];" : "=r"(a.x), "=r"(a.y) : "l"(src) : "memory");
         asm volatile("ld.relaxed.sys.global.v2.u32 {%0,%1}, [%2];" : "=r"(b.x), "=r"(b.y) : "l"(src + 1) : "memory");
         asm volatile("ld.relaxed.sys.global.v2.u32 {%0,%1}, [%2];" : "=r"(c.x), "=r"(c.y) : "l"(src + 2) : "memory");
-      } while (a.y != S.epoch || b.y != S.epoch || c.y != S.epoch);
+        if (a.y == S.expect && b.y == S.expect && c.y == S.expect) break;
+        first_miss = true;
+        if ((++spins & 1023u) == 0u) {  // the global timer costs ~1 us to read: only on the slow path
+          long long now;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+          if (t0 == 0) t0 = now;
+          if (now - t0 > S.timeout_ns) {
+            if (S.err) *reinterpret_cast<volatile int *>(S.err) = 1 + lane;  // which peer was missing
+            if (S.diag && blockIdx.x == 0 && threadIdx.x < 32) atomicAdd(&S.diag->timeouts, 1ull);
+            a.x = b.x = c.x = 0x7fc00000u;  // NaN: the weights of this call are void
+            break;
+          }
+        }
+      }
       ps = __uint_as_float(a.x), pm = __uint_as_float(b.x), pz = __uint_as_float(c.x);
+    }
+    if (S.diag && blockIdx.x == 0 && threadIdx.x < 32) {
+      const bool any_miss = __any_sync(FULL, first_miss);
+      if (timing) {
+        atomicAdd(&S.diag->wait_cycles, (unsigned long long)(clock64() - c0));
+        atomicAdd(&S.diag->polled_calls, 1ull);
+        if (any_miss) atomicAdd(&S.diag->waited_calls, 1ull);
+      }
     }
     w_sum = 0.0f, w_min = FLT_MAX, w_size = 0.0f;
     for (int r = 0; r < S.world; ++r) {
@@ -340,7 +422,8 @@ __global__ void __launch_bounds__(kSampleWarps * 32)
   {
     const float x = lane == 0 ? leaf_p : w_min;
     float r = 0.0f;
-    if (lane < 2) r = mrl_is_weight(x, w_sum, w_size, S.beta);
+    const float beta = S.beta_dev ? __ldg(S.beta_dev) : S.beta;
+    if (lane < 2) r = mrl_is_weight(x, w_sum, w_size, beta);
     const float max_w = __shfl_sync(FULL, r, 1);
     if (lane == 0) {
       S.indices[i] = leaf;
@@ -349,7 +432,7 @@ __global__ void __launch_bounds__(kSampleWarps * 32)
   }
   dbg_mark(S.dbg, 4);
   if (S.word_units > 0) {
-    if (!S.peers) {
+    if (!S.mailbox) {
       row_pass_store();
       for (int u0 = 128; u0 < S.word_units; u0 += 128) {
         row_pass_load(u0);
@@ -387,6 +470,7 @@ struct UpdateArgs {
   uint64_t epoch;
   long long *dbg;
   int32_t prefetch;  // option "tree_prefetch"
+  PublishArgs pub;   // sharded buffer, kPublishOnMutation: the kernel that finishes the root publishes it
 };
 
 __device__ __forceinline__ void recompute_node(float *sum, float *mn, int64_t node) {
@@ -472,6 +556,7 @@ __global__ void __launch_bounds__(1024) prb_update_kernel(const __grid_constant_
     __stcg(U.sum + i, ssum[i]);
     __stcg(U.mn + i, smin[i]);
   }
+  if (tid < 32) publish_root(U.pub, tid, ssum[1], smin[1]);
   dbg_mark(U.dbg, 6);
 }
 
@@ -674,6 +759,7 @@ __global__ void __launch_bounds__(kWalkThreads)
     __stcg(U.sum + i, ssum[i]);
     __stcg(U.mn + i, smin[i]);
   }
+  if (tid < 32) publish_root(U.pub, tid, ssum[1], smin[1]);
   dbg_mark(U.dbg, 14);
 }
 
@@ -1103,6 +1189,9 @@ __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __gri
           __stcg(U.mn + node, xm);
         }
       }
+      // lane 0 now holds the root: the sharded buffer's peers get it from here (kPublishOnMutation), a
+      // whole step before their next sample needs it
+      publish_root(U.pub, tid, __shfl_sync(0xffffffffu, xs, 0), __shfl_sync(0xffffffffu, xm, 0));
     }
     dbg_mark_gt(U.dbg, 16);
   } else {
@@ -1126,6 +1215,7 @@ __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __gri
       __stcg(U.sum + i, ssum[i]);
       __stcg(U.mn + i, smin[i]);
     }
+    if (tid < 32) publish_root(U.pub, tid, ssum[1], smin[1]);
   }
   if (tid == 0) U.state->done_ctas = 0u;  // ready for the next launch (stream-ordered)
 }
@@ -1133,7 +1223,7 @@ __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __gri
 // ---- push --------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32)
     prb_push_kernel(float *sum, float *mn, const PrbState *state, int64_t cap2, int32_t levels,
-                    int64_t slot, const __grid_constant__ ColTable tab) {
+                    int64_t slot, const __grid_constant__ ColTable tab, const PublishArgs pub) {
   const int lane = threadIdx.x;
   constexpr unsigned FULL = 0xffffffffu;
   // row write (io -> ring)
@@ -1181,6 +1271,8 @@ __global__ void __launch_bounds__(32)
     __stcg(sum + leaf_node, p);
     __stcg(mn + leaf_node, p);
   }
+  // (vs, vm) is the root in every lane after the walk (levels == 0: the leaf is the root)
+  publish_root(pub, lane, vs, vm);
 }
 
 // leaves [lo, hi) (slots, no wrap) <- max_priority, then every ancestor of the range, one level at a
@@ -1233,6 +1325,12 @@ __global__ void prb_stats_kernel(const float *sum, const float *mn, const PrbSta
   out4[3] = state->max_priority;
 }
 
+// tail of the mutating calls that have no single kernel which ends with the root in hand (batched push,
+// set_state, connect, and a sample that follows a sample): one warp reads the root and publishes it
+__global__ void __launch_bounds__(32) prb_publish_kernel(const float *sum, const float *mn, const PublishArgs pub) {
+  publish_root(pub, threadIdx.x, __ldcg(sum + 1), __ldcg(mn + 1));
+}
+
 static void fill_table(ColTable &tab, const PrbBuffer *b, void *const *io) {
   tab.ncols = b->ncols;
   for (int c = 0; c < b->ncols; ++c) {
@@ -1243,6 +1341,28 @@ static void fill_table(ColTable &tab, const PrbBuffer *b, void *const *io) {
   }
 }
 
+// kPublishOnMutation: the publication a mutating call carries.  `bump` = this is a new state of the tree
+// (false: the unchanged statistics are re-published into the slot of the coming sample).
+static PublishArgs make_publication(PrbBuffer *b, int64_t size_after, bool bump = true) {
+  PublishArgs P;
+  ShardLink &k = b->link;
+  if (k.peer_dev && k.mode == kPublishOnMutation) {
+    P.peers = k.peer_dev, P.rank = k.rank, P.world = k.world;
+    P.slot = k.epoch & 1u;
+    P.tag = bump ? ++k.version : k.version;
+    P.size = (float)size_after;
+    k.published_epoch = k.epoch;
+  }
+  return P;
+}
+static int publish_tail(PrbBuffer *b, cudaStream_t st, bool bump = true) {
+  const PublishArgs P = make_publication(b, b->size, bump);
+  if (!P.peers) return MRL_OK;
+  prb_publish_kernel<<<1, 32, 0, st>>>(b->sum, b->mn, P);
+  MRL_LAUNCHED();
+  return MRL_OK;
+}
+
 static int rebuild_range(PrbBuffer *b, int64_t lo, int64_t hi, cudaStream_t st) {
   if (hi <= lo) return MRL_OK;
   if (hi - lo <= 4096) {
@@ -1251,7 +1371,7 @@ static int rebuild_range(PrbBuffer *b, int64_t lo, int64_t hi, cudaStream_t st) 
     return MRL_OK;
   }
   int64_t blocks = (hi - lo + 255) / 256;
-  if (blocks > kNumSM * 8) blocks = kNumSM * 8;
+  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
   prb_set_leaves_kernel<<<(unsigned)blocks, 256, 0, st>>>(b->sum, b->mn, b->state, b->cap2, lo, hi);
   MRL_LAUNCHED();
   int64_t a = b->cap2 + lo, e = b->cap2 + hi - 1;
@@ -1259,7 +1379,7 @@ static int rebuild_range(PrbBuffer *b, int64_t lo, int64_t hi, cudaStream_t st) 
     a >>= 1;
     e >>= 1;
     int64_t nb = (e - a + 1 + 255) / 256;
-    if (nb > kNumSM * 8) nb = kNumSM * 8;
+    if (nb > sm_count() * 8) nb = sm_count() * 8;
     prb_level_kernel<<<(unsigned)nb, 256, 0, st>>>(b->sum, b->mn, a, e);
     MRL_LAUNCHED();
   }
@@ -1272,10 +1392,12 @@ static int prb_push_batch_impl(PrbBuffer *b, int64_t nrows, void *const *src, cu
     const int64_t slot = (b->head + 1) % cap;
     ColTable tab;
     fill_table(tab, b, src);
-    prb_push_kernel<<<1, 32, 0, st>>>(b->sum, b->mn, b->state, b->cap2, b->levels, slot, tab);
+    const int64_t size_after = b->size < cap ? b->size + 1 : b->size;
+    prb_push_kernel<<<1, 32, 0, st>>>(b->sum, b->mn, b->state, b->cap2, b->levels, slot, tab,
+                                      make_publication(b, size_after));
     MRL_LAUNCHED();
     b->head = slot;
-    if (b->size < cap) b->size++;
+    b->size = size_after;
     return MRL_OK;
   }
   const int64_t pos = (b->head + 1) % cap;
@@ -1297,20 +1419,44 @@ static int prb_push_batch_impl(PrbBuffer *b, int64_t nrows, void *const *src, cu
   }
   b->head = (b->head + nrows) % cap;
   b->size = b->size + nrows > cap ? cap : b->size + nrows;
-  return MRL_OK;
+  return publish_tail(b, st);
 }
 
 static int prb_sample_impl(PrbBuffer *b, int64_t n, float beta, const float *uniforms,
                            const float *gstats, int32_t world, int64_t *indices, float *weights,
-                           void *const *out_cols, cudaStream_t st, bool p2p = false) {
+                           void *const *out_cols, cudaStream_t st, bool p2p = false,
+                           const float *beta_dev = nullptr) {
+  if (b->size <= 0) {
+    set_error("PriorityReplayBuffer.sample: the buffer is empty");
+    return MRL_ERR_STATE;
+  }
   SampleArgs S;
-  S.peers = nullptr, S.mailbox = nullptr, S.rank = 0, S.epoch = 0;
+  S.pub = PublishArgs(), S.mailbox = nullptr, S.slot = 0, S.expect = 0, S.diag = nullptr, S.err = nullptr;
+  S.timeout_ns = g_shard_timeout_ns, S.beta_dev = beta_dev;
   if (p2p) {
-    S.peers = b->link.peer_dev;
-    S.mailbox = b->link.mailbox;
-    S.rank = b->link.rank;
-    S.epoch = ++b->link.epoch;
-    world = b->link.world;
+    ShardLink &k = b->link;
+    if (k.err_host && *reinterpret_cast<volatile int *>(k.err_host)) {
+      set_error("sharded PriorityReplayBuffer: an earlier sample gave up waiting for the root statistics of rank %d "
+                "(every rank must issue the same sequence of calls on one stream)", *k.err_host - 1);
+      return MRL_ERR_STATE;
+    }
+    world = k.world;
+    S.mailbox = k.mailbox, S.diag = k.diag, S.err = k.err_dev;
+    S.pub.rank = k.rank;
+    if (k.mode == kPublishOnSample) {
+      const uint32_t e = ++k.epoch;
+      S.pub.peers = k.peer_dev, S.pub.world = k.world, S.pub.slot = e & 1u, S.pub.tag = e;
+      S.pub.size = (float)b->size;
+      S.slot = e & 1u, S.expect = e;
+    } else {
+      // nothing has changed the tree since the previous sample: its publication sits in the other slot
+      if (k.published_epoch != k.epoch) {
+        const int rc = publish_tail(b, st, false);
+        if (rc) return rc;
+      }
+      S.slot = k.epoch & 1u, S.expect = k.version;
+      ++k.epoch;
+    }
   }
   S.sum = b->sum, S.mn = b->mn, S.uniforms = uniforms, S.gstats = gstats;
   S.indices = indices, S.weights = weights;
@@ -1371,18 +1517,16 @@ static int prb_update_impl(PrbBuffer *b, const int64_t *indices, const float *pr
   U.epoch = ++b->epoch;
   U.dbg = g_debug_timers;
   U.prefetch = g_tree_prefetch ? 1 : 0;
+  U.pub = make_publication(b, b->size);
   if (n <= kWalkMax && b->levels - kTopLevels <= kWalkLevels && g_update_path == 1) {
     int threads = (int)((n + 31) / 32 * 32);
     threads = threads < 256 ? 256 : (threads > kWalkThreads ? kWalkThreads : threads);
     int bits = 6;
     while ((1 << bits) < 2 * (n < threads ? n : threads)) ++bits;
     const size_t smem = (size_t)(1 << bits) * (2 * 8 + 2 * 8 + 4) + (size_t)kWalkLevels * threads * 8;
-    static bool configured = false;
-    if (!configured) {
+    if (first_use_on_device((const void *)prb_update_walk_kernel))
       MRL_CUDA(cudaFuncSetAttribute(prb_update_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     1024 * 36 + kWalkLevels * kWalkThreads * 8));
-      configured = true;
-    }
     prb_update_walk_kernel<<<1, threads, smem, st>>>(U, bits);
   } else if (g_update_path == 0 && b->levels - kTopLevels <= kWalkLevels && b->levels > kTopLevels &&
              n < (1LL << 31)) {
@@ -1422,6 +1566,8 @@ static void link_free(PrbBuffer *b) {
     if (k.peer[r] && r != k.rank) cudaIpcCloseMemHandle(k.peer[r]);
   if (k.peer_dev) cudaFree(k.peer_dev);
   if (k.mailbox) cudaFree(k.mailbox);
+  if (k.diag) cudaFree(k.diag);
+  if (k.err_host) cudaFreeHost(k.err_host);
   k = ShardLink();
 }
 
@@ -1480,7 +1626,7 @@ extern "C" int mrl_prb_create(int64_t capacity, float alpha, int32_t ncols,
     set_error("mrl_prb_create: allocation failed: %s", cudaGetErrorString(e));
     return MRL_ERR_CUDA;
   }
-  prb_init_kernel<<<kNumSM * 4, 256>>>(b->sum, b->mn, b->tag, b->state, b->cap2);
+  prb_init_kernel<<<sm_count() * 4, 256>>>(b->sum, b->mn, b->tag, b->state, b->cap2);
   g_launches.fetch_add(1);
   e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
@@ -1572,6 +1718,17 @@ extern "C" int mrl_prb_sample_sharded(int64_t handle, int64_t n, float beta, con
                          as_stream(stream));
 }
 
+// MRL_ERR_STATE when a kernel of this handle gave up polling its mailbox (the word is mapped host memory)
+static int link_error(const PrbBuffer *b) {
+  const ShardLink &k = b->link;
+  if (k.err_host && *reinterpret_cast<volatile int *>(k.err_host)) {
+    set_error("sharded PriorityReplayBuffer: the sample gave up waiting for the root statistics of rank %d "
+              "(every rank must issue the same sequence of calls on one stream)", *k.err_host - 1);
+    return MRL_ERR_STATE;
+  }
+  return MRL_OK;
+}
+
 static int prb_sample_host_impl(PrbBuffer *b, int64_t n, float beta, const float *uniforms,
                                 int64_t *indices, float *weights, void *const *out_cols,
                                 void *stream, bool p2p) {
@@ -1608,6 +1765,7 @@ static int prb_sample_host_impl(PrbBuffer *b, int64_t n, float beta, const float
     if (rc) return rc;
     rc = stream_wait_spin(st);
     if (rc) return rc;
+    if (p2p && (rc = link_error(b))) return rc;
     memcpy(indices, hz + o_idx, (size_t)n * 8);
     memcpy(weights, hz + o_w, (size_t)n * 4);
     if (out_cols)
@@ -1622,6 +1780,7 @@ static int prb_sample_host_impl(PrbBuffer *b, int64_t n, float beta, const float
     MRL_CUDA(cudaMemcpyAsync(b->stage.host, d, total, cudaMemcpyDeviceToHost, st));
     rc = stream_wait_spin(st);
     if (rc) return rc;
+    if (p2p && (rc = link_error(b))) return rc;
     const uint8_t *hz = b->stage.host;
     memcpy(indices, hz + o_idx, (size_t)n * 8);
     memcpy(weights, hz + o_w, (size_t)n * 4);
@@ -1634,6 +1793,7 @@ static int prb_sample_host_impl(PrbBuffer *b, int64_t n, float beta, const float
         MRL_CUDA(cudaMemcpyAsync(out_cols[c], d + off[c], (size_t)n * b->row_bytes[c],
                                  cudaMemcpyDeviceToHost, st));
     MRL_CUDA(cudaStreamSynchronize(st));
+    if (p2p && (rc = link_error(b))) return rc;
     memcpy(indices, b->stage.host + o_idx, (size_t)n * 8);
     memcpy(weights, b->stage.host + o_w, (size_t)n * 4);
   }
@@ -1676,17 +1836,21 @@ extern "C" int mrl_prb_update_host(int64_t handle, const int64_t *indices,
     const char *e = getenv("MRL_UPDATE_PATH");
     g_update_path = (e && e[0] == 'w') ? 1 : ((e && e[0] == 't') ? 2 : 0);
   }
+  // the indices are host memory here, so checking them costs nothing (the device entry point keeps the
+  // reference's contract: "caller needs to ensure the validity of the indices", priority_replay_buffer.py:113)
+  for (int64_t i = 0; i < n; ++i)
+    MRL_REQUIRE(indices[i] >= 0 && indices[i] < b->capacity,
+                "mrl_prb_update_host: index %lld at position %lld is outside [0, %lld)", (long long)indices[i],
+                (long long)i, (long long)b->capacity);
   if (update_takes_inline(b, n) && !g_no_inline_update) {
     // learner-sized batch: it rides in the launch itself (no copy, no staging, the caller's arrays are free
     // again when this returns)
     InlineBatch ib;
-    bool fits = true;
     for (int64_t i = 0; i < n; ++i) {
-      fits = fits && indices[i] >= 0 && indices[i] < (1LL << 31);
       ib.idx[i] = (int32_t)indices[i];
       ib.pr[i] = priorities[i];
     }
-    if (fits) return prb_update_impl(b, nullptr, nullptr, n, st, &ib);
+    return prb_update_impl(b, nullptr, nullptr, n, st, &ib);
   }
   const size_t o_p = (size_t)n * 8, total = o_p + (size_t)n * 4;
   int rc = b->stage.wait();
@@ -1754,7 +1918,12 @@ extern "C" int mrl_prb_shard_init(int64_t handle, int32_t rank, int32_t world, v
   k.rank = rank, k.world = world;
   const size_t bytes = sizeof(uint2) * 2 * (size_t)world * 4;
   MRL_CUDA(cudaMalloc((void **)&k.mailbox, bytes));
-  MRL_CUDA(cudaMemset(k.mailbox, 0, bytes));  // epoch 0 never matches a call (epochs start at 1)
+  MRL_CUDA(cudaMemset(k.mailbox, 0, bytes));  // tag 0 never matches a call (tags start at 1)
+  MRL_CUDA(cudaMalloc((void **)&k.diag, sizeof(ShardDiag)));
+  MRL_CUDA(cudaMemset(k.diag, 0, sizeof(ShardDiag)));
+  MRL_CUDA(cudaHostAlloc((void **)&k.err_host, sizeof(int), cudaHostAllocMapped));
+  *k.err_host = 0;
+  MRL_CUDA(cudaHostGetDevicePointer((void **)&k.err_dev, k.err_host, 0));
   MRL_CUDA(cudaDeviceSynchronize());
   cudaIpcMemHandle_t h;
   MRL_CUDA(cudaIpcGetMemHandle(&h, k.mailbox));
@@ -1762,10 +1931,20 @@ extern "C" int mrl_prb_shard_init(int64_t handle, int32_t rank, int32_t world, v
   return MRL_OK;
 }
 
-extern "C" int mrl_prb_shard_connect(int64_t handle, const void *all_ipc_handles) {
+extern "C" int mrl_prb_shard_set_mode(int64_t handle, int32_t mode) {
+  PRB_GET(b, handle);
+  MRL_REQUIRE(mode == kPublishOnSample || mode == kPublishOnMutation, "mrl_prb_shard_set_mode: mode is 0 or 1");
+  MRL_REQUIRE(b->link.mailbox && !b->link.peer_dev,
+              "mrl_prb_shard_set_mode: call it between mrl_prb_shard_init and mrl_prb_shard_connect");
+  b->link.mode = mode;
+  return MRL_OK;
+}
+
+extern "C" int mrl_prb_shard_connect(int64_t handle, const void *all_ipc_handles, void *stream) {
   PRB_GET(b, handle);
   ShardLink &k = b->link;
   MRL_REQUIRE(k.world >= 1 && k.mailbox && all_ipc_handles, "mrl_prb_shard_connect: call mrl_prb_shard_init first");
+  MRL_REQUIRE(!k.peer_dev, "mrl_prb_shard_connect: already connected");
   for (int r = 0; r < k.world; ++r) {
     if (r == k.rank) {
       k.peer[r] = k.mailbox;
@@ -1774,12 +1953,43 @@ extern "C" int mrl_prb_shard_connect(int64_t handle, const void *all_ipc_handles
     cudaIpcMemHandle_t h;
     memcpy(&h, (const char *)all_ipc_handles + 64 * (size_t)r, sizeof(h));
     void *p = nullptr;
-    MRL_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      // a rank on another node, or no peer access: the caller falls back to the all-gather path
+      cudaGetLastError();
+      for (int q = 0; q < r; ++q)
+        if (q != k.rank && k.peer[q]) cudaIpcCloseMemHandle(k.peer[q]), k.peer[q] = nullptr;
+      set_error("mrl_prb_shard_connect: cannot map the mailbox of rank %d: %s", r, cudaGetErrorString(e));
+      return MRL_ERR_CUDA;
+    }
     k.peer[r] = (uint2 *)p;
   }
   MRL_CUDA(cudaMalloc((void **)&k.peer_dev, sizeof(uint2 *) * kMaxWorld));
   MRL_CUDA(cudaMemcpy(k.peer_dev, k.peer, sizeof(uint2 *) * kMaxWorld, cudaMemcpyHostToDevice));
-  k.epoch = 0;
+  k.epoch = 0, k.version = 0, k.published_epoch = 0;
+  // kPublishOnMutation: the state the buffer has now is publication number 1 (every peer's mailbox exists
+  // since its own mrl_prb_shard_init, which precedes the exchange of the handles)
+  return publish_tail(b, as_stream(stream));
+}
+
+extern "C" int mrl_prb_shard_diag(int64_t handle, int64_t *wait_cycles, int64_t *polled_calls,
+                                  int64_t *waited_calls, int64_t *timeouts, int32_t reset, void *stream) {
+  PRB_GET(b, handle);
+  MRL_REQUIRE(b->link.diag, "mrl_prb_shard_diag: the buffer is not sharded");
+  cudaStream_t st = as_stream(stream);
+  ShardDiag d;
+  MRL_CUDA(cudaMemcpyAsync(&d, b->link.diag, sizeof(d), cudaMemcpyDeviceToHost, st));
+  if (reset) MRL_CUDA(cudaMemsetAsync(b->link.diag, 0, sizeof(ShardDiag), st));
+  MRL_CUDA(cudaStreamSynchronize(st));
+  if (wait_cycles) *wait_cycles = (int64_t)d.wait_cycles;
+  if (polled_calls) *polled_calls = (int64_t)d.polled_calls;
+  if (waited_calls) *waited_calls = (int64_t)d.waited_calls;
+  if (timeouts) *timeouts = (int64_t)d.timeouts;
+  if (b->link.err_host && *reinterpret_cast<volatile int *>(b->link.err_host)) {
+    set_error("sharded PriorityReplayBuffer: a sample gave up waiting for the root statistics of rank %d",
+              *b->link.err_host - 1);
+    return MRL_ERR_STATE;
+  }
   return MRL_OK;
 }
 
@@ -1818,5 +2028,5 @@ extern "C" int mrl_prb_set_state(int64_t handle, int64_t size, int64_t head, uin
   b->size = size;
   b->head = head;
   b->ctr = rng_counter;
-  return MRL_OK;
+  return publish_tail(b, st);
 }

@@ -20,6 +20,8 @@
 // bit-comparable kernel.
 #include <stdlib.h>
 
+#include <map>
+
 #include "scan.cuh"
 
 namespace mrl {
@@ -428,11 +430,38 @@ constexpr int WT_S = 32;
 constexpr int WT_WARPS = 4;
 constexpr int WT_WIN = 8;
 
-struct WTileWs {
-  unsigned long long *ticket;  // tiles handed out since the workspace was created
-  uint4 *agg;                  // [tiles][32] {a, epoch, b, epoch}
-  uint2 *incl;                 // [tiles][32] {x, epoch}
+// Launch state of the look-back kernels lives IN the workspace and is advanced by the last CTA of every
+// launch (not by the host): a launch reads `base` and `epoch` when it starts, takes tickets from `ticket`,
+// and its last CTA to finish sets base <- ticket, epoch <- epoch + 1 for the next launch on the stream.
+// Nothing launch-specific travels in the kernel parameters, so a captured CUDA graph replays correctly.
+// (The epoch is 32 bits and words are only trusted when they carry the current epoch; a word written exactly
+// 2^32 launches ago and not since could be mistaken -- every launch of a shape rewrites all of its words.)
+struct LLCtl {
+  unsigned long long ticket;  // tickets handed out since the workspace was created
+  unsigned long long base;    // value of `ticket` when the current launch started
+  unsigned int epoch;         // tag of the current launch's words
+  unsigned int done;          // CTAs of the current launch that have finished
 };
+struct WTileWs {
+  LLCtl *ctl;
+  uint4 *agg;   // [tiles][32] {a, epoch, b, epoch}
+  uint2 *incl;  // [tiles][32] {x, epoch}
+};
+// end of a look-back kernel: every thread of the CTA has issued its last ticket / word
+__device__ __forceinline__ void ll_finish(LLCtl *ctl) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int prev;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(&ctl->done) : "memory");
+    if (prev == gridDim.x - 1) {  // all other CTAs read base / epoch before their own increment
+      const unsigned long long t = *reinterpret_cast<volatile unsigned long long *>(&ctl->ticket);
+      const unsigned int e = *reinterpret_cast<volatile unsigned int *>(&ctl->epoch);
+      *reinterpret_cast<volatile unsigned long long *>(&ctl->base) = t;
+      *reinterpret_cast<volatile unsigned int *>(&ctl->epoch) = e + 1u == 0u ? 1u : e + 1u;
+      *reinterpret_cast<volatile unsigned int *>(&ctl->done) = 0u;
+    }
+  }
+}
 
 __device__ __forceinline__ uint4 ld_relaxed_v4(const uint4 *p) {
   uint4 v;
@@ -573,17 +602,19 @@ __device__ __forceinline__ void wtile_body(const ScanArgs &A, const WTileWs &ws,
 
 template <int OP, bool HD>
 __global__ void __launch_bounds__(WT_WARPS * 32, OP == OP_GAE ? 3 : 4)
-    scan_tm_wtile_kernel(const __grid_constant__ ScanArgs A, WTileWs ws, unsigned long long ticket_base,
-                         unsigned int epoch, int n_chunks, int n_wgroups, int n_cgroups) {
-  __shared__ unsigned int s_ticket;
+    scan_tm_wtile_kernel(const __grid_constant__ ScanArgs A, WTileWs ws, int n_chunks, int n_wgroups,
+                         int n_cgroups) {
+  __shared__ unsigned int s_ticket, s_epoch;
   __shared__ int s_zero;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
-    s_ticket = (unsigned int)(atomicAdd(ws.ticket, 1ull) - ticket_base);
+    const unsigned long long base = *reinterpret_cast<volatile unsigned long long *>(&ws.ctl->base);
+    s_epoch = *reinterpret_cast<volatile unsigned int *>(&ws.ctl->epoch);
+    s_ticket = (unsigned int)(atomicAdd(&ws.ctl->ticket, 1ull) - base);
     s_zero = 0;
   }
   __syncthreads();
-  const unsigned int ticket = s_ticket;
+  const unsigned int ticket = s_ticket, epoch = s_epoch;
   const int chunk = n_chunks - 1 - (int)(ticket / (unsigned)n_cgroups);  // latest chunk first
   int wgroup = (int)(ticket % (unsigned)n_cgroups) * WT_WARPS + w;
   const bool warp_on = wgroup < n_wgroups;
@@ -636,15 +667,17 @@ __global__ void __launch_bounds__(WT_WARPS * 32, OP == OP_GAE ? 3 : 4)
   // Scheduling fence (see scan_tm_tile4_kernel): the barrier pins the loads above, the never-taken
   // branch on an opaque zero pins their consumers below.
   __syncthreads();
-  if (*reinterpret_cast<volatile int *>(&s_zero) != 0 || !warp_on) return;
-
-  const bool full_cols = ((int64_t)wgroup + 1) * 32 <= A.N;
-  if (interior && full_cols)
-    wtile_body<OP, HD, true>(A, ws, epoch, a, v, db, lastv, chunk, wgroup, n_chunks, n_wgroups, lane,
-                             col, colc, valid);
-  else
-    wtile_body<OP, HD, false>(A, ws, epoch, a, v, db, lastv, chunk, wgroup, n_chunks, n_wgroups, lane,
-                              col, colc, valid);
+  if (*reinterpret_cast<volatile int *>(&s_zero) != 0) return;
+  if (warp_on) {
+    const bool full_cols = ((int64_t)wgroup + 1) * 32 <= A.N;
+    if (interior && full_cols)
+      wtile_body<OP, HD, true>(A, ws, epoch, a, v, db, lastv, chunk, wgroup, n_chunks, n_wgroups, lane,
+                               col, colc, valid);
+    else
+      wtile_body<OP, HD, false>(A, ws, epoch, a, v, db, lastv, chunk, wgroup, n_chunks, n_wgroups, lane,
+                                col, colc, valid);
+  }
+  ll_finish(ws.ctl);
 }
 
 // ---- time-major single-pass scan, software-pipelined warp tiles (default for aligned shapes) --
@@ -675,10 +708,13 @@ __device__ __forceinline__ void cp_async4(void *smem, const void *g) {
 
 template <int OP, bool HD>
 __global__ void __launch_bounds__(PIPE_WARPS * 32, 3)
-    scan_tm_pipe_kernel(const __grid_constant__ ScanArgs A, WTileWs ws, unsigned long long ticket_base,
-                        unsigned int epoch, int n_chunks, int n_wgroups) {
+    scan_tm_pipe_kernel(const __grid_constant__ ScanArgs A, WTileWs ws, int n_chunks, int n_wgroups) {
   extern __shared__ __align__(16) unsigned char pipe_smem[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  // (every warp reads the launch state itself, before its first ticket: the last CTA rewrites it only after
+  // all CTAs -- hence all warps -- have finished)
+  const unsigned long long ticket_base = *reinterpret_cast<volatile unsigned long long *>(&ws.ctl->base);
+  const unsigned int epoch = *reinterpret_cast<volatile unsigned int *>(&ws.ctl->epoch);
   PipeBuf *bufs = reinterpret_cast<PipeBuf *>(pipe_smem) + 2 * w;
   const long long n_tiles = (long long)n_chunks * n_wgroups;
   constexpr unsigned FULL = 0xffffffffu;
@@ -686,7 +722,7 @@ __global__ void __launch_bounds__(PIPE_WARPS * 32, 3)
 
   auto take = [&]() -> long long {
     unsigned long long t = 0;
-    if (lane == 0) t = atomicAdd(ws.ticket, 1ull) - ticket_base;
+    if (lane == 0) t = atomicAdd(&ws.ctl->ticket, 1ull) - ticket_base;
     t = __shfl_sync(FULL, t, 0);
     return (long long)t < n_tiles ? (long long)t : -1;
   };
@@ -757,6 +793,7 @@ __global__ void __launch_bounds__(PIPE_WARPS * 32, 3)
     cur = nxt;
     cb ^= 1;
   }
+  ll_finish(ws.ctl);
 }
 
 // ---- batch-major warp scan ----------------------------------------------------------------
@@ -926,9 +963,57 @@ static void launch_bm(const ScanArgs &A, cudaStream_t st) {
 
 static bool aligned16(const void *p) { return (((uintptr_t)p) & 15) == 0; }
 
-// workspace of the tile scan (ticket, flags, aggregates), grow-only, one per process
-static uint8_t *g_tile_ws = nullptr;
-static size_t g_tile_ws_bytes = 0;
+// Workspaces are keyed by (device, stream): two scans running at once on different streams or devices never
+// share flag words, partials or scratch (process-global statics let concurrent launches corrupt
+// each other's look-back words, and lived on whichever device came first).  Work on ONE stream is ordered by
+// the stream.  Buffers only grow; a retired buffer is kept until exit, because a captured graph may still
+// point at it.
+struct StreamWs {
+  uint8_t *ll = nullptr;  // look-back words: [LLCtl | agg | incl]
+  size_t ll_bytes = 0;
+  uint8_t *tile = nullptr;  // tile4 kernel: flags, aggregates
+  size_t tile_bytes = 0;
+  double2 *moments = nullptr;  // [kMomentSlots] partial (sum, sum of squares) + [1] total + ticket
+  uint8_t *scratch = nullptr;  // *_host scans, V-trace intermediates
+  size_t scratch_bytes = 0;
+};
+static std::mutex g_ws_mu;
+static std::map<std::pair<int, cudaStream_t>, StreamWs> g_ws;
+
+static StreamWs *stream_ws(cudaStream_t st) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> g(g_ws_mu);
+  return &g_ws[std::make_pair(dev, st)];  // (std::map: references stay valid)
+}
+static bool capturing(cudaStream_t st) {
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) {
+    cudaGetLastError();
+    return true;
+  }
+  return cap != cudaStreamCaptureStatusNone;
+}
+// grow-only buffer of a stream workspace; `zero`: cleared when (re)allocated.  Allocation is not a stream
+// operation, so a capturing stream must find the buffer in place (run the call once before capturing).
+static int ws_reserve(uint8_t **buf, size_t *have, size_t need, bool zero, cudaStream_t st, bool *fresh = nullptr) {
+  if (fresh) *fresh = false;
+  if (need <= *have) return MRL_OK;
+  if (capturing(st)) {
+    set_error("this call needs %zu bytes of workspace that are not allocated yet: run it once on this stream "
+              "before capturing it in a CUDA graph", need);
+    return MRL_ERR_STATE;
+  }
+  size_t cap = 1 << 16;
+  while (cap < need) cap <<= 1;
+  uint8_t *p = nullptr;
+  MRL_CUDA(cudaMalloc((void **)&p, cap));
+  if (zero) MRL_CUDA(cudaMemsetAsync(p, 0, cap, st));
+  *buf = p, *have = cap;  // (the previous buffer stays allocated: graphs / launches in flight may use it)
+  if (fresh) *fresh = true;
+  return MRL_OK;
+}
+
 static int g_tile_mode = -1;  // MRL_TM_KERNEL=chunked forces the two-pass kernel
 static int64_t g_host_chunks = 0;  // option "host_scan_chunks": pieces of the *_host scans, 0 = auto, 1 = no pipelining
 static int g_bm_mode = 0;     // 0 auto, 1 warp-per-row register kernel only, 2 TMA row kernel whenever it fits
@@ -952,28 +1037,16 @@ int set_scan_option(const char *key, int64_t value) {
   return MRL_OK;
 }
 
-static int tile_workspace(size_t need, uint8_t **p) {
-  if (need > g_tile_ws_bytes) {
-    if (g_tile_ws) cudaFree(g_tile_ws);
-    g_tile_ws = nullptr;
-    g_tile_ws_bytes = 0;
-    MRL_CUDA(cudaMalloc((void **)&g_tile_ws, need));
-    g_tile_ws_bytes = need;
-  }
-  *p = g_tile_ws;
-  return MRL_OK;
-}
-
 template <int OP, bool HD>
-static int launch_scan_hd(ScanArgs A, int32_t layout, int32_t mode, cudaStream_t st) {
+static int launch_scan_hd(ScanArgs A, int32_t layout, int32_t mode, cudaStream_t st, int *mom_parts) {
   if (layout == MRL_TIME_MAJOR) {
     A.st = A.N, A.sc = 1, A.dst = A.B, A.dsc = 1;
     bool chunked;
     if (mode == MRL_SCAN_SEQUENTIAL) chunked = false;
     else if (mode == MRL_SCAN_PARALLEL) chunked = A.T >= 2;
-    else chunked = A.T >= 64 && A.N < (int64_t)kNumSM * 1024;
+    else chunked = A.T >= 64 && A.N < (int64_t)sm_count() * 1024;
     if (chunked && (g_tile_mode == 0 || g_tile_mode == 6)) {
-      const int rc = scan_tm_strip_launch(A, OP, g_tile_mode == 6, st);
+      const int rc = scan_tm_strip_launch(A, OP, g_tile_mode == 6, st, mom_parts);
       if (rc != kScanNotApplicable) {
         if (rc != MRL_OK) return rc;
         MRL_LAUNCHED();
@@ -994,59 +1067,31 @@ static int launch_scan_hd(ScanArgs A, int32_t layout, int32_t mode, cudaStream_t
       const size_t tiles = (size_t)nch * n_wgroups;
       const size_t agg_bytes = tiles * 32 * sizeof(uint4);
       const size_t need = 256 + agg_bytes + tiles * 32 * sizeof(uint2);
-      {
-        // This path keeps its ticket base and flag epoch on the HOST (they travel as launch parameters): a
-        // replayed capture would reuse the capture's values and its consumers would wait for flags that never
-        // come (a captured replay hung in testing).  Refuse instead.
-        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-        const cudaError_t ce = cudaStreamIsCapturing(st, &cap);
-        if (ce != cudaSuccess || cap != cudaStreamCaptureStatusNone) {
-          if (ce != cudaSuccess) cudaGetLastError();
-          set_error("this scan shape runs the look-back kernels, which cannot be captured in a CUDA graph "
-                    "(host-side epoch); launch it on a stream that is not capturing");
-          return MRL_ERR_STATE;
-        }
-      }
-      // flag-in-payload workspace: zeroed once when (re)allocated, then validated by the launch epoch
-      static uint8_t *ll_ws = nullptr;
-      static size_t ll_bytes = 0;
-      static unsigned long long ll_ticket_base = 0;
-      static unsigned int ll_epoch = 0;
-      if (need > ll_bytes) {
-        if (ll_ws) {
-          MRL_CUDA(cudaStreamSynchronize(st));
-          cudaFree(ll_ws);
-        }
-        ll_ws = nullptr, ll_bytes = 0;
-        MRL_CUDA(cudaMalloc((void **)&ll_ws, need));
-        MRL_CUDA(cudaMemsetAsync(ll_ws, 0, need, st));
-        ll_bytes = need, ll_ticket_base = 0, ll_epoch = 0;
-      }
-      if (++ll_epoch == 0u) {  // epoch wrapped: clear stale words once
-        MRL_CUDA(cudaMemsetAsync(ll_ws + 256, 0, ll_bytes - 256, st));
-        ll_epoch = 1;
+      // flag-in-payload workspace of this (device, stream): zeroed when (re)allocated, then validated by the
+      // launch epoch, which the kernels advance themselves (LLCtl) -- capturable in a CUDA graph
+      StreamWs *W = stream_ws(st);
+      bool fresh = false;
+      int rc = ws_reserve(&W->ll, &W->ll_bytes, need, true, st, &fresh);
+      if (rc) return rc;
+      if (fresh) {
+        const LLCtl init = {0ull, 0ull, 1u, 0u};
+        MRL_CUDA(cudaMemcpyAsync(W->ll, &init, sizeof(init), cudaMemcpyHostToDevice, st));
       }
       WTileWs ws;
-      ws.ticket = reinterpret_cast<unsigned long long *>(ll_ws);
-      ws.agg = reinterpret_cast<uint4 *>(ll_ws + 256);
-      ws.incl = reinterpret_cast<uint2 *>(ll_ws + 256 + agg_bytes);
+      ws.ctl = reinterpret_cast<LLCtl *>(W->ll);
+      ws.agg = reinterpret_cast<uint4 *>(W->ll + 256);
+      ws.incl = reinterpret_cast<uint2 *>(W->ll + 256 + agg_bytes);
       if (pipe) {
         const size_t smem = sizeof(PipeBuf) * 2 * PIPE_WARPS;
-        static bool configured = false;
-        if (!configured) {
+        if (first_use_on_device((const void *)scan_tm_pipe_kernel<OP, HD>))
           MRL_CUDA(cudaFuncSetAttribute(scan_tm_pipe_kernel<OP, HD>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          configured = true;
-        }
-        int64_t ctas = (int64_t)kNumSM * 3;
+        int64_t ctas = (int64_t)sm_count() * 3;
         if (ctas * PIPE_WARPS > (int64_t)tiles) ctas = ((int64_t)tiles + PIPE_WARPS - 1) / PIPE_WARPS;
-        scan_tm_pipe_kernel<OP, HD><<<(unsigned)ctas, PIPE_WARPS * 32, smem, st>>>(
-            A, ws, ll_ticket_base, ll_epoch, (int)nch, (int)n_wgroups);
-        ll_ticket_base += (unsigned long long)tiles + (unsigned long long)(ctas * PIPE_WARPS);
+        scan_tm_pipe_kernel<OP, HD><<<(unsigned)ctas, PIPE_WARPS * 32, smem, st>>>(A, ws, (int)nch, (int)n_wgroups);
       } else {
         scan_tm_wtile_kernel<OP, HD><<<(unsigned)(nch * n_cgroups), WT_WARPS * 32, 0, st>>>(
-            A, ws, ll_ticket_base, ll_epoch, (int)nch, (int)n_wgroups, (int)n_cgroups);
-        ll_ticket_base += (unsigned long long)(nch * n_cgroups);
+            A, ws, (int)nch, (int)n_wgroups, (int)n_cgroups);
       }
     } else if (chunked && (g_tile_mode == 3 || g_tile_mode == 0 || g_tile_mode == 6) && vec4) {
       const int64_t n4 = (A.T + T4_TC - 1) / T4_TC;
@@ -1054,9 +1099,10 @@ static int launch_scan_hd(ScanArgs A, int32_t layout, int32_t mode, cudaStream_t
       const size_t tiles = (size_t)n4 * n_groups;
       const size_t flag_bytes = (4 + tiles * 4 + 255) / 256 * 256;
       const size_t agg_bytes = tiles * T4_COLS * sizeof(float2);
-      uint8_t *wsp;
-      int rc = tile_workspace(flag_bytes + agg_bytes + tiles * T4_COLS * sizeof(float), &wsp);
+      StreamWs *W = stream_ws(st);
+      int rc = ws_reserve(&W->tile, &W->tile_bytes, flag_bytes + agg_bytes + tiles * T4_COLS * sizeof(float), false, st);
       if (rc) return rc;
+      uint8_t *wsp = W->tile;
       MRL_CUDA(cudaMemsetAsync(wsp, 0, flag_bytes, st));
       Tile4Ws ws;
       ws.ticket = reinterpret_cast<unsigned int *>(wsp);
@@ -1083,7 +1129,7 @@ static int launch_scan_hd(ScanArgs A, int32_t layout, int32_t mode, cudaStream_t
       scan_seq_kernel<OP, HD><<<(unsigned)blocks, 128, 0, st>>>(A);
     } else {
       if (g_bm_mode != 1) {
-        const int rc = scan_bm_row_launch(A, OP, g_bm_mode == 2, st);
+        const int rc = scan_bm_row_launch(A, OP, g_bm_mode == 2, st, mom_parts);
         if (rc != kScanNotApplicable) {
           if (rc != MRL_OK) return rc;
           MRL_LAUNCHED();
@@ -1105,32 +1151,28 @@ static int launch_scan_hd(ScanArgs A, int32_t layout, int32_t mode, cudaStream_t
 }
 
 template <int OP>
-static int launch_scan(ScanArgs A, int32_t layout, int32_t mode, cudaStream_t st) {
+static int launch_scan(ScanArgs A, int32_t layout, int32_t mode, cudaStream_t st, int *mom_parts = nullptr) {
+  if (mom_parts) *mom_parts = 0;
   if (A.T <= 0 || A.N <= 0) return MRL_OK;
   if (g_tile_mode < 0) {
     const char *e = getenv("MRL_TM_KERNEL");
-    // "s": TMA strips whenever aligned (also below the width where auto picks them)
-    // default 0: 128-column tiles when aligned, else 32-column tiles; "t": 32-column tiles only;
-    // "c": two-pass chunked kernel only
-    // "4": 128-column CTA tiles (aligned inputs only)
-    // default / "w": warp-owned tiles with flag-in-payload look-back; "4": 128-column CTA tiles
-    // (aligned inputs; also serves the next_value form of GAE); "c": two-pass chunked kernel
+    // MRL_TM_KERNEL (same choices as option "tm_kernel"): default auto = TMA strips for wide aligned batches,
+    // else warp tiles with look-back (cp.async pipeline when aligned); "s" strips whenever aligned, "w" warp
+    // tiles only, "4" 128-column CTA tiles (aligned; also serves the next_value form of GAE), "c" two-pass
     g_tile_mode = 0;
     if (e && e[0] == 'c') g_tile_mode = 2;
     if (e && e[0] == '4') g_tile_mode = 3;
     if (e && e[0] == 'w') g_tile_mode = 5;
     if (e && e[0] == 's') g_tile_mode = 6;
   }
-  if (OP != OP_AFFINE && A.done) return launch_scan_hd<OP, true>(A, layout, mode, st);
-  return launch_scan_hd<OP, false>(A, layout, mode, st);
+  if (OP != OP_AFFINE && A.done) return launch_scan_hd<OP, true>(A, layout, mode, st, mom_parts);
+  return launch_scan_hd<OP, false>(A, layout, mode, st, mom_parts);
 }
 
 // ---- advantage normalisation ----------------------------------------------------------------
-// pass 1: one float64 partial (sum, sum of squares) per CTA; pass 2: every CTA folds the partials in the
-// same fixed order (deterministic), then scales its share.  Replaces moments() + elementwise ops of
-// ppo.py:361-368.
-constexpr int NORM_CTAS = kNumSM * 4;
-
+// (x - mean) / (sqrt(var) + eps) over all elements, moments in float64 and a fixed order (ppo.py:361-368,
+// a2c.py:190-192).  The moments come as per-CTA partials: from the scan kernel that produced x (ScanArgs.mom:
+// no extra pass) or from norm_partial_kernel; the apply pass folds them in index order in every CTA.
 __global__ void __launch_bounds__(256)
     norm_partial_kernel(const float *__restrict__ x, int64_t n, double2 *__restrict__ part) {
   __shared__ double ss[8], sq[8];
@@ -1167,16 +1209,26 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     norm_apply_kernel(const float *__restrict__ x, float *__restrict__ out, int64_t n, float eps,
                       const double2 *__restrict__ part, int nparts) {
+  __shared__ double ra[8], rb[8];
   __shared__ float s_mean, s_inv;
-  if (threadIdx.x < 32) {
+  {
+    // 256 threads, contiguous runs of the partials, folded in index order (same in every CTA)
+    const int per = (nparts + 255) / 256;
     double a = 0.0, b = 0.0;
-    for (int i = threadIdx.x; i < nparts; i += 32) a += part[i].x, b += part[i].y;
+    for (int i = threadIdx.x * per; i < nparts && i < (threadIdx.x + 1) * per; ++i) {
+      const double2 v = __ldcg(part + i);
+      a += v.x, b += v.y;
+    }
 #pragma unroll
     for (int off = 16; off; off >>= 1) {
       a += __shfl_xor_sync(0xffffffffu, a, off);
       b += __shfl_xor_sync(0xffffffffu, b, off);
     }
+    if ((threadIdx.x & 31) == 0) ra[threadIdx.x >> 5] = a, rb[threadIdx.x >> 5] = b;
+    __syncthreads();
     if (threadIdx.x == 0) {
+      a = 0.0, b = 0.0;
+      for (int w = 0; w < 8; ++w) a += ra[w], b += rb[w];
       const double mean = a / (double)n;
       double var = b / (double)n - mean * mean;
       var = var > 0.0 ? var : 0.0;
@@ -1187,23 +1239,56 @@ __global__ void __launch_bounds__(256)
   __syncthreads();
   const float mean = s_mean, inv = s_inv;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-    out[i] = __fmul_rn(__fsub_rn(__ldg(x + i), mean), inv);
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (((((uintptr_t)x) | ((uintptr_t)out)) & 15) == 0) {
+    const int64_t n4 = n / 4;
+    for (int64_t i = gid; i < n4; i += stride) {
+      const float4 v = __ldcs(reinterpret_cast<const float4 *>(x) + i);
+      __stcs(reinterpret_cast<float4 *>(out) + i,
+             make_float4(__fmul_rn(__fsub_rn(v.x, mean), inv), __fmul_rn(__fsub_rn(v.y, mean), inv),
+                         __fmul_rn(__fsub_rn(v.z, mean), inv), __fmul_rn(__fsub_rn(v.w, mean), inv)));
+    }
+    for (int64_t i = n4 * 4 + gid; i < n; i += stride) out[i] = __fmul_rn(__fsub_rn(x[i], mean), inv);
+  } else {
+    for (int64_t i = gid; i < n; i += stride) out[i] = __fmul_rn(__fsub_rn(x[i], mean), inv);
+  }
 }
 
-// grow-only device scratch for the *_host entry points
-static uint8_t *g_scratch = nullptr;
-static size_t g_scratch_bytes = 0;
-static int scratch(size_t need, uint8_t **p) {
-  if (need > g_scratch_bytes) {
-    if (g_scratch) cudaFree(g_scratch);
-    g_scratch = nullptr;
-    g_scratch_bytes = 0;
-    MRL_CUDA(cudaMalloc((void **)&g_scratch, need));
-    g_scratch_bytes = need;
+static int moments_ws(cudaStream_t st, double2 **p) {
+  StreamWs *W = stream_ws(st);
+  if (!W->moments) {
+    if (capturing(st)) {
+      set_error("the normalisation workspace of this stream is not allocated yet: run the call once before capturing");
+      return MRL_ERR_STATE;
+    }
+    MRL_CUDA(cudaMalloc((void **)&W->moments, sizeof(double2) * kMomentSlots));
   }
-  *p = g_scratch;
+  *p = W->moments;
   return MRL_OK;
+}
+
+// x -> out with the moments taken from `nparts` partials already in `part` (nparts == 0: computed here)
+static int normalize_impl(const float *x, float *out, int64_t n, float eps, double2 *part, int nparts,
+                          cudaStream_t st) {
+  int64_t ctas = (n + 2047) / 2048;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  ctas = ctas > cap ? cap : ctas;
+  if (nparts == 0) {
+    nparts = (int)(ctas > kMomentSlots ? kMomentSlots : ctas);
+    norm_partial_kernel<<<nparts, 256, 0, st>>>(x, n, part);
+    MRL_LAUNCHED();
+  }
+  norm_apply_kernel<<<(unsigned)ctas, 256, 0, st>>>(x, out, n, eps, part, nparts);
+  MRL_LAUNCHED();
+  return MRL_OK;
+}
+
+// grow-only device scratch of a stream (the *_host entry points, V-trace intermediates)
+static int scratch(size_t need, uint8_t **p, cudaStream_t st) {
+  StreamWs *W = stream_ws(st);
+  const int rc = ws_reserve(&W->scratch, &W->scratch_bytes, need, false, st);
+  *p = W->scratch;
+  return rc;
 }
 static size_t up256(size_t x) { return (x + 255) / 256 * 256; }
 
@@ -1258,18 +1343,230 @@ extern "C" int mrl_affine_scan(const float *a, const float *b, const float *x_la
 extern "C" int mrl_normalize(const float *x, float *out, int64_t n, float eps, void *stream) {
   MRL_REQUIRE(n >= 0 && (n == 0 || (x && out)), "mrl_normalize: bad arguments");
   if (n == 0) return MRL_OK;
-  static double2 *part = nullptr;
-  if (!part) MRL_CUDA(cudaMalloc((void **)&part, sizeof(double2) * NORM_CTAS));
   cudaStream_t st = as_stream(stream);
-  int ctas = (int)((n + 1023) / 1024);
-  ctas = ctas > NORM_CTAS ? NORM_CTAS : ctas;
-  norm_partial_kernel<<<ctas, 256, 0, st>>>(x, n, part);
-  g_launches.fetch_add(1);
-  norm_apply_kernel<<<ctas, 256, 0, st>>>(x, out, n, eps, part, ctas);
+  double2 *part;
+  const int rc = moments_ws(st, &part);
+  if (rc) return rc;
+  return normalize_impl(x, out, n, eps, part, 0, st);
+}
+
+extern "C" int mrl_gae_normalized(const float *reward, const float *value, const float *next_value,
+                                  const float *last_value, const uint8_t *done, float *adv, float *ret,
+                                  int64_t T, int64_t B, float gamma, float lambda, float eps, int32_t layout,
+                                  int32_t mode, void *stream) {
+  MRL_REQUIRE(T >= 0 && B >= 0, "mrl_gae_normalized: bad shape");
+  MRL_REQUIRE(layout == MRL_TIME_MAJOR || layout == MRL_BATCH_MAJOR, "mrl_gae_normalized: bad layout");
+  if (T == 0 || B == 0) return MRL_OK;
+  MRL_REQUIRE(reward && value && adv, "mrl_gae_normalized: NULL reward/value/adv");
+  cudaStream_t st = as_stream(stream);
+  ScanArgs A{};
+  A.a = reward, A.v = value, A.nv = next_value, A.last = last_value, A.done = done;
+  A.out = adv, A.ret = ret;
+  A.T = T, A.B = B, A.E = 1, A.N = B, A.gamma = gamma, A.gl = gamma * lambda;
+  int rc = moments_ws(st, &A.mom);
+  if (rc) return rc;
+  int parts = 0;
+  rc = launch_scan<OP_GAE>(A, layout, mode, st, &parts);
+  if (rc) return rc;
+  return normalize_impl(adv, adv, T * B, eps, A.mom, parts, st);
+}
+
+extern "C" int mrl_discounted_return_normalized(const float *reward, const uint8_t *done, const float *last_value,
+                                                float *out, int64_t T, int64_t B, int64_t E, float gamma,
+                                                float eps, int32_t layout, int32_t mode, void *stream) {
+  MRL_REQUIRE(T >= 0 && B >= 0 && E >= 1, "mrl_discounted_return_normalized: bad shape");
+  MRL_REQUIRE(layout == MRL_TIME_MAJOR || (layout == MRL_BATCH_MAJOR && E == 1),
+              "mrl_discounted_return_normalized: batch-major layout needs E == 1");
+  MRL_REQUIRE(gamma >= 0.0f && gamma <= 1.0f,
+              "The discounted factor should be a number in range [0, 1], but got %f.", (double)gamma);
+  if (T == 0 || B == 0) return MRL_OK;
+  MRL_REQUIRE(reward && out, "mrl_discounted_return_normalized: NULL reward/out");
+  cudaStream_t st = as_stream(stream);
+  ScanArgs A{};
+  A.a = reward, A.done = done, A.last = last_value, A.out = out;
+  A.T = T, A.B = B, A.E = E, A.N = B * E, A.gamma = gamma;
+  int rc = moments_ws(st, &A.mom);
+  if (rc) return rc;
+  int parts = 0;
+  rc = launch_scan<OP_DR>(A, layout, mode, st, &parts);
+  if (rc) return rc;
+  return normalize_impl(out, out, T * B * E, eps, A.mom, parts, st);
+}
+
+namespace mrl {
+// ---- V-trace (IMPALA) -----------------------------------------------------------------------
+// get_vs_and_advantages (mindspore_rl/algorithm/impala/vtrace.py:48-108), time-major [T, B]:
+//   rho = min(exp(log_rho), clip_rho); c = min(rho, clip_c); pg_rho = min(rho, clip_pg)          (:79-82)
+//   delta_t = rho_t * (r_t + discount_t * V_{t+1} - V_t),  V_T = bootstrap                       (:84-86)
+//   acc_t = delta_t + discount_t * c_t * acc_{t+1} * mask_t,  acc_T = 0                          (:88-93)
+//   vs_t = acc_t + V_t                                                                          (:99)
+//   pg_adv_t = pg_rho_t * (r_t + discount_t * vs_{t+1} - V_t),  vs_T = bootstrap                 (:103-105)
+// The reference runs ~12 element-wise ops and a Python loop over T; here it is either ONE kernel (thread per
+// column walking t = T-1..0 in the reference's operation order with 4 steps of loads in flight: 28 bytes per
+// element, everything else in registers -- vs_{t+1} is simply the previous step's result) or, for long and
+// narrow trajectories, prep -> parallel affine scan -> post (three passes instead of twelve).
+struct VtraceArgs {
+  const float *log_rhos, *discounts, *rewards, *values, *bootstrap, *masks;  // masks may be NULL (= 1)
+  float clip_rho, clip_pg, clip_c;                                           // +inf = no clipping
+  float *vs, *pg;
+  int64_t T, B;
+};
+
+__global__ void __launch_bounds__(128) vtrace_seq_kernel(const __grid_constant__ VtraceArgs V) {
+  const int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= V.B) return;
+  constexpr int U = 4;
+  const float boot = __ldg(V.bootstrap + col);
+  float acc = 0.0f;      // vs_minus_v_xs of the step after
+  float v_next = boot;   // V_{t+1}
+  float vs_next = boot;  // vs_{t+1}
+  for (int64_t t0 = V.T; t0 > 0; t0 -= U) {
+    float lr[U], dc[U], rw[U], vl[U], mk[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      int64_t t = t0 - 1 - u;
+      t = t < 0 ? 0 : t;  // clamped: the load is always legal, the result may be unused
+      const int64_t i = t * V.B + col;
+      lr[u] = __ldg(V.log_rhos + i), dc[u] = __ldg(V.discounts + i), rw[u] = __ldg(V.rewards + i);
+      vl[u] = __ldg(V.values + i), mk[u] = V.masks ? __ldg(V.masks + i) : 1.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t t = t0 - 1 - u;
+      if (t >= 0) {
+        const float rho = fminf(expf(lr[u]), V.clip_rho);
+        const float c = fminf(rho, V.clip_c), pg_rho = fminf(rho, V.clip_pg);
+        const float delta = __fmul_rn(rho, __fsub_rn(__fadd_rn(rw[u], __fmul_rn(dc[u], v_next)), vl[u]));
+        acc = __fadd_rn(delta, __fmul_rn(__fmul_rn(__fmul_rn(dc[u], c), acc), mk[u]));
+        const float vs = __fadd_rn(acc, vl[u]);
+        const int64_t i = t * V.B + col;
+        V.vs[i] = vs;
+        V.pg[i] = __fmul_rn(pg_rho, __fsub_rn(__fadd_rn(rw[u], __fmul_rn(dc[u], vs_next)), vl[u]));
+        v_next = vl[u], vs_next = vs;
+      }
+    }
+  }
+}
+
+// a = delta, b = discount * c * mask for the affine scan
+__global__ void __launch_bounds__(256) vtrace_prep_kernel(const __grid_constant__ VtraceArgs V, float *__restrict__ a,
+                                                          float *__restrict__ b) {
+  const int64_t n = V.T * V.B, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const bool lastrow = i >= n - V.B;
+    const float v1 = lastrow ? __ldg(V.bootstrap + (i - (n - V.B))) : __ldg(V.values + i + V.B);
+    const float rho = fminf(expf(__ldg(V.log_rhos + i)), V.clip_rho);
+    const float c = fminf(rho, V.clip_c);
+    const float dc = __ldg(V.discounts + i);
+    a[i] = __fmul_rn(rho, __fsub_rn(__fadd_rn(__ldg(V.rewards + i), __fmul_rn(dc, v1)), __ldg(V.values + i)));
+    b[i] = __fmul_rn(__fmul_rn(dc, c), V.masks ? __ldg(V.masks + i) : 1.0f);
+  }
+}
+
+// acc (in V.vs) -> vs and pg_adv; row t needs acc and V of row t+1: rows are walked by whole CTAs so that the
+// in-place update of row t+1 never races the read of it (vs is written to V.vs only after pg used acc[t+1])
+__global__ void __launch_bounds__(256) vtrace_post_kernel(const __grid_constant__ VtraceArgs V, const float *__restrict__ acc) {
+  const int64_t n = V.T * V.B, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const bool lastrow = i >= n - V.B;
+    const float vl = __ldg(V.values + i);
+    const float vs = __fadd_rn(__ldg(acc + i), vl);
+    const float vs1 = lastrow ? __ldg(V.bootstrap + (i - (n - V.B)))
+                              : __fadd_rn(__ldg(acc + i + V.B), __ldg(V.values + i + V.B));
+    const float rho = fminf(expf(__ldg(V.log_rhos + i)), V.clip_rho);
+    const float pg_rho = fminf(rho, V.clip_pg);
+    V.vs[i] = vs;
+    V.pg[i] = __fmul_rn(pg_rho, __fsub_rn(__fadd_rn(__ldg(V.rewards + i), __fmul_rn(__ldg(V.discounts + i), vs1)), vl));
+  }
+}
+
+}  // namespace mrl
+using namespace mrl;
+
+extern "C" int mrl_vtrace(const float *log_rhos, const float *discounts, const float *rewards, const float *values,
+                          const float *bootstrap_value, const float *masks, float clip_rho_threshold,
+                          float clip_pg_threshold, float clip_cs_threshold, float *vs, float *pg_advantages,
+                          int64_t T, int64_t B, int32_t mode, void *stream) {
+  MRL_REQUIRE(T >= 0 && B >= 0, "mrl_vtrace: bad shape");
+  if (T == 0 || B == 0) return MRL_OK;
+  MRL_REQUIRE(log_rhos && discounts && rewards && values && bootstrap_value && vs && pg_advantages,
+              "mrl_vtrace: NULL argument");
+  MRL_REQUIRE(vs != pg_advantages, "mrl_vtrace: vs and pg_advantages must be distinct arrays");
+  cudaStream_t st = as_stream(stream);
+  VtraceArgs V;
+  V.log_rhos = log_rhos, V.discounts = discounts, V.rewards = rewards, V.values = values;
+  V.bootstrap = bootstrap_value, V.masks = masks;
+  V.clip_rho = clip_rho_threshold, V.clip_pg = clip_pg_threshold, V.clip_c = clip_cs_threshold;
+  V.vs = vs, V.pg = pg_advantages, V.T = T, V.B = B;
+  const bool seq = mode == MRL_SCAN_SEQUENTIAL ||
+                   (mode == MRL_SCAN_AUTO && (B >= 32768 || T < 64 || T * B < (1 << 18)));
+  if (seq) {
+    vtrace_seq_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(V);
+    MRL_LAUNCHED();
+    return MRL_OK;
+  }
+  const size_t f = ((size_t)T * B * 4 + 255) / 256 * 256;
+  uint8_t *sc;
+  int rc = scratch(3 * f, &sc, st);
+  if (rc) return rc;
+  float *a = (float *)sc, *b = (float *)(sc + f), *acc = (float *)(sc + 2 * f);
+  int64_t ctas = (T * B + 1023) / 1024;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  ctas = ctas > cap ? cap : ctas;
+  vtrace_prep_kernel<<<(unsigned)ctas, 256, 0, st>>>(V, a, b);
+  MRL_LAUNCHED();
+  ScanArgs A{};
+  A.a = a, A.v = b, A.last = nullptr, A.out = acc;
+  A.T = T, A.B = B, A.E = 1, A.N = B;
+  rc = launch_scan<OP_AFFINE>(A, MRL_TIME_MAJOR, MRL_SCAN_PARALLEL, st);
+  if (rc) return rc;
+  vtrace_post_kernel<<<(unsigned)ctas, 256, 0, st>>>(V, acc);
   MRL_LAUNCHED();
   return MRL_OK;
 }
 
+// ---- TD(lambda) targets of COMA ---------------------------------------------------------------
+// build_td_lambda_targets (mindspore_rl/algorithm/coma/coma.py:489-501), batch-major:
+//   ret[:, t] = (td_lambda*gamma) * ret[:, t+1]
+//               + mask[:, t] * (rewards[:, t] + ((1-td_lambda)*gamma) * target_qs[:, t+1] * (1 - terminated[:, t]))
+// t = max_t-1 .. 0 on a zero-initialised ret shaped like target_qs [B, Tq, A] (Tq > max_t); rewards, terminated,
+// mask are [B, Tr, RA] with RA = 1 (broadcast over the A agents) or A.  Episodes x agents is a few hundred
+// rows of <= a few hundred steps: one thread per (episode, agent) row walks it in the reference's operation
+// order (bit-identical), adjacent threads = adjacent agents (coalesced).
+namespace mrl {
+__global__ void __launch_bounds__(128)
+    td_lambda_kernel(const float *__restrict__ rewards, const float *__restrict__ terminated,
+                     const float *__restrict__ mask, const float *__restrict__ q, float *__restrict__ ret,
+                     int64_t B, int64_t Tq, int64_t Tr, int64_t A, int64_t RA, int64_t max_t, float lg, float bg) {
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= B * A) return;
+  const int64_t b = row / A, a = row - b * A;
+  const float *qr = q + b * Tq * A + a;
+  float *rr = ret + b * Tq * A + a;
+  const int64_t ra = RA == 1 ? 0 : a;
+  for (int64_t t = max_t; t < Tq; ++t) rr[t * A] = 0.0f;  // zeros_like(target_qs) beyond the recurrence
+  float x = 0.0f;
+  for (int64_t t = max_t - 1; t >= 0; --t) {
+    const int64_t i = (b * Tr + t) * RA + ra;
+    const float boot = __fmul_rn(__fmul_rn(bg, qr[(t + 1) * A]), __fsub_rn(1.0f, terminated[i]));
+    x = __fadd_rn(__fmul_rn(lg, x), __fmul_rn(mask[i], __fadd_rn(rewards[i], boot)));
+    rr[t * A] = x;
+  }
+}
+}  // namespace mrl
+
+extern "C" int mrl_td_lambda(const float *rewards, const float *terminated, const float *mask,
+                             const float *target_qs, float *ret, int64_t B, int64_t Tq, int64_t Tr, int64_t A,
+                             int64_t RA, int64_t max_t, float lambda_gamma, float bootstrap_gamma, void *stream) {
+  MRL_REQUIRE(B >= 0 && Tq >= 1 && Tr >= 0 && A >= 1 && (RA == 1 || RA == A), "mrl_td_lambda: bad shape");
+  MRL_REQUIRE(max_t >= 0 && max_t < Tq && max_t <= Tr, "mrl_td_lambda: need max_t < Tq and max_t <= Tr");
+  if (B == 0) return MRL_OK;
+  MRL_REQUIRE(rewards && terminated && mask && target_qs && ret, "mrl_td_lambda: NULL argument");
+  td_lambda_kernel<<<(unsigned)((B * A + 127) / 128), 128, 0, as_stream(stream)>>>(
+      rewards, terminated, mask, target_qs, ret, B, Tq, Tr, A, RA, max_t, lambda_gamma, bootstrap_gamma);
+  MRL_LAUNCHED();
+  return MRL_OK;
+}
 
 // ---- host arrays in, host arrays out: chunked along the batch axis and pipelined ------------------------
 // The scans are independent per column, so a [T,B] / [B,T] problem that lives in host memory is cut into
@@ -1298,8 +1595,12 @@ static int scan_host_pipelined(const HostScan &H, cudaStream_t st, Launch launch
   const size_t f = up256((size_t)T * Bc * E * 4), fd = up256((size_t)T * Bc), fl = up256((size_t)Bc * E * 4);
   const size_t o_a = 0, o_v = f, o_nv = 2 * f, o_out = 3 * f, o_ret = 4 * f, o_d = 5 * f, o_l = o_d + fd;
   const size_t piece = o_l + fl;
+  // one host scan at a time per process: the copy streams and events below are shared (the call is
+  // synchronous anyway)
+  static std::mutex host_mu;
+  std::lock_guard<std::mutex> host_guard(host_mu);
   uint8_t *s;
-  int rc = scratch(piece * (size_t)K, &s);
+  int rc = scratch(piece * (size_t)K, &s, st);
   if (rc) return rc;
   static cudaStream_t s_in = nullptr, s_out = nullptr;
   static cudaEvent_t ev_in[16], ev_k[16], ev_start = nullptr, ev_done = nullptr;

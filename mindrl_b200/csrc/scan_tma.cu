@@ -195,6 +195,9 @@ __global__ void __launch_bounds__((NG * kWarps + 1) * 32)
     else X = l;
   }
   const bool want_ret = OP == OP_GAE && A.ret != nullptr;
+  const bool mom = NG == 1 && A.mom != nullptr;  // moments of `out` for the normalisation that follows
+  const bool colok = col < A.N;
+  double msum = 0.0, msq = 0.0;
   float *my_out = ostage + warp * (n_obufs * C::kNOut * C::kWarpOut);
   int s = grp;  // (n_stages >= 2 >= NG)
   uint32_t ph = 0;
@@ -292,6 +295,11 @@ __global__ void __launch_bounds__((NG * kWarps + 1) * 32)
       x = fstep(ea[i], eb[i], x);
       oa[(h * RPU + i) * COLS + c] = x;
       if (want_ret) oa[C::kWarpOut + (h * RPU + i) * COLS + c] = __fadd_rn(x, aux[i]);
+      if (mom && colok && (k > 0 || (n_tiles - 1) * C::kRows + unit * RPU + i < T)) {
+        const double xd = (double)x;
+        msum += xd;
+        msq = fma(xd, xd, msq);
+      }
     }
     fence_async_smem();
     __syncwarp();
@@ -305,6 +313,22 @@ __global__ void __launch_bounds__((NG * kWarps + 1) * 32)
     }
     s += NG;
     if (s >= n_stages) s -= n_stages, ph ^= 1u;
+  }
+  if (NG == 1 && mom) {  // fixed-order fold: lanes, then the 8 warps in order -> one partial per CTA
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+      msum += __shfl_xor_sync(0xffffffffu, msum, off);
+      msq += __shfl_xor_sync(0xffffffffu, msq, off);
+    }
+    double2 *red = reinterpret_cast<double2 *>(comp);
+    consumer_barrier<1>();  // every warp has read its last maps
+    if (lane == 0) red[warp] = make_double2(msum, msq);
+    consumer_barrier<1>();
+    if (warp == 0 && lane == 0) {
+      double a = 0.0, b = 0.0;
+      for (int w = 0; w < kWarps; ++w) a += red[w].x, b += red[w].y;
+      A.mom[blockIdx.x] = make_double2(a, b);
+    }
   }
   if (lane == 0) bulk_wait_all();
 }
@@ -358,7 +382,7 @@ bool make_map(CUtensorMap *m, const void *base, bool is_u8, int64_t rows, int64_
 bool al16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 template <int OP, bool HD, int COLS, int RPU, int NG>
-int strip_launch(const ScanArgs &A, cudaStream_t st) {
+int strip_launch(ScanArgs A, cudaStream_t st, int *mom_parts) {
   using C = StripCfg<OP, HD, COLS, RPU, NG>;
   static_assert(C::kRows <= 256 && C::smem_bytes(2, 1) <= (NG == 1 && RPU <= 16 ? 111 : 225) * 1024, "tile too large");
   CUtensorMap ma, mv, mv1, md, mo, mr;
@@ -371,16 +395,14 @@ int strip_launch(const ScanArgs &A, cudaStream_t st) {
   mr = mo;
   if (OP == OP_GAE && A.ret && !make_map(&mr, A.ret, false, A.T, A.N, COLS, C::kWarpRows))
     return kScanNotApplicable;
-  static bool configured = false;
-  if (!configured) {
+  if (first_use_on_device((const void *)scan_tm_strip_kernel<OP, HD, COLS, RPU, NG>))
     MRL_CUDA(cudaFuncSetAttribute(scan_tm_strip_kernel<OP, HD, COLS, RPU, NG>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    configured = true;
-  }
   const int64_t n_strips = (A.N + COLS - 1) / COLS;
+  if (NG != 1 || n_strips > kMomentSlots) A.mom = nullptr;
   const int n_tiles = (int)((A.T + C::kRows - 1) / C::kRows);
-  if (RPU > 16 && n_strips > kNumSM) return kScanNotApplicable;  // 256-step tiles need the whole SM
-  const int budget = ((NG == 2 || n_strips <= kNumSM) ? 226 : 112) * 1024 - 1024;
+  if (RPU > 16 && n_strips > sm_count()) return kScanNotApplicable;  // 256-step tiles need the whole SM
+  const int budget = ((NG == 2 || n_strips <= sm_count()) ? 226 : 112) * 1024 - 1024;
   int obufs = 2, stages = (budget - C::smem_bytes(0, 2)) / C::kStage;
   if (stages < 3) obufs = 1, stages = (budget - C::smem_bytes(0, 1)) / C::kStage;
   stages = stages > kMaxStages ? kMaxStages : stages;
@@ -388,22 +410,23 @@ int strip_launch(const ScanArgs &A, cudaStream_t st) {
   if (g_strip_stages > 0 && g_strip_stages < stages) stages = (int)(g_strip_stages < 2 ? 2 : g_strip_stages);
   scan_tm_strip_kernel<OP, HD, COLS, RPU, NG><<<(unsigned)n_strips, C::kThreads, C::smem_bytes(stages, obufs), st>>>(
       ma, mv, mv1, md, mo, mr, A, n_tiles, stages, obufs);
+  if (mom_parts) *mom_parts = A.mom ? (int)n_strips : 0;
   return MRL_OK;
 }
 
 template <int OP, bool HD>
-int strip_launch_cols(const ScanArgs &A, int cols, int rpu, cudaStream_t st) {
+int strip_launch_cols(const ScanArgs &A, int cols, int rpu, cudaStream_t st, int *mp) {
   // two consumer groups per CTA: opt-in (measured equal to one group at 4096 x 2048: once the ring is
   // deep enough the strips are bound by HBM, not by the consumers' dependent chain)
-  const bool two = g_strip_groups == 2;
-  if (cols == 32 && rpu == 16 && two) return strip_launch<OP, HD, 32, 16, 2>(A, st);
+  const bool two = g_strip_groups == 2 && !A.mom;
+  if (cols == 32 && rpu == 16 && two) return strip_launch<OP, HD, 32, 16, 2>(A, st, mp);
   if (cols == 32 && rpu == 32) {
-    const int rc = strip_launch<OP, HD, 32, 32, 1>(A, st);
+    const int rc = strip_launch<OP, HD, 32, 32, 1>(A, st, mp);
     if (rc != kScanNotApplicable) return rc;
     rpu = 16;
   }
-  if (cols == 16) return rpu == 16 ? strip_launch<OP, HD, 16, 16, 1>(A, st) : strip_launch<OP, HD, 16, 8, 1>(A, st);
-  return rpu == 16 ? strip_launch<OP, HD, 32, 16, 1>(A, st) : strip_launch<OP, HD, 32, 8, 1>(A, st);
+  if (cols == 16) return rpu == 16 ? strip_launch<OP, HD, 16, 16, 1>(A, st, mp) : strip_launch<OP, HD, 16, 8, 1>(A, st, mp);
+  return rpu == 16 ? strip_launch<OP, HD, 32, 16, 1>(A, st, mp) : strip_launch<OP, HD, 32, 8, 1>(A, st, mp);
 }
 
 }  // namespace
@@ -414,7 +437,8 @@ int64_t g_strip_min_cols = 2048;  // auto: narrower batches keep the look-back k
 
 // Time-major [T, N], E == 1.  Needs 16-byte aligned bases and row pitches (N % 4 == 0; N % 16 == 0 with
 // done flags): the tensor maps address rows by pitch.
-int scan_tm_strip_launch(const ScanArgs &A, int op, bool force, cudaStream_t st) {
+int scan_tm_strip_launch(const ScanArgs &A, int op, bool force, cudaStream_t st, int *mom_parts) {
+  if (mom_parts) *mom_parts = 0;
   if (A.E != 1 || (op == OP_GAE && A.nv)) return kScanNotApplicable;
   if (A.T >= (1LL << 31) - 256 || A.N >= (1LL << 31) - 64 || A.N % 4 != 0) return kScanNotApplicable;
   if (!al16(A.a) || !al16(A.out) || (op != OP_DR && !al16(A.v)) || (A.ret && !al16(A.ret)))
@@ -429,11 +453,12 @@ int scan_tm_strip_launch(const ScanArgs &A, int op, bool force, cudaStream_t st)
   // 22.6 -> 20.6 us for GAE without returns at 4096 x 2048; GAE with both outputs is HBM-bound either
   // way and keeps the deeper ring of the 128-step tiles.  (Falls back to 16 when the strips do not get an SM each.)
   if (rpu == 0) rpu = (op == OP_GAE && A.ret) ? 16 : 32;
+  int *mp = mom_parts;
   if (op == OP_DR)
-    return hd ? strip_launch_cols<OP_DR, true>(A, cols, rpu, st) : strip_launch_cols<OP_DR, false>(A, cols, rpu, st);
+    return hd ? strip_launch_cols<OP_DR, true>(A, cols, rpu, st, mp) : strip_launch_cols<OP_DR, false>(A, cols, rpu, st, mp);
   if (op == OP_GAE)
-    return hd ? strip_launch_cols<OP_GAE, true>(A, cols, rpu, st) : strip_launch_cols<OP_GAE, false>(A, cols, rpu, st);
-  return strip_launch_cols<OP_AFFINE, false>(A, cols, rpu, st);
+    return hd ? strip_launch_cols<OP_GAE, true>(A, cols, rpu, st, mp) : strip_launch_cols<OP_GAE, false>(A, cols, rpu, st, mp);
+  return strip_launch_cols<OP_AFFINE, false>(A, cols, rpu, st, mp);
 }
 
 // =============================================================================================
@@ -519,6 +544,8 @@ __global__ void __launch_bounds__(kThreads)
   // warp w owns positions [256w, 256w+256) of the tile, lane l the 8 consecutive steps 256w+8l..+7
   constexpr unsigned FULL = 0xffffffffu;
   const bool want_ret = OP == OP_GAE && A.ret != nullptr;
+  const bool mom = A.mom != nullptr;  // moments of `out` for the normalisation that follows
+  double msum = 0.0, msq = 0.0;
   const bool use_last = A.last != nullptr && !(OP == OP_GAE && NVF);
   float *my_out = ostage + warp * (2 * C::kNOut * C::kWarpOut);
   float X = 0.0f, v_after = 0.0f;
@@ -643,6 +670,15 @@ __global__ void __launch_bounds__(kThreads)
         o[q] = xe;
         o2[q] = __fadd_rn(xe, aux[q]);
       }
+      if (mom) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (p0 + q < len) {
+            const double xd = (double)o[q];
+            msum += xd;
+            msq = fma(xd, xd, msq);
+          }
+      }
       float4 *dst = reinterpret_cast<float4 *>(oa + 8 * lane);
       dst[0] = make_float4(o[0], o[1], o[2], o[3]);
       dst[1] = make_float4(o[4], o[5], o[6], o[7]);
@@ -667,18 +703,31 @@ __global__ void __launch_bounds__(kThreads)
     if (++c == n_chunks) c = 0, row += G;
     if (++s == n_stages) s = 0, ph ^= 1u;
   }
+  if (mom) {  // fixed-order fold: lanes, then the 8 warps in order -> one partial per CTA
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+      msum += __shfl_xor_sync(FULL, msum, off);
+      msq += __shfl_xor_sync(FULL, msq, off);
+    }
+    double2 *red = reinterpret_cast<double2 *>(comp);
+    consumer_barrier();  // every warp has read its last maps
+    if (lane == 0) red[warp] = make_double2(msum, msq);
+    consumer_barrier();
+    if (warp == 0 && lane == 0) {
+      double a = 0.0, b = 0.0;
+      for (int w = 0; w < kWarps; ++w) a += red[w].x, b += red[w].y;
+      A.mom[blockIdx.x] = make_double2(a, b);
+    }
+  }
   if (lane == 0) bulk_wait_all();
 }
 
 template <int OP, bool HD, bool NVF>
-int row_launch(const ScanArgs &A, cudaStream_t st) {
+int row_launch(const ScanArgs &A, cudaStream_t st, int *mom_parts) {
   using C = RowCfg<OP, HD, NVF>;
-  static bool configured = false;
-  if (!configured) {
+  if (first_use_on_device((const void *)scan_bm_row_kernel<OP, HD, NVF>))
     MRL_CUDA(cudaFuncSetAttribute(scan_bm_row_kernel<OP, HD, NVF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   C::smem_bytes(kMaxStages) < 226 * 1024 ? C::smem_bytes(kMaxStages) : 226 * 1024));
-    configured = true;
-  }
   const int n_chunks = (int)((A.T + BM_L - 1) / BM_L);
   // ring depth: the SM's shared memory split between g_row_ctas_per_sm resident CTAs
   const int per_sm = (int)g_row_ctas_per_sm;
@@ -689,10 +738,11 @@ int row_launch(const ScanArgs &A, cudaStream_t st) {
   // as many CTAs as fit at once, trimmed so that every CTA gets the same number of rows
   int fit = (227 * 1024) / (smem + 1024);
   fit = fit > 7 ? 7 : (fit < 1 ? 1 : fit);  // 2048 threads per SM / 288
-  const int64_t max_ctas = (int64_t)kNumSM * fit;
+  const int64_t max_ctas = (int64_t)sm_count() * fit;
   const int64_t per = (A.N + max_ctas - 1) / max_ctas;
   const int64_t ctas = (A.N + per - 1) / per;
   scan_bm_row_kernel<OP, HD, NVF><<<(unsigned)ctas, kThreads, smem, st>>>(A, n_chunks, stages);
+  if (mom_parts) *mom_parts = A.mom ? (int)ctas : 0;  // (ctas <= 7 * SMs < kMomentSlots)
   return MRL_OK;
 }
 
@@ -701,7 +751,9 @@ int row_launch(const ScanArgs &A, cudaStream_t st) {
 int64_t g_row_min_t = 512;
 
 // Batch-major [N, T].  Bulk copies need 16-byte aligned row starts: T % 4 == 0 (T % 16 == 0 with done).
-int scan_bm_row_launch(const ScanArgs &A, int op, bool force, cudaStream_t st) {
+int scan_bm_row_launch(const ScanArgs &A, int op, bool force, cudaStream_t st, int *mom_parts) {
+  if (mom_parts) *mom_parts = 0;
+  int *mp = mom_parts;
   if (A.T % 4 != 0 || A.T >= (1LL << 40)) return kScanNotApplicable;
   if (!al16(A.a) || !al16(A.out) || (op != OP_DR && !al16(A.v)) || (A.ret && !al16(A.ret)) ||
       (A.nv && !al16(A.nv)))
@@ -709,10 +761,10 @@ int scan_bm_row_launch(const ScanArgs &A, int op, bool force, cudaStream_t st) {
   const bool hd = op != OP_AFFINE && A.done != nullptr;
   if (hd && (A.T % 16 != 0 || !al16(A.done))) return kScanNotApplicable;
   if (!force && (A.T < g_row_min_t || A.N * A.T < (1 << 20))) return kScanNotApplicable;
-  if (op == OP_DR) return hd ? row_launch<OP_DR, true, false>(A, st) : row_launch<OP_DR, false, false>(A, st);
-  if (op == OP_AFFINE) return row_launch<OP_AFFINE, false, false>(A, st);
-  if (A.nv) return hd ? row_launch<OP_GAE, true, true>(A, st) : row_launch<OP_GAE, false, true>(A, st);
-  return hd ? row_launch<OP_GAE, true, false>(A, st) : row_launch<OP_GAE, false, false>(A, st);
+  if (op == OP_DR) return hd ? row_launch<OP_DR, true, false>(A, st, mp) : row_launch<OP_DR, false, false>(A, st, mp);
+  if (op == OP_AFFINE) return row_launch<OP_AFFINE, false, false>(A, st, mp);
+  if (A.nv) return hd ? row_launch<OP_GAE, true, true>(A, st, mp) : row_launch<OP_GAE, false, true>(A, st, mp);
+  return hd ? row_launch<OP_GAE, true, false>(A, st, mp) : row_launch<OP_GAE, false, false>(A, st, mp);
 }
 
 }  // namespace mrl

@@ -35,6 +35,9 @@ def _prep(x, dtype, kind):
 
 
 def _done_u8(done, kind):
+    """done flags as uint8.  Any non-zero value counts as "done" (the reference computes (1 - done) in float,
+    discounted_return.py:88; its callers only pass booleans / 0-1 masks, which is what this path supports --
+    fractional masks belong to affine_scan, whose b[t] is arbitrary)."""
     if done is None:
         return None, None
     if kind == "device":
@@ -145,13 +148,15 @@ def discounted_reward(rewards, gamma, last_value=None, done=None, layout="batch_
 
 
 def gae(reward, value, gamma, lam, next_value=None, last_value=None, done=None,
-        layout="time_major", mode="auto", want_returns=True):
+        layout="time_major", mode="auto", want_returns=True, normalize=False, epsilon=1e-8):
     """Generalised advantage estimation.
 
       m = 1 - done;  delta = r + gamma * V' * m - V;  adv = delta + gamma*lam * m * adv';  ret = adv + V
     PPO form (ppo.py:334-350): next_value = critic(next_state), done=None, layout='batch_major'.
     MAPPO form (mappo.py:478-497): value[t+1] with last_value as bootstrap, done = 1 - mask,
-    layout='time_major'.  Returns (advantage, returns or None)."""
+    layout='time_major'.  Returns (advantage, returns or None).
+    normalize=True (device arrays): the advantages come back as (adv - mean) / (sqrt(var) + epsilon), PPO's
+    _normalized_advantage (ppo.py:361-368), with the moments accumulated by the scan kernel itself."""
     kind = _kind(reward, value, next_value, last_value, done)
     r, r_ptr = _prep(reward, np.float32, kind)
     v, v_ptr = _prep(value, np.float32, kind)
@@ -167,6 +172,13 @@ def gae(reward, value, gamma, lam, next_value=None, last_value=None, done=None,
         raise ValueError("value must have the shape of reward (pass V[T] as last_value)")
     adv = _empty_like(r, kind)
     ret = _empty_like(r, kind) if want_returns else None
+    if normalize:
+        if kind != "device":
+            raise TypeError("gae(normalize=True) takes device arrays")
+        _ffi.check(_ffi.lib().mrl_gae_normalized(
+            r_ptr, v_ptr, nv_ptr, lv_ptr, d_ptr, adv.data_ptr(), None if ret is None else ret.data_ptr(), T, B,
+            float(gamma), float(lam), float(epsilon), lay, _MODES[mode], K.current_stream()))
+        return adv, ret
     fn = _ffi.lib().mrl_gae if kind == "device" else _ffi.lib().mrl_gae_host
     _ffi.check(fn(r_ptr, v_ptr, nv_ptr, lv_ptr, d_ptr, _out_ptr(adv, kind),
                   None if ret is None else _out_ptr(ret, kind), T, B, float(gamma), float(lam), lay,
@@ -203,3 +215,57 @@ def normalize_advantage(advantage, epsilon=1e-8):
     _ffi.check(_ffi.lib().mrl_normalize(x_ptr, out.data_ptr(), _prod(x.shape), float(epsilon),
                                         K.current_stream()))
     return out
+
+
+def discounted_return_normalized(reward, done, last_state_value, gamma, epsilon=1e-8, mode="auto"):
+    """A2C's returns + normalisation (a2c.py:189-192) as one operation on device arrays:
+    DiscountedReturn(gamma)(reward, done, last) followed by (x - mean) / (sqrt(var) + epsilon)."""
+    if gamma > 1.0 or gamma < 0.0:
+        raise ValueError(f"The discounted factor should be a number in range [0, 1], but got {gamma}.")
+    if _kind(reward, done, last_state_value) != "device":
+        raise TypeError("discounted_return_normalized takes device arrays")
+    r, r_ptr = _prep(reward, np.float32, "device")
+    T, B = int(r.shape[0]), _prod(r.shape[1:])
+    d, d_ptr = _done_u8(done, "device")
+    lv, lv_ptr = _prep(last_state_value, np.float32, "device")
+    out = _empty_like(r, "device")
+    _ffi.check(_ffi.lib().mrl_discounted_return_normalized(
+        r_ptr, d_ptr, lv_ptr, out.data_ptr(), T, B, 1, float(gamma), float(epsilon), _ffi.TIME_MAJOR,
+        _MODES[mode], K.current_stream()))
+    return out
+
+
+def td_lambda_targets(rewards, terminated, mask, target_qs, gamma, td_lambda, max_t=None):
+    """COMA's build_td_lambda_targets (mindspore_rl/algorithm/coma/coma.py:489-501), batch-major:
+
+        ret[:, t] = td_lambda * gamma * ret[:, t + 1]
+                    + mask[:, t] * (rewards[:, t] + (1 - td_lambda) * gamma * target_qs[:, t + 1] * (1 - terminated[:, t]))
+
+    for t = max_t - 1 .. 0 on ret = zeros_like(target_qs).  target_qs is [B, Tq, A] (A agents, Tq > max_t);
+    rewards, terminated, mask are [B, Tr, 1] (broadcast over the agents), [B, Tr] or [B, Tr, A].  max_t defaults
+    to Tq - 1.  Device arrays in, device array shaped like target_qs out; the whole loop is one kernel of the
+    library (mrl_td_lambda) in the reference's operation order, so results are bit-identical."""
+    if _kind(rewards, terminated, mask, target_qs) != "device":
+        raise TypeError("td_lambda_targets takes device arrays")
+    q, q_ptr = _prep(target_qs, np.float32, "device")
+    qshape = tuple(q.shape)
+    if len(qshape) < 2:
+        raise ValueError("target_qs needs [batch, time, ...]")
+    Bn, Tq = int(qshape[0]), int(qshape[1])
+    A = _prod(qshape[2:])
+    r, r_ptr = _prep(rewards, np.float32, "device")
+    te, te_ptr = _prep(terminated, np.float32, "device")
+    m, m_ptr = _prep(mask, np.float32, "device")
+    Tr = int(r.shape[1])
+    RA = _prod(r.shape[2:])
+    for x in (te, m):
+        if tuple(x.shape[:2]) != (Bn, Tr) or _prod(x.shape[2:]) != RA:
+            raise ValueError("rewards, terminated and mask must share one shape")
+    if int(r.shape[0]) != Bn or RA not in (1, A):
+        raise ValueError("rewards must be [batch, time, 1] or [batch, time, agents]")
+    max_t = Tq - 1 if max_t is None else int(max_t)
+    ret = _empty_like(q, "device")
+    _ffi.check(_ffi.lib().mrl_td_lambda(r_ptr, te_ptr, m_ptr, q_ptr, ret.data_ptr(), Bn, Tq, Tr, A, RA, max_t,
+                                        float(td_lambda * gamma), float((1 - td_lambda) * gamma),
+                                        K.current_stream()))
+    return ret

@@ -1,40 +1,44 @@
-"""V-trace targets (IMPALA) with the reverse recurrence on the scan kernels.
+"""V-trace targets (IMPALA) on the CUDA library.
 
 Same signature and return values as mindspore_rl/algorithm/impala/vtrace.py:48-108
-(get_vs_and_advantages).  The element-wise parts (exp, clipping, deltas) stay tensor ops of the
-carrier (torch on the GPU); the sequential loop of the reference (vtrace.py:84-93)
-
-    acc = delta_t + discount_t * c_t * acc * mask_t,   t = T-1 .. 0
-
-is one call of mrl_affine_scan with a = delta, b = discount * c * mask.
+(get_vs_and_advantages).  Everything -- exp and the three clips (:79-82), the deltas (:84-86), the
+reverse recurrence (:88-93), vs (:99) and the policy-gradient advantages (:103-105) -- runs inside
+mrl_vtrace (csrc/scan.cu): one kernel for IMPALA-sized unrolls, three passes for long narrow
+trajectories.  PyTorch only carries the device memory.
 """
+import math
+
+import numpy as np
+
 from .. import _carrier as K
-from .discounted_return import affine_scan
+from .. import _ffi
+from .discounted_return import _MODES
 
 
 def get_vs_and_advantages(log_rhos, discounts, rewards, values, bootstrap_value,
                           clip_rho_threshold, clip_pg_threshold, clip_cs_threshold, masks,
                           mode="auto"):
-    """All inputs time-major [T, B] CUDA tensors (bootstrap_value [B]).  Returns (vs, pg_advantages)."""
-    torch = K.torch
-    if torch is None or not all(K.is_torch(x) and x.is_cuda for x in
-                                (log_rhos, discounts, rewards, values, bootstrap_value, masks)):
-        raise TypeError("get_vs_and_advantages takes torch CUDA tensors")
-    f32 = torch.float32
-    log_rhos, discounts, rewards, values, masks = (x.to(f32) for x in (log_rhos, discounts, rewards, values, masks))
-    bootstrap_value = bootstrap_value.to(f32)
-    rhos = torch.exp(log_rhos)                                                     # :79
-    if clip_rho_threshold is not None:
-        rhos = torch.minimum(rhos, torch.tensor(clip_rho_threshold, dtype=f32, device=rhos.device))
-    cs = rhos if clip_cs_threshold is None else torch.minimum(
-        rhos, torch.tensor(clip_cs_threshold, dtype=f32, device=rhos.device))      # :81
-    pg_rhos = rhos if clip_pg_threshold is None else torch.minimum(
-        rhos, torch.tensor(clip_pg_threshold, dtype=f32, device=rhos.device))      # :82
-    values_1 = torch.cat([values[1:], bootstrap_value.unsqueeze(0)], 0)            # :84
-    deltas = rhos * (rewards + discounts * values_1 - values)                      # :86
-    b = discounts * cs * masks                                                     # :91 (masks are 0/1)
-    vs_minus_v_xs = affine_scan(deltas.contiguous(), b.contiguous(), None, layout="time_major", mode=mode)
-    vs = vs_minus_v_xs + values                                                    # :99
-    target_v_1 = torch.cat([vs[1:], bootstrap_value.unsqueeze(0)], 0)              # :103
-    pg_advantage = pg_rhos * (rewards + discounts * target_v_1 - values)           # :105
-    return vs, pg_advantage
+    """All inputs time-major [T, B] device arrays (bootstrap_value [B]); a threshold of None disables
+    that clip; masks may be None (= 1).  Returns (vs, pg_advantages)."""
+    xs = (log_rhos, discounts, rewards, values, bootstrap_value) + (() if masks is None else (masks,))
+    if not all(K.classify(x) == "device" for x in xs):
+        raise TypeError("get_vs_and_advantages takes device arrays")
+    lr, d, r, v, bv = (K.as_device(x, np.float32) for x in (log_rhos, discounts, rewards, values, bootstrap_value))
+    m = None if masks is None else K.as_device(masks, np.float32)
+    T = int(lr.shape[0])
+    B = int(np.prod(lr.shape[1:], dtype=np.int64))
+    for name, x in (("discounts", d), ("rewards", r), ("values", v)) + ((("masks", m),) if m is not None else ()):
+        if int(np.prod(x.shape, dtype=np.int64)) != T * B:
+            raise ValueError(f"{name} must have the shape of log_rhos")
+    if int(np.prod(bv.shape, dtype=np.int64)) != B:
+        raise ValueError("bootstrap_value must have the shape of log_rhos[0]")
+    vs = K.device_empty(tuple(lr.shape), np.float32)
+    pg = K.device_empty(tuple(lr.shape), np.float32)
+    inf = math.inf
+    _ffi.check(_ffi.lib().mrl_vtrace(
+        lr.data_ptr(), d.data_ptr(), r.data_ptr(), v.data_ptr(), bv.data_ptr(), None if m is None else m.data_ptr(),
+        inf if clip_rho_threshold is None else float(clip_rho_threshold),
+        inf if clip_pg_threshold is None else float(clip_pg_threshold),
+        inf if clip_cs_threshold is None else float(clip_cs_threshold),
+        vs.data_ptr(), pg.data_ptr(), T, B, _MODES[mode], K.current_stream()))
+    return vs, pg

@@ -303,7 +303,7 @@ static int64_t orc_tree_descend(const orc_prb *b, float mass) {
 static int orc_prb_sample_impl(orc_prb *b, int64_t n, float beta, const float *uniforms,
                                const float *gstats, int32_t world, int64_t *indices,
                                float *weights, void *const *out_cols) {
-  if (n <= 0) return 1;
+  if (n <= 0 || b->size <= 0) return 1; /* nothing to sample from */
   const float root_sum = b->sum[1];
   float w_sum = root_sum, w_min = b->mn[1], w_size = (float)b->size;
   if (gstats) {
@@ -321,14 +321,16 @@ static int orc_prb_sample_impl(orc_prb *b, int64_t n, float beta, const float *u
   for (int64_t i = 0; i < n; ++i) {
     const float u = uniforms ? uniforms[i] : mrl_uniform01(b->seed, b->ctr + (uint64_t)i);
     const float mass = (u + (float)i) * seg;
-    const int64_t leaf = orc_tree_descend(b, mass);
+    int64_t leaf = orc_tree_descend(b, mass);
+    /* a mass that rounds past the total walks into the empty part of the tree (leaves >= size,
+     * priority 0): the newest valid leaf is returned instead, so that index, weight and row
+     * belong together (decision of this oracle, documented in DESIGN.md section 3) */
+    if (leaf >= b->size) leaf = b->size - 1;
     indices[i] = leaf;
     const float p = b->sum[leaf + b->cap2];
     weights[i] = mrl_is_weight(p, w_sum, w_size, beta) / max_w;
     if (out_cols) {
-      /* a mass that rounds past the total lands on an empty leaf; leaves >= capacity have no
-       * row: read the last row instead (documented in DESIGN.md) */
-      const int64_t slot = leaf < b->capacity ? leaf : b->capacity - 1;
+      const int64_t slot = leaf;
       for (int c = 0; c < b->ncols; ++c) {
         const int64_t rb = b->row_bytes[c];
         memcpy((uint8_t *)out_cols[c] + i * rb, b->cols[c] + slot * rb, (size_t)rb);
