@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- throughput of the experience data path on B200 (contract in the task statement).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--only c2|c3|c4]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--only c1|c2|c3|c4|c5|insert]
 
 Headline workload (BASELINE.json configs[1], "C2"): PriorityReplayBuffer, capacity 1M (2^20 leaves),
 40-byte rows (obs 4xf32, action i32, reward f32, next obs 4xf32), batch 256, alpha 0.6, beta 0.4.
@@ -11,9 +11,17 @@ One step = sample(256) followed by update_priorities(256 fresh priorities).  met
   e2e       the same step through the C ABI's *_host entry points with pinned HOST buffers
             (H2D of indices+priorities, D2H of indices, weights and rows inside the timed region)
   roofline  dominant kernel of the step against the measured HBM copy bandwidth
-  cpu_baseline  the CPU oracle (port of the reference's sequential algorithm) on one host core
-  also      BASELINE configs[2] (Atari-shaped PER, gather-bound) and configs[3] (GAE 4096x2048),
-            each with its own value / e2e / roofline / cpu_baseline (N=1 only)
+  cpu_baseline  the CPU oracle (port of the reference's sequential algorithm) on one host core, the loop
+            timed inside the C library
+  parity_check  BEFORE the timed loops, every rank runs sample+update steps with injected uniforms on the very
+            path that is timed next (sharded exchange included) against the CPU oracle: indices, weight bits,
+            rows, whole tree.  A mismatch ends the run non-zero.
+  exchange  (N > 1) the peer-mailbox exchange of the root statistics: protocol, exchange_wait_us per sample
+  c5        BASELINE configs[4] at THIS N (N = 1: one shard at batch 4096), and at N > 1 the same step un-sharded
+            in the same run with the resulting weak-scaling efficiency
+  also      BASELINE configs[2] (Atari-shaped PER, gather-bound), configs[3] (GAE 4096x2048, with the
+            element-wise error histogram of the parallel kernels), configs[0] (DQN-shaped uniform buffer)
+            and bulk insert, each with its own value / e2e / roofline / cpu_baseline
 
 L2 hygiene: before EVERY timed iteration a 256 MiB buffer is overwritten and a second 256 MiB buffer
 is read (not timed; the read leaves the L2 full of clean lines, so the timed kernels do not pay for
@@ -137,8 +145,7 @@ class Ctx:
         self.local_rank = int(os.environ.get("LOCAL_RANK", 0))
         if self.world > 1:
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-            # keep stdout to the one JSON line (NCCL prints its version banner there at VERSION/INFO)
-            os.environ["NCCL_DEBUG"] = os.environ.get("MRL_NCCL_DEBUG", "WARN")
+            # (NCCL_DEBUG is left as the caller set it: main() already sends everything but the JSON line to stderr)
         torch.cuda.set_device(self.local_rank)
         if self.world > 1:
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
@@ -245,15 +252,90 @@ def make_prb(ctx, capacity, rows, seed):
         e = min(capacity, s + 8192)
         ffi.check(L.mrl_prb_update(h.value, idx[s:e].data_ptr(), pr[s:e].data_ptr(), e - s, ctx.stream))
     torch.cuda.synchronize()
-    return h.value, cols
+    return h.value, cols, pr
 
 
-def bench_per(ctx, name, rows, batch, steps, warmup, primary):
-    """PER sample + update_priorities loop (C2 / C3 / per-rank shard of C5)"""
+def build_parity_oracle(ctx, capacity, rows, init_prio, batch):
+    """the CPU oracle holding what make_prb put into the GPU buffer: the same rows (the fill pattern is shared
+    arithmetic, include/mrl_arith.h) when they are narrow, 8-byte stand-in rows carrying the slot id when they are
+    Atari-sized (56 GB do not fit the host: those rows are checked through the slot id every row embeds)"""
+    from oracle import oracle as O
+    narrow = sum(rows) <= 512
+    orows = rows if narrow else [8]
+    o = O.PriorityBufferOracle(ALPHA, capacity, batch, [(r,) for r in orows], [np.uint8] * len(orows), 7, ctx.rank)
+    if narrow:
+        o.insert_batch([O.fill_rows(capacity, r, 1000 + 17 * ctx.rank + c) for c, r in enumerate(rows)])
+    else:
+        o.insert_batch([np.arange(capacity, dtype=np.int64).view(np.uint8).reshape(capacity, 8)])
+    o.update_priorities(np.arange(capacity), init_prio.cpu().numpy())
+    return o, narrow
+
+
+def parity_check(ctx, h, o, narrow, rows, batch, sample_fn, steps=4):
+    """BEFORE the timed loops: `steps` sample+update steps with injected uniforms on the GPU path this bench is
+    about to time (sharded exchange included) against the CPU oracle -- indices, weights (bit patterns), rows and,
+    at the end, the whole sum / min tree.  At N > 1 the oracle gets the global statistics from an all-gather of
+    every rank's root statistics (NCCL), i.e. independently of the peer mailboxes under test."""
+    torch, L, ffi = ctx.torch, ctx.L, ctx.ffi
+    st = ctx.stream
+    rng = np.random.default_rng(4242 + ctx.rank)
+    idx = torch.empty(batch, dtype=torch.int64, device="cuda")
+    w = torch.empty(batch, dtype=torch.float32, device="cuda")
+    outs = [torch.empty((batch, r), dtype=torch.uint8, device="cuda") for r in rows]
+    out_tab = ffi.ptr_table([x.data_ptr() for x in outs])
+    stats = torch.empty(4, dtype=torch.float32, device="cuda")
+    gstats = torch.empty((ctx.world, 4), dtype=torch.float32, device="cuda")
+    ok, detail = True, []
+    for k in range(steps):
+        u = rng.random(batch).astype(np.float32)
+        ud = torch.as_tensor(u).cuda()
+        g = None
+        if ctx.world > 1:
+            ffi.check(L.mrl_prb_root_stats(h, stats.data_ptr(), st))
+            ctx.dist.all_gather_into_tensor(gstats, stats)
+            g = gstats.cpu().numpy()
+        sample_fn(ud.data_ptr(), idx, w, out_tab)
+        want = o.sample(BETA, uniforms=u, gstats=g)
+        gi, gw = idx.cpu().numpy(), w.cpu().numpy()
+        step_ok = np.array_equal(gi, want[0]) and np.array_equal(gw.view(np.uint32), want[1].view(np.uint32))
+        if narrow:
+            step_ok = step_ok and all(np.array_equal(a.cpu().numpy(), b) for a, b in zip(outs, want[2:]))
+        else:  # every row starts with its slot id (mrl_fill_rows)
+            for a, r in zip(outs, rows):
+                if r >= 8:
+                    step_ok = step_ok and np.array_equal(a[:, :8].contiguous().cpu().numpy().view(np.int64).reshape(-1), gi)
+        pr = (np.abs(rng.normal(size=batch)) + 1e-3).astype(np.float32)
+        ffi.check(L.mrl_prb_update(h, idx.data_ptr(), torch.as_tensor(pr).cuda().data_ptr(), batch, st))
+        torch.cuda.synchronize()
+        o.update_priorities(want[0], pr)
+        ok = ok and bool(step_ok)
+        if not step_ok:
+            detail.append(f"step {k}: {int((gi != want[0]).sum())} indices, "
+                          f"{int((gw.view(np.uint32) != want[1].view(np.uint32)).sum())} weights differ")
+    cap2 = 1 << L_1M
+    gs, gm = np.empty(2 * cap2, np.float32), np.empty(2 * cap2, np.float32)
+    ffi.check(L.mrl_prb_tree_dump(h, gs.ctypes.data, gm.ctypes.data, st))
+    os_, om = o.tree()
+    tree_ok = np.array_equal(gs[1:], os_[1:]) and np.array_equal(gm[1:], om[1:])
+    ok = ok and bool(tree_ok)
+    if ctx.world > 1:
+        flag = torch.tensor([1 if ok else 0], device="cuda")
+        ctx.dist.all_reduce(flag, op=ctx.dist.ReduceOp.MIN)
+        ok = bool(flag.item() == 1)
+    return {"world": ctx.world, "steps": steps, "batch": batch, "ok": ok, "tree_bit_exact": bool(tree_ok),
+            "checked": "indices, weight bits, " + ("rows" if narrow else "slot id embedded in every wide row")
+                       + ", sum/min tree after the last update; oracle = CPU restatement, global statistics from "
+                         "an NCCL all-gather" + ("" if not detail else "; " + "; ".join(detail))}
+
+
+def bench_per(ctx, name, rows, batch, steps, warmup, primary, sharded=None, parity=True, details=True):
+    """PER sample + update_priorities loop (C2 / C3 / per-rank shard of C5).
+    sharded: None = follow the world size; False = every rank runs the un-sharded single-GPU step (the N=1
+    equivalent measured in the same run, for C5's efficiency)."""
     torch, L, ffi = ctx.torch, ctx.L, ctx.ffi
     cap = 1_000_000
     R = sum(rows)
-    h, cols = make_prb(ctx, cap, rows, 7)
+    h, cols, init_prio = make_prb(ctx, cap, rows, 7)
     st = ctx.stream
     idx = torch.empty(batch, dtype=torch.int64, device="cuda")
     w = torch.empty(batch, dtype=torch.float32, device="cuda")
@@ -264,34 +346,69 @@ def bench_per(ctx, name, rows, batch, steps, warmup, primary):
     g.manual_seed(99 + ctx.rank)
     prio = torch.randn((pool, batch), device="cuda", generator=g).abs_() + 1e-3
     prio_ptr = [prio[i].data_ptr() for i in range(pool)]
-    sharded = ctx.world > 1
+    sharded = ctx.world > 1 if sharded is None else sharded
+    world_eff = ctx.world if sharded else 1
     stats = torch.empty(4, dtype=torch.float32, device="cuda")
     gstats = torch.empty((ctx.world, 4), dtype=torch.float32, device="cuda")
-    p2p = sharded and os.environ.get("MRL_SHARD_EXCHANGE", "p2p") == "p2p" and ctx.world <= 32
-    if p2p:  # peer mailboxes: the sample kernel exchanges the root statistics itself
+    exchange = os.environ.get("MRL_SHARD_EXCHANGE", "p2p")  # p2p | p2p_sample | nccl
+    p2p = sharded and exchange in ("p2p", "p2p_sample") and ctx.world <= 32
+    if p2p:  # peer mailboxes: the buffer's own kernels exchange the root statistics
         buf = C.create_string_buffer(64)
         ffi.check(L.mrl_prb_shard_init(h, ctx.rank, ctx.world, buf))
+        ffi.check(L.mrl_prb_shard_set_mode(h, 0 if exchange == "p2p_sample" else 1))
         parts = [None] * ctx.world
         ctx.dist.all_gather_object(parts, buf.raw)
         allh = b"".join(parts)
-        ffi.check(L.mrl_prb_shard_connect(h, C.create_string_buffer(allh, len(allh))))
+        ffi.check(L.mrl_prb_shard_connect(h, C.create_string_buffer(allh, len(allh)), st))
+        torch.cuda.synchronize()
         ctx.dist.barrier()
 
-    def step(i):
+    def sample_into(u_ptr, idx_, w_, tab_):
         if p2p:
-            ffi.check(L.mrl_prb_sample_sharded_p2p(h, batch, BETA, None, idx.data_ptr(), w.data_ptr(),
-                                                   out_tab, st))
+            ffi.check(L.mrl_prb_sample_sharded_p2p(h, batch, BETA, u_ptr, idx_.data_ptr(), w_.data_ptr(), tab_, st))
         elif sharded:  # root stats all-gather (16 B/rank over NVLink), then local strata
             ffi.check(L.mrl_prb_root_stats(h, stats.data_ptr(), st))
             ctx.dist.all_gather_into_tensor(gstats, stats)
-            ffi.check(L.mrl_prb_sample_sharded(h, batch, BETA, None, gstats.data_ptr(), ctx.world,
-                                               idx.data_ptr(), w.data_ptr(), out_tab, st))
+            ffi.check(L.mrl_prb_sample_sharded(h, batch, BETA, u_ptr, gstats.data_ptr(), ctx.world,
+                                               idx_.data_ptr(), w_.data_ptr(), tab_, st))
         else:
-            ffi.check(L.mrl_prb_sample(h, batch, BETA, None, idx.data_ptr(), w.data_ptr(), out_tab, st))
+            ffi.check(L.mrl_prb_sample(h, batch, BETA, u_ptr, idx_.data_ptr(), w_.data_ptr(), tab_, st))
+
+    check = None
+    if parity and (sharded or ctx.world == 1):
+        o, narrow = build_parity_oracle(ctx, cap, rows, init_prio, batch)
+        check = parity_check(ctx, h, o, narrow, rows, batch, sample_into)
+        del o
+        if not check["ok"]:
+            raise SystemExit(f"parity_check failed on rank {ctx.rank}: {check}")
+    del init_prio
+
+    def step(i):
+        sample_into(None, idx, w, out_tab)
         ffi.check(L.mrl_prb_update(h, idx.data_ptr(), prio_ptr[i % pool], batch, st))
 
+    if p2p:
+        ffi.check(L.mrl_prb_shard_diag(h, None, None, None, None, 1, st))  # reset the exchange counters
     total_ms, launches = ctx.timed(step, steps, warmup, sample_clocks=primary)
-    value = ctx.world * batch * steps / (total_ms * 1e-3)
+    value = world_eff * batch * steps / (total_ms * 1e-3)
+    exchange_info = None
+    if p2p:
+        v = [C.c_int64() for _ in range(4)]
+        ffi.check(L.mrl_prb_shard_diag(h, *[C.byref(x) for x in v], 0, st))
+        cyc, polled, waited, timeouts = (x.value for x in v)
+        mhz = (ctx.clocks.summary().get("sm_mhz") or ctx.clocks.max_mhz or 1965.0)
+        mine = cyc / max(polled, 1) / mhz  # us per sample call spent in the mailbox poll (warp 0 of CTA 0)
+        worst = ctx.max_over_ranks(mine)
+        exchange_info = {"protocol": "publish_on_mutation" if exchange == "p2p" else "publish_on_sample",
+                         "exchange_wait_us": worst, "exchange_wait_us_rank0": mine, "polled_calls": polled,
+                         "calls_that_waited": waited, "timeouts": timeouts,
+                         "note": "SM cycles between entering and leaving the mailbox poll, warp 0 of CTA 0, per "
+                                 "sample call (warm-up included), at the sampled SM clock; max over ranks"}
+    if not details:
+        ffi.check(L.mrl_prb_destroy(h))
+        return {"workload": name, "metric": "per_sample_update_samples_per_s", "value": value, "unit": "samples/s",
+                "ms_per_step": total_ms / steps, "steps": steps, "gpu_launches": launches,
+                "parity_check": check, "exchange": exchange_info}
 
     # ---- per-kernel durations for the roofline (same flush discipline) -------------------
     ksteps = max(20, min(steps, 300))
@@ -307,7 +424,7 @@ def bench_per(ctx, name, rows, batch, steps, warmup, primary):
     t_update, _ = ctx.timed(only_update, ksteps, 3)
     kern = {
         "prb_sample_kernel(descent+weights)": {"ms": t_sample / ksteps, "bytes": (4 * L_1M + 16) * batch},
-        "prb_update_kernel": {"ms": t_update / ksteps, "bytes": (24 * L_1M + 20) * batch},
+        "prb_update_sub_kernel": {"ms": t_update / ksteps, "bytes": (24 * L_1M + 20) * batch},
     }
     if R > 512:  # wide columns are gathered by their own kernel: time it through a uniform-buffer view
         wide = [c for c, r in enumerate(rows) if r > 512]
@@ -330,7 +447,6 @@ def bench_per(ctx, name, rows, batch, steps, warmup, primary):
     dom = "gather_bulk_kernel" if "gather_bulk_kernel" in kern else max(kern, key=lambda k: kern[k]["ms"])
     ach = kern[dom]["bytes"] / (kern[dom]["ms"] * 1e-3) / 1e9
     tkey = ("c3:" if R > 512 else "c2:") + {"prb_sample_kernel(descent+weights)": "prb_sample_kernel",
-                                             "prb_update_kernel": "prb_update_sub_kernel",
                                              "gather_bulk_kernel": "gather_bulk_kernel<4>"}.get(dom, dom)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm, "unit": "GB/s",
                 "frac": ach / hbm, "traffic": ncu_traffic(tkey), "peak_source": peak_src,
@@ -363,14 +479,15 @@ def bench_per(ctx, name, rows, batch, steps, warmup, primary):
 
     esteps = max(10, min(steps, 200 if R > 512 else 1000))
     e_ms = ctx.timed_host(step_host, esteps, 3)
-    e2e = {"value": ctx.world * batch * esteps / (e_ms * 1e-3), "unit": "samples/s",
+    e2e = {"value": world_eff * batch * esteps / (e_ms * 1e-3), "unit": "samples/s",
            "h2d_bytes_per_step": batch * 12, "d2h_bytes_per_step": batch * (12 + R),
            "steps": esteps, "ms_per_step": e_ms / esteps}
     ffi.check(L.mrl_prb_destroy(h))
     return {"workload": name, "metric": "per_sample_update_samples_per_s", "value": value,
             "unit": "samples/s", "ms_per_step": total_ms / steps, "steps": steps,
             "gpu_launches": launches, "roofline": roofline, "e2e": e2e,
-            "algorithmic_bytes_per_sample": 2 * R + 28 * L_1M + 36}
+            "algorithmic_bytes_per_sample": 2 * R + 28 * L_1M + 36, "parity_check": check,
+            "exchange": exchange_info}
 
 
 def bench_urb(ctx, steps, warmup):
@@ -471,23 +588,60 @@ def bench_insert(ctx, steps, warmup):
             "e2e": e2e, "variants": out}
 
 
+def cpu_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_urb(seconds=2.0):
+    """C1's CPU leg: the oracle's append 1 + sample 64 loop timed INSIDE the C library (no Python wrapper in the
+    timed region), on one core and with the gather half split over all cores (as upstream's CPU kernel does)"""
     from oracle import oracle as O
     rng = np.random.default_rng(1)
     cap, batch = 100_000, 64
     shapes, types = [(r,) for r in C2_ROWS], [np.uint8] * len(C2_ROWS)
     b = O.UniformBufferOracle(batch, cap, shapes, types, seed=5)
     b.insert([rng.integers(0, 256, size=(cap, r), dtype=np.uint8) for r in C2_ROWS])
-    rows = [[rng.integers(0, 256, size=(r,), dtype=np.uint8) for r in C2_ROWS] for _ in range(64)]
-    for i in range(10):
-        b.insert(rows[i]); b.sample()
-    t0 = time.perf_counter()
-    steps = 0
-    while time.perf_counter() - t0 < seconds:
-        b.insert(rows[steps % 64]); b.sample()
-        steps += 1
-    dt = time.perf_counter() - t0
-    return batch * steps / dt, steps, dt
+    pool = [rng.integers(0, 256, size=(64, r), dtype=np.uint8) for r in C2_ROWS]
+    b.bench_loop(2000, pool)
+    per = b.bench_loop(20000, pool) / 20000
+    steps = max(1000, int(seconds / max(per, 1e-9)))
+    dt = b.bench_loop(steps, pool)
+    nt = cpu_threads()
+    mt_steps = max(200, min(steps, 20000))
+    b.bench_loop(200, pool, threads=nt)
+    dt_mt = b.bench_loop(mt_steps, pool, threads=nt)
+    return {"value": batch * steps / dt, "unit": "samples/s", "cores": 1, "kind": "port",
+            "sample": f"{steps} steps of insert 1 + sample 64 in {dt:.2f}s, timed inside the C oracle (orc_urb_bench_loop)",
+            "all_cores": {"value": batch * mt_steps / dt_mt, "cores": nt,
+                          "sample": f"{mt_steps} steps, the gather of every sample split over {nt} threads "
+                                    "(orc_urb_gather_mt; a thread pool start per 5.6 KB batch costs more than it saves)"},
+            "host": host_info()}
+
+
+def cpu_wide_gather(seconds=3.0):
+    """C3's row gather on the host: 512 Atari-shaped rows (2 x 28 224 B) per batch out of a 16 384-row buffer, one core
+    and all cores (upstream splits this loop over its thread pool)"""
+    from oracle import oracle as O
+    rng = np.random.default_rng(2)
+    cap, batch = 16384, 512
+    rows = [28224, 28224]
+    b = O.UniformBufferOracle(batch, cap, [(r,) for r in rows], [np.uint8] * 2, seed=5)
+    block = [rng.integers(0, 256, size=(2048, r), dtype=np.uint8) for r in rows]
+    for _ in range(cap // 2048):
+        b.insert(block)
+    slots = rng.integers(0, cap, size=batch)
+    out = {}
+    for name, nt in (("one_core", 1), ("all_cores", cpu_threads())):
+        b.gather_bench(slots, nt, 3)
+        per = b.gather_bench(slots, nt, 10) / 10
+        reps = max(10, int(seconds / 2 / max(per, 1e-9)))
+        dt = b.gather_bench(slots, nt, reps)
+        out[name] = {"cores": nt, "GBps": 2 * sum(rows) * batch * reps / dt / 1e9, "ms_per_batch": dt / reps * 1e3,
+                     "reps": reps}
+    return out
 
 
 def bench_gae(ctx, steps, warmup):
@@ -576,6 +730,50 @@ def bench_gae(ctx, steps, warmup):
     sustained("discounted_return_batch_major", lambda r_, v_, d_, a_, t_: ffi.check(L.mrl_discounted_return(
         p_(r_), p_(d_), p_(v_[T]), p_(a_), T, B, 1, 0.99, 1, 0, st)), 9)
     del sets
+
+    # GAE + PPO's advantage normalisation as one operation (moments fused into the scan's store phase) against
+    # the two-step form (scan, then mrl_normalize = moments pass + apply pass)
+    def gae_norm_fused(i):
+        ffi.check(L.mrl_gae_normalized(r.data_ptr(), v.data_ptr(), None, v[T].data_ptr(), d.data_ptr(), adv.data_ptr(),
+                                       ret.data_ptr(), T, B, 0.99, 0.95, 1e-8, 0, 0, st))
+
+    def gae_then_norm(i):
+        gae_tm(i)
+        ffi.check(L.mrl_normalize(adv.data_ptr(), adv.data_ptr(), n, 1e-8, st))
+
+    run("gae+normalize_fused_moments[T,B]", gae_norm_fused, 17 + 8, 4 * B)
+    run("gae_then_normalize_separate[T,B]", gae_then_norm, 17 + 12, 4 * B)
+
+    # element-wise error of the PARALLEL kernels against the sequential kernel (which is bit-identical to the CPU
+    # oracle: tests/test_gpu_scans.py).  north_star words the tolerance as "1e-5 relative"; sums that cancel to ~0
+    # have no meaningful element-wise relative error (the fp32 oracle itself misses 1e-5 against float64 there),
+    # so the bound held by the tests is |gpu - oracle| <= 1e-5 * max(||oracle||_inf, 1) and the distribution of the
+    # element-wise relative error is reported here.
+    def err_stats(par, seq):
+        diff = (par.double() - seq.double()).abs()
+        rel = diff / seq.double().abs().clamp_min(1e-30)
+        srt = rel.flatten().sort().values
+        q = lambda f: float(srt[min(srt.numel() - 1, int(f * srt.numel()))])  # noqa: E731
+        scale = max(1.0, float(seq.abs().max()))
+        return {"p50": q(0.5), "p99": q(0.99), "p999": q(0.999), "max_rel": float(srt[-1]), "max_abs": float(diff.max()),
+                "max_abs_over_norm": float(diff.max()) / scale, "frac_elems_rel_gt_1e-5": float((rel > 1e-5).double().mean()),
+                "frac_elems_rel_gt_1e-5_and_abs_gt_1e-5": float(((rel > 1e-5) & (diff > 1e-5)).double().mean())}
+
+    seq_adv, seq_ret = torch.empty_like(adv), torch.empty_like(ret)
+    ffi.check(L.mrl_gae(r.data_ptr(), v.data_ptr(), None, v[T].data_ptr(), d.data_ptr(), seq_adv.data_ptr(),
+                        seq_ret.data_ptr(), T, B, 0.99, 0.95, 0, 1, st))
+    gae_tm(0)
+    scan_error = {"gae_time_major_adv": err_stats(adv, seq_adv), "gae_time_major_ret": err_stats(ret, seq_ret)}
+    ffi.check(L.mrl_gae(r.data_ptr(), v.data_ptr(), None, v[T].data_ptr(), d.data_ptr(), seq_adv.data_ptr(),
+                        seq_ret.data_ptr(), T, B, 0.99, 0.95, 1, 1, st))
+    gae_bm(0)
+    scan_error["gae_batch_major_adv"] = err_stats(adv, seq_adv)
+    ffi.check(L.mrl_discounted_return(r.data_ptr(), d.data_ptr(), v[T].data_ptr(), seq_adv.data_ptr(), T, B, 1, 0.99, 0, 1, st))
+    dr_tm(0)
+    scan_error["discounted_return_time_major"] = err_stats(adv, seq_adv)
+    scan_error["tolerance_held_by_the_tests"] = "|gpu - oracle| <= 1e-5 * max(||oracle||_inf, 1) (norm-wise); north_star: 1e-5 relative"
+    scan_error["reference"] = "sequential GPU kernel = CPU oracle bit for bit (tests/test_gpu_scans.py)"
+    del seq_adv, seq_ret
     main = out["gae_time_major[T,B]"]
     roofline = {"bound": "hbm", "kernel": "scan_tm_strip_kernel<GAE, done, 32 cols, 16 steps/lane>", "achieved": main["GBps"],
                 "peak": hbm, "unit": "GB/s", "frac": main["frac"],
@@ -608,11 +806,12 @@ def bench_gae(ctx, steps, warmup):
     return {"workload": name,
             "metric": "gae_elements_per_s", "value": main["elems_per_s"] * w, "unit": "elements/s",
             "ms_per_step": main["ms"], "steps": steps, "roofline": roofline, "e2e": e2e,
-            "variants": out}
+            "scan_error": scan_error, "variants": out}
 
 
 # ---- CPU baselines (oracle port; the only place bench.py executes oracle/) ---------------
-def cpu_per(rows, batch, capacity, seconds=8.0, max_steps=4000):
+def cpu_per(rows, batch, capacity, seconds=8.0, max_steps=200000, warm_seconds=0.5):
+    """PER sample + update_priorities on the CPU oracle, the loop timed inside the C library"""
     from oracle import oracle as O
     rng = np.random.default_rng(0)
     shapes = [(r,) for r in rows]
@@ -620,22 +819,16 @@ def cpu_per(rows, batch, capacity, seconds=8.0, max_steps=4000):
     b = O.PriorityBufferOracle(ALPHA, capacity, batch, shapes, types, 7, 0)
     chunk = max(1, min(capacity, (64 << 20) // max(sum(rows), 1)))
     block = [rng.integers(0, 256, size=(chunk, r), dtype=np.uint8) for r in rows]
-    for s in range(0, capacity, chunk):
-        n = min(chunk, capacity - s)
+    for s_ in range(0, capacity, chunk):
+        n = min(chunk, capacity - s_)
         b.insert_batch([blk[:n] for blk in block])
     pr = (np.abs(rng.normal(size=capacity)) + 1e-3).astype(np.float32)
     b.update_priorities(np.arange(capacity), pr)
     prio = (np.abs(rng.normal(size=(64, batch))) + 1e-3).astype(np.float32)
-    for i in range(3):
-        out = b.sample(BETA)
-        b.update_priorities(out[0], prio[i])
-    t0 = time.perf_counter()
-    steps = 0
-    while steps < max_steps and time.perf_counter() - t0 < seconds:
-        out = b.sample(BETA)
-        b.update_priorities(out[0], prio[steps % 64])
-        steps += 1
-    dt = time.perf_counter() - t0
+    per = b.bench_loop(20, BETA, prio) / 20
+    b.bench_loop(max(3, int(warm_seconds / max(per, 1e-9))), BETA, prio)  # time-based warm-up (caches, page faults)
+    steps = max(20, min(max_steps, int(seconds / max(per, 1e-9))))
+    dt = b.bench_loop(steps, BETA, prio)
     return batch * steps / dt, steps, dt
 
 
@@ -669,6 +862,22 @@ def host_info():
     return info
 
 
+C2_NAME = ("C2 PER cap 1M (2^20 leaves) 40-byte rows batch 256 alpha 0.6 beta 0.4, "
+           "sample+update_priorities per step")
+
+
+def headline_config(world):
+    """the `config` object of the JSON line: the same dict in both arms (the driver compares them key by key)"""
+    return {"workload": C2_NAME, "capacity": 1_000_000, "batch": 256, "row_bytes": sum(C2_ROWS), "alpha": ALPHA,
+            "beta": BETA, "per_rank": True,
+            "l2": "flushed before every timed iteration (256 MiB written, then 256 MiB read; untimed); step time = "
+                  "sum of per-iteration CUDA-event durations on the launching stream (reference arm: host clock "
+                  "around the C loop)",
+            "sharding": ("per-rank sub-buffers (1M rows each); root statistics published to peer mailboxes over NVLink "
+                         "by the mutating kernels (MRL_SHARD_EXCHANGE=p2p_sample: by the sample kernel; nccl: NCCL "
+                         "all-gather)" if world > 1 else "single GPU")}
+
+
 def run_reference(args, emit):
     """the reference arm: the reference's sequential CPU algorithm (oracle port) on the host"""
     rank = int(os.environ.get("RANK", 0))
@@ -683,26 +892,25 @@ def run_reference(args, emit):
     b.insert_batch([rng.integers(0, 256, size=(cap, r), dtype=np.uint8) for r in C2_ROWS])
     b.update_priorities(np.arange(cap), (np.abs(rng.normal(size=cap)) + 1e-3).astype(np.float32))
     prio = (np.abs(rng.normal(size=(64, batch))) + 1e-3).astype(np.float32)
-    for i in range(max(args.warmup, 3)):
-        out = b.sample(BETA)
-        b.update_priorities(out[0], prio[i % 64])
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        out = b.sample(BETA)
-        b.update_priorities(out[0], prio[i % 64])
-    dt = time.perf_counter() - t0
-    value = batch * args.steps / dt
+    # warm-up: the W steps asked for AND at least half a second, so that a 20-step run is not timed cold
+    per = b.bench_loop(max(args.warmup, 3), BETA, prio) / max(args.warmup, 3)
+    warm = max(args.warmup, 3) + max(0, int(0.5 / max(per, 1e-9)))
+    b.bench_loop(warm - max(args.warmup, 3), BETA, prio) if warm > max(args.warmup, 3) else None
+    # each "step" of this arm is a bounded sample of the workload: K_inner back-to-back sample+update steps
+    inner = max(1, int(1.0 / max(per, 1e-9) / max(args.steps, 1)))  # ~1 s of CPU work over the whole run
+    dt = b.bench_loop(args.steps * inner, BETA, prio)
+    value = batch * args.steps * inner / dt
     line = {
         "impl": "reference", "metric": "per_sample_update_samples_per_s", "value": value,
         "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": dt * 1e3 / (args.steps * inner), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C2 PER cap 1M (2^20 leaves) 40-byte rows batch 256 alpha 0.6 beta 0.4, "
-                               "sample+update_priorities per step", "capacity": cap, "batch": batch},
+        "config": headline_config(args.gpus),
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": 1, "kind": "port",
-                         "sample": f"{args.steps} steps of sample(256)+update(256) on the full 1M-leaf tree; "
-                                   "MindSpore (the reference's kernels) is not installable here, so this is "
-                                   "the oracle port of its sequential CPU algorithm",
+                         "sample": f"{args.steps} x {inner} steps of sample(256)+update(256) on the full 1M-leaf tree after "
+                                   f"{warm} warm-up steps, timed inside the C oracle (orc_prb_bench_loop); MindSpore (the "
+                                   "reference's kernels) is not installable here, so this is the oracle port of its "
+                                   "sequential CPU algorithm (one core: upstream's PER kernels are sequential loops)",
                          "host": host_info()},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -725,7 +933,7 @@ def main():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--only", default="all", choices=["all", "c1", "c2", "c3", "c4", "insert"])
+    ap.add_argument("--only", default="all", choices=["all", "c1", "c2", "c3", "c4", "c5", "insert"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baselines")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -734,16 +942,32 @@ def main():
         return
 
     ctx = Ctx(args)
-    primary, also = None, []
+    primary, also, c5 = None, [], None
+    C5_NAME = "C5 sharded PER 1M rows/rank, 40-byte rows, batch 4096/rank, sample+update_priorities per step"
     if args.only in ("all", "c2"):
-        primary = bench_per(ctx, "C2 PER cap 1M (2^20 leaves) 40-byte rows batch 256 alpha 0.6 beta 0.4, "
-                                 "sample+update_priorities per step", C2_ROWS, 256, args.steps, args.warmup, True)
+        primary = bench_per(ctx, C2_NAME, C2_ROWS, 256, args.steps, args.warmup, True)
+    if args.only in ("all", "c5"):
+        # C5 at EVERY N (N = 1: one shard, batch 4096), so that the records hold a 1 -> 8 curve for it; at N > 1
+        # every rank also runs the un-sharded step on its own GPU in the same run (the N = 1 equivalent)
+        c5_steps = max(20, min(args.steps, 300))
+        r = bench_per(ctx, C5_NAME, C2_ROWS, 4096, c5_steps, args.warmup, primary is None)
+        c5 = {"workload": C5_NAME, "metric": r["metric"], "unit": r["unit"], "value": r["value"], "n_gpus": ctx.world,
+              "ms_per_step": r["ms_per_step"], "steps": r["steps"], "e2e": r["e2e"]["value"],
+              "parity_check": r["parity_check"], "exchange": r["exchange"]}
+        if ctx.world > 1:
+            solo = bench_per(ctx, C5_NAME + " (un-sharded, every rank alone)", C2_ROWS, 4096, c5_steps, args.warmup,
+                             False, sharded=False, parity=False, details=False)
+            c5["single_gpu_same_run"] = {"value": solo["value"], "ms_per_step": solo["ms_per_step"],
+                                         "note": "the same step without the exchange, all ranks at once, max over ranks"}
+            c5["weak_scaling_efficiency_vs_same_run_single_gpu"] = r["value"] / (ctx.world * solo["value"])
+        (also.append(r) if primary else None)
+        primary = primary or r
     if ctx.world == 1 and args.only in ("all", "c3"):
         r = bench_per(ctx, "C3 Atari-shaped PER cap 1M obs 84x84x4 u8 (x2) batch 512", C3_ROWS, 512,
                       max(20, min(args.steps, 200)), args.warmup, primary is None)
         (also.append(r) if primary else None)
         primary = primary or r
-    if ctx.world == 1 and args.only in ("all", "c4"):
+    if args.only in ("all", "c4") and (ctx.world == 1 or args.only == "all"):
         r = bench_gae(ctx, max(10, min(args.steps, 50)), args.warmup)
         (also.append(r) if primary else None)
         primary = primary or r
@@ -755,66 +979,49 @@ def main():
         r = bench_insert(ctx, max(10, min(args.steps, 50)), args.warmup)
         (also.append(r) if primary else None)
         primary = primary or r
-    if ctx.world > 1 and args.only == "all":
-        r = bench_per(ctx, "C5 sharded PER 1M/rank batch 4096/rank, root-stat all-gather per sample",
-                      C2_ROWS, 4096, max(20, min(args.steps, 300)), args.warmup, False)
-        also.append(r)
-        also.append(bench_gae(ctx, max(10, min(args.steps, 50)), args.warmup))
 
     if ctx.rank == 0:
         if not args.no_cpu:
-            if "PER" in primary["workload"]:
-                wide = "C3" in primary["workload"]
-                v, n, dt = cpu_per(C3_ROWS if wide else C2_ROWS, 512 if wide else 256,
-                                   32768 if wide else 1_000_000)
-                primary["cpu_baseline"] = {
-                    "value": v, "unit": "samples/s", "cores": 1, "kind": "port",
-                    "sample": f"{n} steps in {dt:.1f}s of sample+update on the oracle, capacity "
-                              f"{32768 if wide else 1_000_000}", "host": host_info()}
-            elif primary["workload"].startswith("insert"):
-                pass
-            elif primary["workload"].startswith("C1"):
-                v, n, dt = cpu_urb()
-                primary["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": 1, "kind": "port",
-                                           "sample": f"{n} steps of insert 1 + sample 64 in {dt:.1f}s on the oracle",
-                                           "host": host_info()}
-            else:
-                g, npl = cpu_gae(2048, 4096)
-                primary["cpu_baseline"] = {"value": g, "unit": "elements/s", "cores": 1, "kind": "port",
-                                           "sample": "full 2048x4096 GAE, best of 3", "host": host_info()}
-            for r in also:
-                if r["workload"].startswith("C3"):
+            for r in [primary] + also:
+                wl = r["workload"]
+                if wl.startswith("C2") or wl.startswith("C5"):
+                    b = 256 if wl.startswith("C2") else 4096
+                    v, n, dt = cpu_per(C2_ROWS, b, 1_000_000, seconds=8.0 if r is primary else 4.0)
+                    r["cpu_baseline"] = {
+                        "value": v, "unit": "samples/s", "cores": 1, "kind": "port",
+                        "sample": f"{n} steps of sample({b})+update({b}) in {dt:.1f}s on the full 1M-leaf oracle tree after a "
+                                  "0.5 s warm-up, timed inside the C oracle (one core: upstream's PER kernels are "
+                                  "sequential loops)", "host": host_info()}
+                elif wl.startswith("C3"):
                     v, n, dt = cpu_per(C3_ROWS, 512, 32768, seconds=6.0)
                     r["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": 1, "kind": "port",
-                                         "sample": f"{n} steps in {dt:.1f}s on a 32768-row oracle buffer (1.8 GB of rows)"}
-                elif r["workload"].startswith("C1"):
-                    v, n, dt = cpu_urb()
-                    r["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": 1, "kind": "port",
-                                         "sample": f"{n} steps of insert 1 + sample 64 in {dt:.1f}s on the oracle "
-                                                   "(through its Python wrapper)"}
-                elif r["workload"].startswith("C4"):
+                                         "sample": f"{n} steps in {dt:.1f}s on a 32768-row oracle buffer (1.8 GB of rows), "
+                                                   "timed inside the C oracle",
+                                         "row_gather_on_host": cpu_wide_gather(), "host": host_info()}
+                elif wl.startswith("C1"):
+                    r["cpu_baseline"] = cpu_urb()
+                elif wl.startswith("C4"):
                     g, npl = cpu_gae(2048, 4096)
                     r["cpu_baseline"] = {"value": g, "unit": "elements/s", "cores": 1, "kind": "port",
                                          "sample": "full 2048x4096 GAE on the C oracle, best of 3",
-                                         "numpy_loop_discounted_return_elements_per_s": npl}
+                                         "numpy_loop_discounted_return_elements_per_s": npl, "host": host_info()}
+        cfg = headline_config(ctx.world)
+        cfg["workload"] = primary["workload"]
+        if ctx.world > 1 and os.environ.get("MRL_BENCH_ALIGN", "0") == "1":
+            cfg["l2"] += "; ranks re-aligned after every flush by an untimed 4-byte NCCL all-reduce"
         line = {
             "metric": primary["metric"], "value": primary["value"], "unit": primary["unit"],
             "n_gpus": ctx.world, "steps": primary["steps"], "warmup": args.warmup,
             "ms_per_step": primary["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": primary["workload"], "per_rank": True,
-                       "l2": "flushed before every timed iteration (256 MiB written, then 256 MiB read; untimed); "
-                             "step time = sum of per-iteration CUDA-event durations on the launching stream"
-                             + ("; ranks re-aligned after every flush by an untimed 4-byte NCCL all-reduce"
-                                if ctx.world > 1 and os.environ.get("MRL_BENCH_ALIGN", "0") == "1" else ""),
-                       "sharding": ("per-rank sub-buffers (1M rows each); root statistics exchanged inside the sample "
-                                    "kernel by peer stores over NVLink (MRL_SHARD_EXCHANGE=nccl: NCCL all-gather)"
-                                    if ctx.world > 1 else "single GPU")},
+            "config": cfg,
             "clocks": ctx.clocks.summary(),
             "e2e": primary["e2e"], "gpu_launches": primary.get("gpu_launches"),
-            "roofline": primary["roofline"], "cpu_baseline": primary.get("cpu_baseline"),
+            "roofline": primary.get("roofline"), "cpu_baseline": primary.get("cpu_baseline"),
+            "parity_check": primary.get("parity_check"), "exchange": primary.get("exchange"),
             "algorithmic_bytes_per_sample": primary.get("algorithmic_bytes_per_sample"),
             "variants": primary.get("variants"),
+            "c5": c5,
             "also": also,
         }
         emit(line)

@@ -86,7 +86,24 @@ SIGNATURES = {
     "mrl_vtrace": [vp, vp, vp, vp, vp, vp, f32, f32, f32, vp, vp, i64, i64, i32, vp],
     "mrl_affine_scan": [vp, vp, vp, vp, i64, i64, i32, i32, vp],
 }
-_RESTYPES = {"mrl_last_error": C.c_char_p, "mrl_launch_count": i64}
+# include/mindrl_b200_aot.h: the MindSpore "aot" custom-operator entry points and the stand-in AotExtra
+AOT_OPS = ["BufferAppend", "BufferGetItem", "BufferSample", "PriorityReplayBufferCreate", "PriorityReplayBufferPush",
+           "PriorityReplayBufferSample", "PriorityReplayBufferUpdate", "PriorityReplayBufferDestroy", "DiscountedReturn",
+           "GaeScan"]
+AOT_SIGNATURES = {
+    "mrl_aot_extra_create": [],
+    "mrl_aot_extra_destroy": [vp],
+    "mrl_aot_extra_set_bool": [vp, C.c_char_p, i32],
+    "mrl_aot_extra_set_int": [vp, C.c_char_p, i64],
+    "mrl_aot_extra_set_float": [vp, C.c_char_p, f32],
+    "mrl_aot_extra_set_str": [vp, C.c_char_p, C.c_char_p],
+    "mrl_aot_extra_set_int2d": [vp, C.c_char_p, vp, vp, i32],
+}
+for _op in AOT_OPS:
+    AOT_SIGNATURES[_op] = [C.c_int, vp, vp, vp, vp, vp, vp]
+    AOT_SIGNATURES[_op + "Init"] = [vp, vp, vp, vp]
+_RESTYPES = {"mrl_last_error": C.c_char_p, "mrl_launch_count": i64, "mrl_aot_extra_create": vp,
+             "mrl_aot_extra_destroy": None}
 
 _lib = None
 
@@ -106,7 +123,7 @@ def lib():
                 f"{LIB_PATH} is missing: build it with `python -m mindrl_b200.build` "
                 "(there is no CPU fallback for the experience data path)")
         L = C.CDLL(LIB_PATH)
-        for name, argtypes in SIGNATURES.items():
+        for name, argtypes in list(SIGNATURES.items()) + list(AOT_SIGNATURES.items()):
             fn = getattr(L, name)  # AttributeError here = header and library out of sync
             fn.argtypes = argtypes
             fn.restype = _RESTYPES.get(name, C.c_int)

@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(OUT_DIR, "libmindrl_b200.so")
-SOURCES = ["abi.cu", "copy.cu", "urb.cu", "prb.cu", "scan.cu", "scan_tma.cu"]
+SOURCES = ["abi.cu", "copy.cu", "urb.cu", "prb.cu", "scan.cu", "scan_tma.cu", "aot_shim.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     # parity rule of include/mrl_arith.h: no fast-math, no implicit fma contraction
@@ -25,7 +25,8 @@ def _nvcc():
 
 
 def _deps():
-    hdrs = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "scan.cuh"), os.path.join(HERE, "..", "include", "mindrl_b200.h"),
+    hdrs = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "scan.cuh"), os.path.join(CSRC, "aot_extra.h"),
+            os.path.join(HERE, "..", "include", "mindrl_b200.h"),
             os.path.join(HERE, "..", "include", "mrl_arith.h")]
     return [h for h in hdrs if os.path.exists(h)]
 

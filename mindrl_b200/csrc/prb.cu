@@ -1708,6 +1708,13 @@ extern "C" int mrl_prb_sample(int64_t handle, int64_t n, float beta, const float
                          as_stream(stream));
 }
 
+int mrl::prb_sample_beta_dev(int64_t handle, int64_t n, const float *beta_dev, int64_t *indices, float *weights,
+                             void *const *out_cols, cudaStream_t st) {
+  PRB_GET(b, handle);
+  MRL_REQUIRE(n >= 1 && indices && weights && beta_dev, "PriorityReplayBufferSample: need n >= 1, beta, indices and weights");
+  return prb_sample_impl(b, n, 0.0f, nullptr, nullptr, 0, indices, weights, out_cols, st, false, beta_dev);
+}
+
 extern "C" int mrl_prb_sample_sharded(int64_t handle, int64_t n, float beta, const float *uniforms,
                                       const float *gstats, int32_t world, int64_t *indices,
                                       float *weights, void *const *out_cols, void *stream) {

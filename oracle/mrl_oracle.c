@@ -495,3 +495,110 @@ double orc_now(void) {
   clock_gettime(CLOCK_MONOTONIC, &ts);
   return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * timed loops for bench.py's cpu_baseline / --impl reference legs: the same oracle functions
+ * as above, called from C so that the CPU number carries no Python-wrapper overhead
+ * (C1's CPU leg was timed through the wrapper).  Return seconds (monotonic clock).
+ * ---------------------------------------------------------------------------------------- */
+/* `steps` iterations of { sample(batch, beta) -> update_priorities(indices, prio[step % pool]) } */
+double orc_prb_bench_loop(void *h, int64_t steps, int64_t batch, float beta, const float *prio,
+                          int64_t pool, int64_t *indices, float *weights, void *const *out_cols) {
+  const double t0 = orc_now();
+  for (int64_t s = 0; s < steps; ++s) {
+    orc_prb_sample(h, batch, beta, NULL, indices, weights, out_cols);
+    orc_prb_update(h, indices, prio + (s % pool) * batch, batch);
+  }
+  return orc_now() - t0;
+}
+
+/* `steps` iterations of { append one row (rows[step % pool]) -> sample(batch) }; the gather half of the
+ * sample is split over `nthreads` threads when nthreads > 1 (as the upstream CPU kernel does) */
+double orc_urb_bench_loop(void *h, int64_t steps, int64_t batch, const void *const *row_pool, int64_t pool,
+                          int64_t *slots, void *const *out_cols, int32_t nthreads) {
+  orc_urb *b = (orc_urb *)h;
+  const void *row[ORC_MAX_COLS];
+  const double t0 = orc_now();
+  for (int64_t s = 0; s < steps; ++s) {
+    for (int i = 0; i < b->ncols; ++i)
+      row[i] = (const uint8_t *)row_pool[i] + (s % pool) * b->row_bytes[i];
+    orc_urb_append(h, 1, row);
+    if (nthreads <= 1) {
+      orc_urb_sample(h, batch, slots, out_cols);
+    } else {
+      for (int64_t j = 0; j < batch; ++j) slots[j] = mrl_uniform_below(b->seed, b->ctr + (uint64_t)j, b->count);
+      b->ctr += (uint64_t)batch;
+      orc_urb_gather_mt(h, slots, batch, out_cols, nthreads);
+    }
+  }
+  return orc_now() - t0;
+}
+
+/* `reps` gathers of n rows at the given slots over nthreads threads (wide rows: the all-cores CPU leg) */
+double orc_urb_gather_bench(void *h, const int64_t *slots, int64_t n, void *const *out_cols, int32_t nthreads,
+                            int64_t reps) {
+  const double t0 = orc_now();
+  for (int64_t r = 0; r < reps; ++r) orc_urb_gather_mt(h, slots, n, out_cols, nthreads);
+  return orc_now() - t0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * TD(lambda) targets of COMA, mindspore_rl/algorithm/coma/coma.py:489-501 (build_td_lambda_targets):
+ *   ret[:, t] = td_lambda * gamma * ret[:, t + 1] + mask[:, t] * (
+ *       rewards[:, t] + (1 - td_lambda) * gamma * target_qs[:, t + 1] * (1 - terminated[:, t]))
+ * gamma and td_lambda are Python floats there (coma.py:395-396): the two products of scalars are
+ * formed in double and meet the float32 tensors as float32 scalars (lg, bg).
+ * PINNED by tests/golden/coma_td_lambda_ref.npz (the reference's own method, run by make_golden.py).
+ * ---------------------------------------------------------------------------------------- */
+int orc_td_lambda(const float *rewards, const float *terminated, const float *mask, const float *q,
+                  float *ret, int64_t B, int64_t Tq, int64_t Tr, int64_t A, int64_t RA, int64_t max_t,
+                  double gamma, double td_lambda) {
+  if (max_t >= Tq || max_t > Tr || (RA != 1 && RA != A)) return 1;
+  const float lg = (float)(td_lambda * gamma), bg = (float)((1.0 - td_lambda) * gamma);
+  for (int64_t b = 0; b < B; ++b)
+    for (int64_t a = 0; a < A; ++a) {
+      for (int64_t t = max_t; t < Tq; ++t) ret[(b * Tq + t) * A + a] = 0.0f; /* F.zeros_like(target_qs) */
+      float x = 0.0f;
+      for (int64_t t = max_t - 1; t >= 0; --t) {
+        const int64_t i = (b * Tr + t) * RA + (RA == 1 ? 0 : a);
+        const float boot = (bg * q[(b * Tq + t + 1) * A + a]) * (1.0f - terminated[i]);
+        const float inner = rewards[i] + boot;
+        x = lg * x + mask[i] * inner;
+        ret[(b * Tq + t) * A + a] = x;
+      }
+    }
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * V-trace, mindspore_rl/algorithm/impala/vtrace.py:79-105, time-major [T,B]; thresholds may be
+ * INFINITY.  exp() is libm's expf here and CUDA's on the device: they may differ in the last bit,
+ * so V-trace parity is held to the scans' tolerance, not bit for bit.
+ * PINNED by tests/golden/vtrace_ref.npz (the reference's vtrace.py imported whole by make_golden.py).
+ * ---------------------------------------------------------------------------------------- */
+int orc_vtrace(const float *log_rhos, const float *discounts, const float *rewards, const float *values,
+               const float *bootstrap, const float *masks, float clip_rho, float clip_pg, float clip_c,
+               float *vs, float *pg, int64_t T, int64_t B) {
+  for (int64_t col = 0; col < B; ++col) {
+    float acc = 0.0f, v_next = bootstrap[col], vs_next = bootstrap[col];
+    for (int64_t t = T - 1; t >= 0; --t) {
+      const int64_t i = t * B + col;
+      float rho = expf(log_rhos[i]);                    /* :79 */
+      rho = rho < clip_rho ? rho : clip_rho;            /* :80 */
+      const float c = rho < clip_c ? rho : clip_c;      /* :81 */
+      const float pg_rho = rho < clip_pg ? rho : clip_pg; /* :82 */
+      const float dv = discounts[i] * v_next;
+      const float delta = rho * ((rewards[i] + dv) - values[i]); /* :86 */
+      const float m = masks ? masks[i] : 1.0f;
+      const float dc = discounts[i] * c;
+      acc = delta + (dc * acc) * m;                     /* :91 */
+      const float v = acc + values[i];                  /* :99 */
+      vs[i] = v;
+      const float dn = discounts[i] * vs_next;
+      pg[i] = pg_rho * ((rewards[i] + dn) - values[i]); /* :105 */
+      v_next = values[i];
+      vs_next = v;
+    }
+  }
+  return 0;
+}

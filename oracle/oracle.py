@@ -70,6 +70,15 @@ def lib():
         L.orc_discounted_return.argtypes = [vp, vp, vp, vp, i64, i64, i64, f32, i32]
         L.orc_gae.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i64, f32, f32, i32]
         L.orc_affine_scan.argtypes = [vp, vp, vp, vp, i64, i64, i32]
+        f64 = C.c_double
+        L.orc_td_lambda.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, f64, f64]
+        L.orc_vtrace.argtypes = [vp, vp, vp, vp, vp, vp, f32, f32, f32, vp, vp, i64, i64]
+        L.orc_prb_bench_loop.restype = f64
+        L.orc_prb_bench_loop.argtypes = [vp, i64, i64, f32, vp, i64, vp, vp, vp]
+        L.orc_urb_bench_loop.restype = f64
+        L.orc_urb_bench_loop.argtypes = [vp, i64, i64, vp, i64, vp, vp, i32]
+        L.orc_urb_gather_bench.restype = f64
+        L.orc_urb_gather_bench.argtypes = [vp, vp, i64, vp, i32, i64]
         L.orc_detpowf.restype = f32
         L.orc_detpowf.argtypes = [f32, f32]
         L.orc_detpowf_array.argtypes = [vp, vp, vp, i64]
@@ -170,6 +179,22 @@ class UniformBufferOracle:
     def reset(self):
         lib().orc_urb_reset(self._h)
 
+    def bench_loop(self, steps, row_pool, n=None, threads=1):
+        """seconds for `steps` iterations of {append 1 row, sample n} timed inside the C library (bench.py)"""
+        n = self.sample_size if n is None else n
+        pool = _as_cols(row_pool, self.dtypes)
+        npool = pool[0].size * pool[0].itemsize // self.row_bytes[0]
+        slots = np.empty(n, dtype=np.int64)
+        outs = self._outs(n)
+        return lib().orc_urb_bench_loop(self._h, steps, n, _ptr_table(pool), npool, slots.ctypes.data,
+                                        _ptr_table(outs), threads)
+
+    def gather_bench(self, slots, threads, reps):
+        """seconds for `reps` gathers of the rows at `slots` over `threads` threads, timed in C (bench.py)"""
+        slots = np.ascontiguousarray(slots, dtype=np.int64)
+        outs = self._outs(len(slots))
+        return lib().orc_urb_gather_bench(self._h, slots.ctypes.data, len(slots), _ptr_table(outs), threads, reps)
+
     def state(self):
         c, h = C.c_int32(), C.c_int32()
         lib().orc_urb_state(self._h, C.addressof(c), C.addressof(h))
@@ -256,8 +281,20 @@ class PriorityBufferOracle:
             g = np.ascontiguousarray(gstats, dtype=np.float32).reshape(-1, 4)
             rc = lib().orc_prb_sample_sharded(self._h, n, beta, _ptr(u), g.ctypes.data, g.shape[0],
                                               idx.ctypes.data, w.ctypes.data, tab)
-        assert rc == 0
+        if rc:
+            raise RuntimeError("PriorityReplayBuffer.sample: the buffer is empty")
         return (idx, w) + (tuple(outs) if gather else ())
+
+    def bench_loop(self, steps, beta, prio_pool, n=None, gather=True):
+        """seconds for `steps` iterations of {sample n, update_priorities with prio_pool[step % len]} timed inside
+        the C library (bench.py's CPU legs)"""
+        n = self.sample_size if n is None else n
+        prio = np.ascontiguousarray(prio_pool, dtype=np.float32).reshape(-1, n)
+        idx = np.empty(n, dtype=np.int64)
+        w = np.empty(n, dtype=np.float32)
+        outs = [np.empty((n,) + s, dtype=d) for s, d in zip(self.shapes, self.dtypes)] if gather else None
+        return lib().orc_prb_bench_loop(self._h, steps, n, beta, prio.ctypes.data, prio.shape[0], idx.ctypes.data,
+                                        w.ctypes.data, _ptr_table(outs) if gather else None)
 
     def update_priorities(self, indices, priorities):
         i = np.ascontiguousarray(indices, dtype=np.int64)
@@ -391,6 +428,36 @@ def libm_pow(x, y):
 
 def uniform01(seed, ctr):
     return lib().orc_uniform01(seed, ctr)
+
+
+def td_lambda_targets(rewards, terminated, mask, target_qs, gamma, td_lambda, max_t=None):
+    """C oracle of coma.py:489-501; target_qs [B, Tq, A], the others [B, Tr, 1 or A]"""
+    q = _f32(target_qs)
+    r, te, m = _f32(rewards), _f32(terminated), _f32(mask)
+    B, Tq = q.shape[0], q.shape[1]
+    A = int(np.prod(q.shape[2:], dtype=np.int64))
+    Tr = r.shape[1]
+    RA = int(np.prod(r.shape[2:], dtype=np.int64))
+    max_t = Tq - 1 if max_t is None else int(max_t)
+    ret = np.empty_like(q)
+    rc = lib().orc_td_lambda(r.ctypes.data, te.ctypes.data, m.ctypes.data, q.ctypes.data, ret.ctypes.data, B, Tq, Tr, A,
+                             RA, max_t, float(gamma), float(td_lambda))
+    assert rc == 0
+    return ret
+
+
+def vtrace(log_rhos, discounts, rewards, values, bootstrap_value, clip_rho, clip_pg, clip_cs, masks):
+    """C oracle of vtrace.py:79-105 (time-major); a threshold of None disables that clip"""
+    lr, d, r, v, b = (_f32(x) for x in (log_rhos, discounts, rewards, values, bootstrap_value))
+    m = _f32(masks)
+    T, B = lr.shape[0], int(np.prod(lr.shape[1:], dtype=np.int64))
+    vs, pg = np.empty_like(lr), np.empty_like(lr)
+    inf = float("inf")
+    rc = lib().orc_vtrace(lr.ctypes.data, d.ctypes.data, r.ctypes.data, v.ctypes.data, b.ctypes.data, _ptr(m),
+                          inf if clip_rho is None else clip_rho, inf if clip_pg is None else clip_pg,
+                          inf if clip_cs is None else clip_cs, vs.ctypes.data, pg.ctypes.data, T, B)
+    assert rc == 0
+    return vs, pg
 
 
 def fill_rows(nrows, row_bytes, seed):

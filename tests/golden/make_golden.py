@@ -14,6 +14,10 @@ cannot be imported (they are closures inside learn()), so their FunctionDef node
 the reference file with `ast` at run time and compiled unmodified against a stand-in `self`
 (add, mul, reshape, squeeze, zeros_like, zero_int, critic_net = a lookup of precomputed values).
 
+mappo_gae_ref.npz: the GAE block of MAPPOLearner.learn (algorithm/mappo/mappo.py:478-500), inline statements
+taken out of the method with `ast`; coma_td_lambda_ref.npz: COMALearner.build_td_lambda_targets
+(algorithm/coma/coma.py:489-501), the method itself; vtrace_ref.npz: the reference's vtrace.py imported whole.
+
 Run in the build container only (the GPU box has no /root/reference):
     python tests/golden/make_golden.py
 """
@@ -36,6 +40,7 @@ class Tensor(np.ndarray):
 
     def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
         raw = [np.asarray(i).view(np.ndarray) if isinstance(i, np.ndarray) else i for i in inputs]
+        kwargs.pop("out", None)  # `x += 1` builds a new tensor, as MindSpore's tensors do (never mutates a shared one)
         out = getattr(ufunc, method)(*raw, **kwargs)
         had64 = any(isinstance(i, np.ndarray) and i.dtype == np.float64 for i in inputs)
         if isinstance(out, np.ndarray) and out.dtype == np.float64 and not had64:
@@ -184,7 +189,112 @@ def make_vtrace():
     print("wrote", OUT_VTRACE, os.path.getsize(OUT_VTRACE), "bytes")
 
 
+MAPPO_REF = "/root/reference/mindspore_rl/algorithm/mappo/mappo.py"
+OUT_MAPPO = os.path.join(os.path.dirname(os.path.abspath(__file__)), "mappo_gae_ref.npz")
+
+
+def make_mappo():
+    """MAPPOLearner.learn's GAE block (mappo.py:478-500) is inline code, not a function: its statements -- from
+    `gae = self.zeros_like(last_value)` to `advantage = (...)[1:]` -- are taken out of learn()'s FunctionDef with
+    `ast` at run time and compiled UNMODIFIED into a function of the names they read (self, reward, value, mask,
+    last_value, last_episode_mask, last_value_prediction, ms).  self.gamma is a float32 tensor and
+    self.td_lambda a Python float, as at mappo.py:430-431; value_normalizer.denormalize is the identity (the
+    scan takes de-normalised values)."""
+    import ast
+    install_shim()
+    ms = sys.modules["mindspore"]
+    src = open(MAPPO_REF).read()
+    tree = ast.parse(src)
+    learn = [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name == "learn"]
+    assert len(learn) == 1
+    body = learn[0].body
+    first = next(i for i, st in enumerate(body) if isinstance(st, ast.Assign) and ast.unparse(st).startswith("gae = self.zeros_like(last_value)"))
+    last = next(i for i, st in enumerate(body) if isinstance(st, ast.Assign) and ast.unparse(st).startswith("advantage = "))
+    assert 478 <= body[first].lineno and body[last].end_lineno <= 500, (body[first].lineno, body[last].end_lineno)
+    fn = ast.FunctionDef(
+        name="mappo_gae_block",
+        args=ast.arguments(posonlyargs=[], args=[ast.arg(arg=a) for a in
+                                                 ("self", "reward", "value", "mask", "last_value", "last_episode_mask",
+                                                  "last_value_prediction", "ms")],
+                           kwonlyargs=[], kw_defaults=[], defaults=[]),
+        body=body[first:last + 1] + [ast.Return(value=ast.Tuple(elts=[ast.Name(id="discounted_r", ctx=ast.Load()),
+                                                                     ast.Name(id="advantage", ctx=ast.Load())], ctx=ast.Load()))],
+        decorator_list=[], type_params=[])
+    mod = ast.fix_missing_locations(ast.Module(body=[fn], type_ignores=[]))
+    ns = {}
+    exec(compile(mod, MAPPO_REF, "exec"), ns)
+
+    class Norm:
+        denormalize = staticmethod(lambda x: x)
+
+    class Self:
+        zero = Tensor(0, np.float32)
+        zeros_like = staticmethod(lambda a: Tensor(np.zeros_like(np.asarray(a))))
+        value_normalizer = Norm()
+
+    rng = np.random.default_rng(31)
+    cases = {}
+    for name, B, gamma, lam in [("a", 1, 0.99, 0.95), ("b", 8, 0.99, 0.95), ("c", 64, 0.9, 0.8), ("d", 33, 0.995, 0.97)]:
+        me = Self()
+        me.gamma = Tensor(gamma, np.float32)
+        me.td_lambda = lam
+        reward = rng.normal(size=(26, B, 1)).astype(np.float32)
+        value = rng.normal(size=(26, B, 1)).astype(np.float32)
+        mask = (rng.random((26, B, 1)) > 0.15).astype(np.float32)
+        last_value = rng.normal(size=(B, 1)).astype(np.float32)
+        dr, adv = ns["mappo_gae_block"](me, Tensor(reward), Tensor(value), Tensor(mask), Tensor(last_value),
+                                        Tensor(mask[-1]), Tensor(value[-1]), ms)
+        dr, adv = np.asarray(dr).view(np.ndarray), np.asarray(adv).view(np.ndarray)
+        assert dr.dtype == np.float32 and adv.dtype == np.float32 and dr.shape == (26, B, 1) and adv.shape == (25, B, 1)
+        for k, v in dict(reward=reward, value=value, mask=mask, last_value=last_value, gamma=np.float32(gamma),
+                         lam=np.float32(lam), discounted_r=dr, advantage=adv).items():
+            cases[f"{name}/{k}"] = v
+    np.savez_compressed(OUT_MAPPO, **cases)
+    print("wrote", OUT_MAPPO, os.path.getsize(OUT_MAPPO), "bytes")
+
+
+COMA_REF = "/root/reference/mindspore_rl/algorithm/coma/coma.py"
+OUT_COMA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "coma_td_lambda_ref.npz")
+
+
+def make_coma():
+    """COMALearner.build_td_lambda_targets (coma.py:489-501), its FunctionDef taken from the reference file with
+    `ast` and compiled unmodified; F.zeros_like is the only outside name it reads.  gamma and td_lambda are
+    Python floats (coma.py:395-396)."""
+    import ast
+    install_shim()
+    tree = ast.parse(open(COMA_REF).read())
+    fns = [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name == "build_td_lambda_targets"]
+    assert len(fns) == 1 and 489 <= fns[0].lineno <= 490
+    mod = ast.Module(body=fns, type_ignores=[])
+
+    class F:
+        zeros_like = staticmethod(lambda a: Tensor(np.zeros_like(np.asarray(a))))
+
+    ns = {"F": F}
+    exec(compile(mod, COMA_REF, "exec"), ns)
+    rng = np.random.default_rng(47)
+    cases = {}
+    for name, (B, T, A), gamma, lam, max_t in [("a", (2, 5, 3), 0.99, 0.8, 5), ("b", (32, 60, 5), 0.99, 0.8, 60),
+                                               ("c", (8, 100, 2), 0.95, 0.6, 73), ("d", (4, 1, 1), 0.99, 0.8, 1)]:
+        rewards = rng.normal(size=(B, T, 1)).astype(np.float32)
+        terminated = (rng.random((B, T, 1)) < 0.05).astype(np.float32)
+        mask = (rng.random((B, T, 1)) > 0.1).astype(np.float32)
+        target_qs = rng.normal(size=(B, T + 1, A)).astype(np.float32)
+        ret = ns["build_td_lambda_targets"](None, Tensor(rewards), Tensor(terminated), Tensor(mask), Tensor(target_qs),
+                                            gamma, lam, max_t)
+        ret = np.asarray(ret).view(np.ndarray)
+        assert ret.dtype == np.float32 and ret.shape == target_qs.shape
+        for k, v in dict(rewards=rewards, terminated=terminated, mask=mask, target_qs=target_qs, gamma=np.float64(gamma),
+                         td_lambda=np.float64(lam), max_t=np.int64(max_t), ret=ret).items():
+            cases[f"{name}/{k}"] = v
+    np.savez_compressed(OUT_COMA, **cases)
+    print("wrote", OUT_COMA, os.path.getsize(OUT_COMA), "bytes")
+
+
 def main():
+    make_mappo()
+    make_coma()
     make_vtrace()
     make_ppo()
     DR = load_reference()

@@ -99,3 +99,55 @@ def test_product_never_imports_the_oracle():
     from mindrl_b200 import _ffi
     out = subprocess.run(["ldd", _ffi.LIB_PATH], capture_output=True, text=True).stdout
     assert "oracle" not in out
+
+
+AOT_HEADER = os.path.join(ROOT, "include", "mindrl_b200_aot.h")
+
+
+def test_aot_header_symbols_are_exported(lib):
+    """every operator of include/mindrl_b200_aot.h exists as <Func> and <Func>Init -- the two symbols MindSpore's
+    ops.Custom("<so>:<Func>", ..., "aot") binds (reference: utils/mcts/cpu/cpu_mcts_ops.cc:38-53) -- and so do the
+    mrl_aot_extra_* helpers; the ctypes table mirrors the header"""
+    from mindrl_b200 import _ffi
+    text = re.sub(r"/\*.*?\*/", "", open(AOT_HEADER).read(), flags=re.S)
+    ops = re.findall(r"^MRL_AOT_OP\((\w+)\);", text, flags=re.M)
+    helpers = sorted(set(re.findall(r"\b(mrl_aot_[a-z0-9_]+)\s*\(", text)))
+    assert sorted(ops) == sorted(_ffi.AOT_OPS) and len(ops) == 10
+    out = subprocess.check_output(["nm", "-D", "--defined-only", _ffi.LIB_PATH], text=True)
+    exported = set(re.findall(r" T (\w+)", out))
+    for op in ops:
+        assert op in exported and op + "Init" in exported, op
+    assert set(helpers) <= exported
+    assert set(helpers) | set(ops) | {o + "Init" for o in ops} == set(_ffi.AOT_SIGNATURES)
+
+
+def test_aot_header_compiles_as_c(tmp_path):
+    src = tmp_path / "t.c"
+    src.write_text('#include "mindrl_b200_aot.h"\nint main(void){return 0;}\n')
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-c", str(src),
+                           "-o", str(tmp_path / "t.o")])
+
+
+def test_aot_attribute_reader_and_init_without_a_gpu(lib):
+    """the Init half of an AOT operator only reads attributes and shapes: it runs without a device.  The stand-in
+    AotExtra hands back what was registered; a bad registration is the reference's error code 2; the operator itself
+    fails loudly (2) when there is no device instead of computing anywhere else"""
+    from aot_host import AotOp
+    n = C.c_int(0)
+    no_gpu = not (lib.mrl_device_count(C.byref(n)) == 0 and n.value > 0)
+    good = AotOp("PriorityReplayBufferCreate", capacity=100, alpha=0.6, shapes=[[4], [1]], dtypes="float32,int32",
+                 seed0=1, seed1=2)
+    h = np.full(1, -5, dtype=np.int64)
+    rc = good([(h.ctypes.data, (1,), np.int64)])
+    assert good.init_rc == 0
+    if no_gpu:
+        assert rc == 2 and h[0] == -5
+    bad = AotOp("PriorityReplayBufferCreate", capacity=100, alpha=0.6, shapes=[[4], [1]], dtypes="float32",
+                seed0=1, seed1=2)
+    assert bad([(h.ctypes.data, (1,), np.int64)]) == 2 and bad.init_rc == 2
+    assert b"shapes and dtypes" in lib.mrl_last_error()
+    weird = AotOp("GaeScan", gamma=0.99, **{"lambda": 0.95}, layout=7)
+    x = np.zeros((4, 4), np.float32)
+    p = (x.ctypes.data, x.shape, np.float32)
+    d = (x.ctypes.data, x.shape, np.bool_)
+    assert weird([p, p, p, d, p, p]) == 2

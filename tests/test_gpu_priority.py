@@ -457,3 +457,91 @@ def test_update_shares_that_overflow_a_warp(pattern):
         g.update_priorities(dev(idx), dev(pr))
         o.update_priorities(idx, pr)
         same_tree(g, o)
+
+
+def test_c5_per_rank_shape_bit_exact():
+    """BASELINE config 5's per-rank shape on ONE GPU: capacity 1M (2^20 leaves), 40-byte rows, sample(4096) +
+    update_priorities(4096) -- the batch the sharded bench runs per rank.  Indices, weights, rows after every step
+    and the whole tree at the end, bit for bit against the oracle; both the internal generator and injected draws."""
+    rng = np.random.default_rng(55)
+    cap, batch = 1_000_000, 4096
+    shapes, types = [(4,), (1,), (1,), (4,)], [np.float32, np.int32, np.float32, np.float32]
+    g = M.PriorityReplayBuffer(ALPHA := 0.6, cap, batch, shapes, types, 7, 0)
+    o = O.PriorityBufferOracle(ALPHA, cap, batch, shapes, types, 7, 0)
+    rows = [rng.normal(size=(cap, 4)).astype(np.float32), rng.integers(0, 4, (cap, 1)).astype(np.int32),
+            rng.normal(size=(cap, 1)).astype(np.float32), rng.normal(size=(cap, 4)).astype(np.float32)]
+    g.insert(*[dev(c) for c in rows])
+    o.insert_batch(rows)
+    pr0 = (np.abs(rng.normal(size=cap)) + 1e-3).astype(np.float32)
+    g.update_priorities(dev(np.arange(cap)), dev(pr0))
+    o.update_priorities(np.arange(cap), pr0)
+    for step in range(6):
+        u = None if step % 2 else rng.random(batch).astype(np.float32)
+        got = g.sample(0.4, uniforms=None if u is None else dev(u))
+        want = o.sample(0.4, uniforms=u)
+        same_sample(got, want)
+        pr = (np.abs(rng.normal(size=batch)) + 1e-3).astype(np.float32)
+        if step == 3:  # duplicates inside one 4096-batch: the last writer wins
+            idx = host(got[0]).copy()
+            idx[1000:2000] = idx[:1000]
+            g.update_priorities(dev(idx), dev(pr))
+            o.update_priorities(idx, pr)
+        else:
+            g.update_priorities(got[0], dev(pr))
+            o.update_priorities(want[0], pr)
+    same_tree(g, o)
+
+
+def test_sample_of_an_empty_buffer_is_an_error():
+    """an empty buffer used to return index 0 and NaN weights silently"""
+    g = M.PriorityReplayBuffer(0.6, 100, 8, [(2,)], [np.float32])
+    with pytest.raises(_ffi.MindRLError) as e:
+        g.sample(0.4)
+    assert e.value.code == _ffi.MRL_ERR_STATE
+    o = O.PriorityBufferOracle(0.6, 100, 8, [(2,)], [np.float32])
+    with pytest.raises(RuntimeError):
+        o.sample(0.4)
+
+
+def test_indices_stay_below_size_and_match_their_rows():
+    """a mass that rounds past the total used to surface the raw (padding / unfilled) leaf as the index
+    while the row came from a clamped slot.  Now index, weight and row all belong to the newest valid row.  Draws
+    of exactly 1.0 - 2^-24 in the last stratum push the mass to (and, by rounding, past) the total."""
+    rng = np.random.default_rng(8)
+    for cap, fill in ((1000, 700), (1024, 1024), (5, 3)):
+        batch = 16
+        g = M.PriorityReplayBuffer(0.7, cap, batch, [(1,)], [np.int64])
+        o = O.PriorityBufferOracle(0.7, cap, batch, [(1,)], [np.int64])
+        rows = [np.arange(fill, dtype=np.int64)[:, None]]
+        g.insert(*[dev(c) for c in rows])
+        o.insert_batch(rows)
+        pr = (rng.random(fill) * 3 + 1e-3).astype(np.float32)
+        g.update_priorities(dev(np.arange(fill)), dev(pr))
+        o.update_priorities(np.arange(fill), pr)
+        for u_last in (np.float32(1.0) - np.float32(2.0 ** -24), np.float32(1.0)):  # 1.0 is outside [0,1): worst case
+            u = rng.random(batch).astype(np.float32)
+            u[-1] = u_last
+            got = g.sample(0.5, uniforms=dev(u))
+            want = o.sample(0.5, uniforms=u)
+            same_sample(got, want)
+            idx = host(got[0])
+            assert np.all(idx < fill) and np.all(idx >= 0)
+            assert np.array_equal(host(got[2]).reshape(-1), idx)
+            assert np.all(np.isfinite(host(got[1])))
+
+
+def test_host_update_rejects_indices_outside_the_buffer():
+    """mrl_prb_update_host wrote out of bounds for an index >= capacity"""
+    g = M.PriorityReplayBuffer(0.6, 5000, 8, [(2,)], [np.float32], carrier="numpy")
+    g.insert(np.zeros((5000, 2), np.float32))
+    before = g.tree()
+    for bad in (5000, 1 << 20, -1, 1 << 40):
+        idx = np.array([1, 2, bad, 3], dtype=np.int64)
+        with pytest.raises(ValueError):
+            g.update_priorities(idx, np.ones(4, np.float32))
+    after = g.tree()
+    assert np.array_equal(before[0], after[0]) and np.array_equal(before[1], after[1])
+    big = np.arange(600, dtype=np.int64)  # staged (not inline) path
+    big[-1] = 5000
+    with pytest.raises(ValueError):
+        g.update_priorities(big, np.ones(600, np.float32))

@@ -447,3 +447,155 @@ def test_host_scans_pipelined_in_pieces(chunks):
                 adv, ret = M.gae(r, v, 0.99, 0.95, next_value=nv, layout="batch_major", want_returns=False)
                 assert ret is None
                 close(adv, O.gae(r, v, nv, None, None, 0.99, 0.95, layout=1)[0])
+
+
+# ---- round 2: fixtures run by the reference's own statements, fused neighbours of the scan, graphs ---------
+def test_mappo_gae_golden(golden_dir):
+    """MAPPO's GAE block (mappo.py:478-500) as run by the reference's own statements: the sequential kernel gives
+    the reference's discounted_r bit for bit, the parallel kernels within the scans' tolerance"""
+    g = np.load(os.path.join(golden_dir, "mappo_gae_ref.npz"))
+    for n in sorted({k.split("/")[0] for k in g.files}):
+        reward, value, mask = g[f"{n}/reward"][..., 0], g[f"{n}/value"][..., 0], g[f"{n}/mask"][..., 0]
+        args = (dev(reward[1:]), dev(value[1:]), float(g[f"{n}/gamma"]), float(g[f"{n}/lam"]))
+        kw = dict(last_value=dev(g[f"{n}/last_value"][..., 0]), done=dev(1.0 - mask[1:]))
+        adv, ret = M.gae(*args, **kw, mode="sequential")
+        exact(ret, g[f"{n}/discounted_r"][1:, :, 0])
+        for mode in ("auto", "parallel"):
+            adv, ret = M.gae(*args, **kw, mode=mode)
+            close(ret, g[f"{n}/discounted_r"][1:, :, 0])
+            close(adv, g[f"{n}/advantage"][..., 0])
+
+
+def test_coma_td_lambda_golden(golden_dir):
+    """COMA's build_td_lambda_targets (coma.py:489-501) as run by the reference's own method: bit-exact"""
+    g = np.load(os.path.join(golden_dir, "coma_td_lambda_ref.npz"))
+    for n in sorted({k.split("/")[0] for k in g.files}):
+        got = M.td_lambda_targets(dev(g[f"{n}/rewards"]), dev(g[f"{n}/terminated"]), dev(g[f"{n}/mask"]),
+                                  dev(g[f"{n}/target_qs"]), float(g[f"{n}/gamma"]), float(g[f"{n}/td_lambda"]),
+                                  max_t=int(g[f"{n}/max_t"]))
+        exact(got, g[f"{n}/ret"])
+    # rewards / mask / terminated with a full agent axis, and against the oracle at a size the fixtures do not have
+    rng = np.random.default_rng(3)
+    B, T, A = 40, 200, 6
+    r, te = rng.normal(size=(B, T, A)).astype(np.float32), (rng.random((B, T, A)) < 0.03).astype(np.float32)
+    m, q = (rng.random((B, T, A)) > 0.1).astype(np.float32), rng.normal(size=(B, T + 1, A)).astype(np.float32)
+    exact(M.td_lambda_targets(dev(r), dev(te), dev(m), dev(q), 0.99, 0.8), O.td_lambda_targets(r, te, m, q, 0.99, 0.8))
+
+
+@pytest.mark.parametrize("T,B", [(1, 4), (5, 3), (20, 16), (100, 8), (64, 2048), (300, 4112), (2048, 256), (512, 40000)])
+def test_vtrace_fused_against_oracle(T, B):
+    """mrl_vtrace (exp, clips, deltas, recurrence, vs, pg advantages in the library) against the oracle's restatement
+    of vtrace.py:79-105 in all three modes; thresholds that clip, thresholds that do not, and no masks"""
+    rng = np.random.default_rng(T * 7 + B)
+    lr = (rng.normal(size=(T, B)) * 0.7).astype(np.float32)
+    disc = (0.99 * (rng.random((T, B)) > 0.02)).astype(np.float32)
+    r, v = rng.normal(size=(T, B)).astype(np.float32), rng.normal(size=(T, B)).astype(np.float32)
+    boot = rng.normal(size=(B,)).astype(np.float32)
+    masks = (rng.random((T, B)) > 0.1).astype(np.float32)
+    for clips, mk in (((1.0, 1.0, 1.0), masks), ((1.5, 2.0, 0.9), masks), ((None, None, None), None)):
+        want_vs, want_pg = O.vtrace(lr, disc, r, v, boot, *clips, mk)
+        for mode in ("auto", "sequential", "parallel"):
+            vs, pg = M.get_vs_and_advantages(dev(lr), dev(disc), dev(r), dev(v), dev(boot), *clips,
+                                             None if mk is None else dev(mk), mode=mode)
+            close(vs, want_vs)
+            close(pg, want_pg)
+
+
+@pytest.mark.parametrize("layout,T,B,with_done", [("time_major", 2048, 4096, True), ("time_major", 300, 4112, False),
+                                                  ("time_major", 1000, 96, True), ("batch_major", 2048, 512, True),
+                                                  ("batch_major", 1024, 300, False), ("batch_major", 130, 17, True),
+                                                  ("time_major", 5, 3, True)])
+def test_gae_with_fused_normalisation(layout, T, B, with_done):
+    """gae(normalize=True): moments accumulated by the scan kernel while it stores (TMA strips / rows) or in a
+    separate pass (the other kernels) -- either way equal to normalising the un-normalised result in float64, and
+    the returns are untouched (ppo.py:353-368)"""
+    rng = np.random.default_rng(T + B)
+    shape = (T, B) if layout == "time_major" else (B, T)
+    r, v = rng.normal(size=shape).astype(np.float32), rng.normal(size=shape).astype(np.float32)
+    lv = rng.normal(size=(B,)).astype(np.float32)
+    d = (rng.random(shape) < 0.01) if with_done else None
+    kw = dict(last_value=dev(lv), done=None if d is None else dev(d), layout=layout)
+    adv, ret = M.gae(dev(r), dev(v), 0.99, 0.95, **kw)
+    nadv, nret = M.gae(dev(r), dev(v), 0.99, 0.95, **kw, normalize=True)
+    exact(nret, ret.cpu().numpy())
+    a = adv.cpu().numpy()
+    a64 = a.astype(np.float64)
+    want = (a - np.float32(a64.mean())) * (np.float32(1.0) / (np.sqrt(np.float32(a64.var())) + np.float32(1e-8)))
+    assert np.allclose(nadv.cpu().numpy(), want, rtol=3e-6, atol=3e-6)
+    again, _ = M.gae(dev(r), dev(v), 0.99, 0.95, **kw, normalize=True)
+    exact(again, nadv.cpu().numpy())  # fixed accumulation order
+    # A2C: returns + normalisation (a2c.py:189-192)
+    if layout == "time_major" and d is not None:
+        out = M.DiscountedReturn(0.99)(dev(r), dev(d), dev(lv)).cpu().numpy()
+        o64 = out.astype(np.float64)
+        want = (out - np.float32(o64.mean())) * (np.float32(1.0) / (np.sqrt(np.float32(o64.var())) + np.float32(1e-8)))
+        got = M.discounted_return_normalized(dev(r), dev(d), dev(lv), 0.99).cpu().numpy()
+        assert np.allclose(got, want, rtol=3e-6, atol=3e-6)
+
+
+@pytest.mark.parametrize("T,B", [(1000, 96), (2048, 128), (2048, 4096), (513, 36)])
+def test_scans_replay_in_a_cuda_graph(T, B):
+    """the look-back kernels kept their epoch / ticket base on the host and could not be captured.
+    They now advance both in the workspace (last CTA), so a captured mrl_gae / mrl_discounted_return replays:
+    look-back shapes (B < 2048 or unaligned) and TMA-strip shapes, fresh inputs on every replay, oracle each time."""
+    rng = np.random.default_rng(T * B)
+    r_d = torch.zeros((T, B), device="cuda")
+    v_d = torch.zeros((T + 1, B), device="cuda")
+    d_d = torch.zeros((T, B), dtype=torch.bool, device="cuda")
+
+    def fresh():
+        r = rng.normal(size=(T, B)).astype(np.float32)
+        v = rng.normal(size=(T + 1, B)).astype(np.float32)
+        d = rng.random((T, B)) < 0.01
+        r_d.copy_(torch.from_numpy(r)), v_d.copy_(torch.from_numpy(v)), d_d.copy_(torch.from_numpy(d))
+        return O.gae(r, v[:T], None, v[T], d, 0.99, 0.95, layout=0), O.discounted_return(r, d, v[T], 0.99)
+
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        want = fresh()
+        adv, ret = M.gae(r_d, v_d[:T], 0.99, 0.95, last_value=v_d[T], done=d_d)  # eager: allocates the workspaces
+        dr = M.DiscountedReturn(0.99)(r_d, d_d, v_d[T])
+        M.gae(r_d, v_d[:T], 0.99, 0.95, last_value=v_d[T], done=d_d, normalize=True)
+        close(adv, want[0][0]), close(dr, want[1])
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=s):
+            adv, ret = M.gae(r_d, v_d[:T], 0.99, 0.95, last_value=v_d[T], done=d_d)
+            dr = M.DiscountedReturn(0.99)(r_d, d_d, v_d[T])
+            nadv, _ = M.gae(r_d, v_d[:T], 0.99, 0.95, last_value=v_d[T], done=d_d, normalize=True)
+        for _ in range(4):
+            want = fresh()
+            graph.replay()
+            torch.cuda.synchronize()
+            close(adv, want[0][0]), close(ret, want[0][1]), close(dr, want[1])
+            a = want[0][0].astype(np.float64)
+            assert np.allclose(nadv.cpu().numpy(), (want[0][0] - a.mean()) / (a.std() + 1e-8), rtol=1e-4, atol=1e-4)
+        # and eager launches still work on the same stream after the replays (the state lives in the workspace)
+        want = fresh()
+        adv2, _ = M.gae(r_d, v_d[:T], 0.99, 0.95, last_value=v_d[T], done=d_d)
+        close(adv2, want[0][0])
+
+
+def test_scans_on_two_streams_at_once():
+    """the look-back workspace, epoch and ticket base were process-global, so two scans in flight on
+    different streams corrupted each other (or hung).  Workspaces are per (device, stream) now: interleave many
+    launches of a look-back shape on two streams without synchronising in between."""
+    rng = np.random.default_rng(99)
+    T, B = 1500, 160  # look-back kernels (B < 2048)
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    data = []
+    for k in range(2):
+        r, v = rng.normal(size=(T, B)).astype(np.float32), rng.normal(size=(T + 1, B)).astype(np.float32)
+        d = rng.random((T, B)) < 0.01
+        data.append((dev(r), dev(v), dev(d), O.gae(r, v[:T], None, v[T], d, 0.99, 0.95, layout=0)))
+    torch.cuda.synchronize()
+    outs = [[], []]
+    for it in range(30):
+        for k in range(2):
+            with torch.cuda.stream(streams[k]):
+                r, v, d, _ = data[k]
+                outs[k].append(M.gae(r, v[:T], 0.99, 0.95, last_value=v[T], done=d))
+    torch.cuda.synchronize()
+    for k in range(2):
+        for adv, ret in outs[k]:
+            close(adv, data[k][3][0]), close(ret, data[k][3][1])

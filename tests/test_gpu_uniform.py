@@ -303,3 +303,33 @@ def test_large_host_batches_go_straight_into_the_ring():
     u = rng.random(16).astype(np.float32)
     got, want = pg.sample(0.4, uniforms=u), po.sample(0.4, uniforms=u)
     assert np.array_equal(got[0], want[0]) and np.array_equal(got[2], want[2]) and np.array_equal(got[3], want[3])
+
+
+@pytest.mark.parametrize("carrier", ["device", "numpy"])
+def test_c1_dqn_shape_loop_bit_exact(carrier):
+    """BASELINE config 1 at its own size: capacity 100 000, batch 64, the DQN loop's {insert 1 row, sample 64} --
+    through the fill phase (count < capacity), the moment the ring gets full, and the wrap-around after it.
+    Cursors after every step; drawn rows bit-exact; whole columns at the three phase boundaries."""
+    rng = np.random.default_rng(21)
+    cap, batch = 100_000, 64
+    g = M.UniformReplayBuffer(batch, cap, SHAPES, TYPES, seed=5, carrier=carrier)
+    o = O.UniformBufferOracle(batch, cap, SHAPES, TYPES, seed=5)
+    to = (lambda a: dev(a)) if carrier == "device" else (lambda a: a)
+    pre = rows(rng, cap - 150)
+    g.insert([to(c) for c in pre])
+    o.insert(pre)
+    steps = rows(rng, 400)
+    for i in range(400):
+        g.insert([to(c[i]) for c in steps])
+        o.insert([c[i] for c in steps])
+        assert (int(g.count), int(g.head)) == o.state()
+        got = g.sample()
+        _, want = o.sample()
+        for a, b in zip(got, want):
+            assert np.array_equal(a.cpu().numpy() if hasattr(a, "cpu") else a, b)
+        if i in (0, 149, 150, 399):
+            same_columns(g, o) if carrier == "device" else None
+    assert bool(g.full()[0]) and o.state() == (cap, 250)
+    for index in (0, -1, cap - 1, 12345):
+        for a, b in zip(g.get_item(index), o.get_item(index)):
+            assert np.array_equal((a.cpu().numpy() if hasattr(a, "cpu") else np.asarray(a)).reshape(-1), np.asarray(b).reshape(-1))

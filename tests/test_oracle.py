@@ -352,3 +352,78 @@ def test_fill_rows_at_is_a_row_subset_of_fill_rows():
             assert np.array_equal(full[:, :8].copy().view(np.int64)[:, 0], np.arange(300))
     big = O.fill_rows_at(np.array([999_999, 1 << 33], dtype=np.int64), 16, 5)  # row numbers beyond any test buffer
     assert big[:, :8].copy().view(np.int64)[:, 0].tolist() == [999_999, 1 << 33]
+
+
+def test_mappo_gae_golden_bit_exact(golden_dir):
+    """the GAE block of MAPPOLearner.learn (mappo.py:478-500), run by the reference's own statements
+    (tests/golden/make_golden.py::make_mappo): steps 1..25 of the [26, B, 1] arrays with V_26 = critic(last obs).
+    The reference's discounted_r is our `ret` bit for bit; its advantage is (discounted_r - V), formed afterwards."""
+    g = np.load(os.path.join(golden_dir, "mappo_gae_ref.npz"))
+    names = sorted({k.split("/")[0] for k in g.files})
+    assert len(names) == 4
+    for n in names:
+        reward, value, mask = g[f"{n}/reward"][..., 0], g[f"{n}/value"][..., 0], g[f"{n}/mask"][..., 0]
+        last = g[f"{n}/last_value"][..., 0]
+        adv, ret = O.gae(reward[1:], value[1:], None, last, 1.0 - mask[1:], float(g[f"{n}/gamma"]), float(g[f"{n}/lam"]), layout=0)
+        dr = g[f"{n}/discounted_r"][..., 0]
+        assert np.array_equal(ret.view(np.uint32), dr[1:].view(np.uint32))
+        assert np.all(dr[0] == 0)  # never written by the reference loop
+        assert np.array_equal((ret - value[1:]).view(np.uint32), g[f"{n}/advantage"][..., 0].view(np.uint32))
+        assert np.allclose(adv, g[f"{n}/advantage"][..., 0], rtol=0, atol=2e-6)  # (gae + V) - V against gae itself
+
+
+def test_coma_td_lambda_golden_bit_exact(golden_dir):
+    """COMALearner.build_td_lambda_targets (coma.py:489-501) run by the reference's own method
+    (make_golden.py::make_coma) against the oracle's restatement"""
+    g = np.load(os.path.join(golden_dir, "coma_td_lambda_ref.npz"))
+    names = sorted({k.split("/")[0] for k in g.files})
+    assert len(names) == 4
+    for n in names:
+        got = O.td_lambda_targets(g[f"{n}/rewards"], g[f"{n}/terminated"], g[f"{n}/mask"], g[f"{n}/target_qs"],
+                                  float(g[f"{n}/gamma"]), float(g[f"{n}/td_lambda"]), int(g[f"{n}/max_t"]))
+        assert np.array_equal(got.view(np.uint32), g[f"{n}/ret"].view(np.uint32)), n
+
+
+def test_vtrace_golden_through_the_whole_oracle(golden_dir):
+    """vtrace.py:79-105 run by the reference's own module against the oracle's restatement of all of it (exp, clips,
+    deltas, recurrence, vs, pg advantages); numpy's exp and libm's expf may differ in the last bit"""
+    g = np.load(os.path.join(golden_dir, "vtrace_ref.npz"))
+    for n in sorted({k.split("/")[0] for k in g.files}):
+        args = [g[f"{n}/{k}"] for k in ("log_rhos", "discounts", "rewards", "values", "boot")]
+        vs, pg = O.vtrace(*args, 1.0, 1.0, 1.0, g[f"{n}/masks"])
+        for got, want in ((vs, g[f"{n}/vs"]), (pg, g[f"{n}/pg"])):
+            assert np.abs(got - want).max() <= 1e-5 * max(1.0, float(np.abs(want).max()))
+
+
+def test_priority_pow_and_weights_against_an_independent_float64_restatement():
+    """include/mrl_arith.h (mrl_detpowf, mrl_priority_pow, mrl_is_weight) is compiled into BOTH the
+    CUDA library and this oracle, so GPU-vs-oracle parity of p**alpha and of the importance weights compares a
+    source with itself.  This test restates both from the published formulas in numpy float64 WITHOUT that
+    header -- PER (Schaul et al. 2015, cited at priority_replay_buffer.py:33):
+        leaf = priority ** alpha;  P(i) = leaf_i / sum;  w_i = (N * P(i)) ** -beta / max_j w_j,
+        max_j w_j = (N * min_leaf / sum) ** -beta
+    -- and checks the oracle's tree leaves and weights against it: leaves equal the correctly rounded float32 of
+    the float64 power (the header's contract), weights agree to float32 rounding of the few fp32 steps."""
+    rng = np.random.default_rng(123)
+    cap, batch, alpha, beta = 4096, 256, 0.6, 0.4
+    o = O.PriorityBufferOracle(alpha, cap, batch, [(1,)], [np.int32], 1, 2)
+    o.insert_batch([np.arange(cap, dtype=np.int32)[:, None]])
+    pr = (np.abs(rng.normal(size=cap)) * 5 + 1e-3).astype(np.float32)
+    o.update_priorities(np.arange(cap), pr)
+    leaves64 = np.power(pr.astype(np.float64), np.float64(np.float32(alpha)))
+    s, m = o.tree()
+    assert np.array_equal(s[cap:2 * cap], leaves64.astype(np.float32))       # correctly rounded pow, every leaf
+    assert abs(float(s[1]) - leaves64.sum()) <= 2e-6 * leaves64.sum()          # fp32 pairwise tree sum
+    assert float(m[1]) == float(leaves64.astype(np.float32).min())
+    u = rng.random(batch).astype(np.float32)
+    idx, w, _ = o.sample(beta, uniforms=u)
+    # stratified proportional draw, restated: stratum i covers mass [(i)/n, (i+1)/n) of the total
+    cum = np.cumsum(leaves64)
+    mass = (u.astype(np.float64) + np.arange(batch)) * (cum[-1] / batch)
+    want_idx = np.searchsorted(cum, mass, side="left")
+    agree = (want_idx == idx).mean()
+    assert agree >= 0.99, agree                                                # fp32 prefix sums move a boundary draw by one leaf
+    prob = leaves64[idx] / cum[-1]
+    w64 = np.power(prob * cap, -np.float64(np.float32(beta))) / np.power(leaves64.min() / cum[-1] * cap, -np.float64(np.float32(beta)))
+    assert np.allclose(w, w64, rtol=3e-6, atol=0)
+    assert w.max() <= 1.0 + 1e-6
