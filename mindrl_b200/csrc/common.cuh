@@ -26,12 +26,15 @@ extern std::atomic<int64_t> g_launches;
 
 inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// (a reported error is also CLEARED -- cudaGetLastError -- so that one failed call does not fail every later
+// launch check of the process)
 #define MRL_CUDA(expr)                                                                   \
   do {                                                                                   \
     cudaError_t _e = (expr);                                                             \
     if (_e != cudaSuccess) {                                                             \
       ::mrl::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
                        __LINE__);                                                        \
+      cudaGetLastError();                                                                \
       return MRL_ERR_CUDA;                                                               \
     }                                                                                    \
   } while (0)
@@ -48,7 +51,7 @@ inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s
 #define MRL_LAUNCHED()                          \
   do {                                          \
     ::mrl::g_launches.fetch_add(1);             \
-    MRL_CUDA(cudaPeekAtLastError());            \
+    MRL_CUDA(cudaGetLastError());               \
   } while (0)
 
 #ifdef __CUDACC__

@@ -354,8 +354,12 @@ static int launch_bulk(const ColTable &tab, const BulkPlan &plan, const int64_t 
   const size_t smem = (size_t)stage_bytes * STAGES;
   // (per device: the limit is a property of the function ON a device; always the most a CTA may take, so
   // one setting serves every stage size)
-  if (first_use_on_device((const void *)gather_bulk_kernel<STAGES>))
-    MRL_CUDA(cudaFuncSetAttribute(gather_bulk_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  if (first_use_on_device((const void *)gather_bulk_kernel<STAGES>)) {
+    cudaFuncAttributes fa;
+    MRL_CUDA(cudaFuncGetAttributes(&fa, gather_bulk_kernel<STAGES>));
+    MRL_CUDA(cudaFuncSetAttribute(gather_bulk_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  227 * 1024 - (int)fa.sharedSizeBytes));
+  }
   MRL_CUDA(launch_pdl(gather_bulk_kernel<STAGES>, dim3((unsigned)blocks), dim3(32), smem, st, tab, plan, slots,
                       capacity, stage_bytes));
   return MRL_OK;

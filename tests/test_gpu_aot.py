@@ -79,8 +79,9 @@ def test_priority_buffer_ops_against_oracle():
     update, destroy = AotOp("PriorityReplayBufferUpdate", handle=handle), AotOp("PriorityReplayBufferDestroy", handle=handle)
     rows = rows_of(rng, 500)
     out_h = torch.zeros(1, dtype=torch.int64, device="cuda")
+    drows = [dev(c) for c in rows]  # (kept alive: t() only takes pointers)
     for i in range(500):
-        assert push([t(dev(c[i])) for c in rows] + [t(out_h)], stream()) == 0
+        assert push([t(c[i]) for c in drows] + [t(out_h)], stream()) == 0
         o.insert(*[c[i] for c in rows])
     assert int(out_h.item()) == handle
     # the internal generator draws the uniforms on both sides (same seed, same counter)
@@ -96,7 +97,8 @@ def test_priority_buffer_ops_against_oracle():
         for a, b in zip(outs, want[2:]):
             assert np.array_equal(a.cpu().numpy(), b)
         pr = (np.abs(rng.normal(size=batch)) + 1e-3).astype(np.float32)
-        assert update([t(idx), t(dev(pr)), t(out_h)], stream()) == 0
+        pr_d = dev(pr)
+        assert update([t(idx), t(pr_d), t(out_h)], stream()) == 0
         o.update_priorities(want[0], pr)
     L = _ffi.lib()
     s_ = np.empty(2 * 4096, np.float32)
@@ -106,7 +108,7 @@ def test_priority_buffer_ops_against_oracle():
     assert np.array_equal(s_[1:], os_[1:]) and np.array_equal(m_[1:], om[1:])
     assert destroy([t(out_h)], stream()) == 0
     assert L.mrl_prb_info(handle, None, None, None) == _ffi.MRL_ERR_HANDLE  # the handle is gone
-    assert update([t(idx), t(dev(pr)), t(out_h)], stream()) == 2            # kErrorCode of the reference's ops
+    assert update([t(idx), t(pr_d), t(out_h)], stream()) == 2               # kErrorCode of the reference's ops
 
 
 def test_discounted_return_and_gae_ops():
@@ -126,7 +128,8 @@ def test_discounted_return_and_gae_ops():
     lv = rng.normal(size=(B, E)).astype(np.float32)
     out = torch.empty((T, B, E), device="cuda")
     op2 = AotOp("DiscountedReturn", gamma=0.97)
-    assert op2([t(dev(rw)), t(dev(dn)), t(dev(lv)), t(out)], stream()) == 0
+    keep = [dev(rw), dev(dn), dev(lv)]
+    assert op2([t(x) for x in keep] + [t(out)], stream()) == 0
     want = O.discounted_return(rw, dn, lv, 0.97)
     assert np.abs(out.cpu().numpy() - want).max() <= 1e-5 * max(1.0, float(np.abs(want).max()))
 
@@ -138,8 +141,8 @@ def test_discounted_return_and_gae_ops():
     for normalize in (False, True):
         g = AotOp("GaeScan", gamma=0.99, **{"lambda": 0.95}, layout=0, normalize=normalize)
         adv, ret = torch.empty((T, B), device="cuda"), torch.empty((T, B), device="cuda")
-        vd = dev(v)
-        assert g([t(dev(rw)), t(vd[:T]), t(vd[T]), t(dev(dn)), t(adv), t(ret)], stream()) == 0
+        vd, rd, dd = dev(v), dev(rw), dev(dn)
+        assert g([t(rd), t(vd[:T]), t(vd[T]), t(dd), t(adv), t(ret)], stream()) == 0
         want = adv_ref
         if normalize:
             a64 = adv_ref.astype(np.float64)
@@ -152,6 +155,7 @@ def test_bad_calls_return_the_reference_error_code():
     op = AotOp("BufferSample", seed=1, unique=True)
     x = torch.zeros((8, 2), device="cuda")
     c = torch.zeros(1, dtype=torch.int32, device="cuda")
-    assert op([t(x), t(c), t(c), t(torch.zeros((2, 2), device="cuda"))], stream()) == 2
+    y = torch.zeros((2, 2), device="cuda")
+    assert op([t(x), t(c), t(c), t(y)], stream()) == 2
     bad = AotOp("BufferAppend")
     assert bad([t(x), t(c)], stream()) == 2  # parameter count does not fit buffer/exp/count/head/out
