@@ -221,9 +221,11 @@ int mrl_prb_sample_sharded(int64_t handle, int64_t n, float beta, const float *u
  *   2. (optional) mrl_prb_shard_set_mode
  *        1 = publish on mutation (default): the kernel that changes the tree (update_priorities' last CTA,
  *            push, the tail of a batched push / set_state) stores {root_sum, root_min, size}, tagged with the
- *            rank's mutation count, into every peer's mailbox; sample #j uses, for every peer, the
+ *            rank's mutation count, into the rank's own outbox, and a one-warp courier kernel on a side stream
+ *            of the handle carries the words into every peer's inbox; sample #j uses, for every peer, the
  *            statistics that peer had at ITS sample #j -- which landed a whole step earlier, so the sample
- *            step does not wait for the slowest rank unless that rank is more than a step behind.
+ *            step does not wait for the slowest rank unless that rank is more than a step behind, and neither
+ *            the sample nor the update kernel touches peer memory.
  *        0 = publish on sample (round 1): the sample kernel stores the statistics itself and waits for the
  *            matching words of all peers.
  *      Same results in both modes and as mrl_prb_root_stats + all-gather + mrl_prb_sample_sharded, PROVIDED

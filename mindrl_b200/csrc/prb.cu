@@ -50,20 +50,28 @@ struct PrbState {
   float pad[2];
 };
 
-// Peer-memory mailboxes of the sharded buffer.  Every rank owns [2][world][4] flag-in-payload words
-// {value bits, tag} (8-byte accesses are single-copy atomic: a reader that sees the tag sees the value) and
-// has every peer's mailbox mapped (CUDA IPC).  Two protocols share the words:
+// Peer-memory mailboxes of the sharded buffer.  Every rank owns an INBOX of [2][world][4] and an OUTBOX of [2][4]
+// flag-in-payload words {value bits, tag} (8-byte accesses are single-copy atomic: a reader that sees the tag
+// sees the value) in one allocation that every peer has mapped (CUDA IPC).  Two protocols share the words:
 //   kPublishOnMutation (default): whoever CHANGES a rank's tree -- the last CTA of the update kernel, the
-//       push kernel, the tail of a batched push / set_state -- stores that rank's {root_sum, root_min, size}
-//       straight into all peers' mailboxes, tag = the rank's mutation count.  sample #j reads slot (j-1)&1 and
-//       expects tag == its own mutation count: ranks run the same program (SPMD), so a peer's statistics "as of
-//       its own sample #j" are exactly its publication number <own mutation count>, and they landed a whole
-//       step before they are needed -- no wait in the sample step unless a peer is more than a step behind.
-//       Mutations issued after sample #j go to slot j&1, so a peer that runs ahead never overwrites what a
-//       slower rank has yet to read (it cannot pass ITS sample #j+1 before the slower rank has published the
-//       mutations that follow its sample #j, which are stream-ordered behind that sample).
-//   kPublishOnSample (round 1): the sample kernel itself stores the statistics, tag = sample call number, and
-//       waits for all peers' words of the same call: every step ends when the slowest rank has got there.
+//       push kernel, the tail of a batched push / set_state -- stores that rank's {root_sum, root_min, size},
+//       tag = the rank's mutation count, into the rank's OWN outbox: a local store.  A one-warp COURIER kernel on
+//       a side stream of the handle (ordered behind the mutating kernel by an event) then copies the outbox words
+//       into every peer's inbox over NVLink.  Neither the update nor the sample kernel ever touches peer memory:
+//       measured (round 2, 2 GPUs), pushing the words from the update kernel itself made that kernel 2 us longer
+//       (it cannot retire before the NVLink writes are acknowledged), and pulling them from the sample kernel
+//       (remote loads issued before the descent) cost the step 6 us -- a kernel that has touched peer memory
+//       retires late, whenever in its life it did so.  The courier's 2 us are off the critical path.
+//       sample #j reads slot (j-1)&1 of its LOCAL inbox and expects tag == its own mutation count: ranks run the
+//       same program (SPMD), so a peer's statistics "as of its own sample #j" are exactly its publication number
+//       <own mutation count>, delivered a whole step before they are needed -- no wait in the sample step unless
+//       a peer is more than a step behind.  Mutations issued after sample #j go to slot j&1 (outbox and inbox),
+//       so a peer that runs ahead never overwrites what a slower rank has yet to read: it cannot pass ITS sample
+//       #j+1 before the slower rank's courier has delivered the mutations that follow its sample #j, which are
+//       ordered behind that sample.  For the same reason an outbox slot is never rewritten before its courier ran.
+//   kPublishOnSample (round 1): the sample kernel itself pushes the statistics into all peers' inboxes, tag =
+//       sample call number, and waits for all peers' words of the same call: every step ends when the slowest
+//       rank has got there.
 // Contract of both: all calls on a sharded handle go to ONE stream, every rank issues the same sequence of
 // sample / mutating calls.  A poll that sees nothing for `shard_timeout_ms` gives up, raises the link's error
 // word (mapped host memory) and the next call on the handle returns MRL_ERR_STATE.
@@ -87,27 +95,49 @@ struct ShardLink {
   ShardDiag *diag = nullptr;
   int *err_host = nullptr;      // pinned + mapped: raised by a kernel whose poll timed out
   int *err_dev = nullptr;
+  cudaStream_t courier = nullptr;  // side stream of the courier kernels
+  cudaEvent_t mutated = nullptr;   // recorded behind every mutating kernel, awaited by the courier
 };
 long long g_shard_timeout_ns = 10000000000ll;  // option "shard_timeout_ms" [10000]
 
 // what a kernel needs to publish the root statistics (all zero = not sharded / not this protocol)
 struct PublishArgs {
-  uint2 *const *peers = nullptr;
+  uint2 *const *peers = nullptr;  // kPublishOnSample: push into every rank's inbox
+  uint2 *outbox = nullptr;        // kPublishOnMutation: this rank's own outbox [2][4]
   int32_t rank = 0, world = 0;
   uint32_t slot = 0, tag = 0;
   float size = 0.0f;
 };
-// lanes 0..world-1 of ONE warp: lane q stores this rank's three words into rank q's mailbox (NVLink peer
-// stores; relaxed, system scope -- the words validate themselves)
+// lanes of ONE warp.  Outbox: lane 0 stores this rank's three words locally.  Push: lane q stores them into rank
+// q's inbox (NVLink peer stores).  Relaxed, system scope -- the words validate themselves.
 __device__ __forceinline__ void publish_root(const PublishArgs &P, int lane, float root_sum, float root_min) {
-  if (P.peers && lane < P.world) {
-    uint2 *dst = P.peers[lane] + ((size_t)P.slot * P.world + P.rank) * 4;
+  uint2 *dst = nullptr;
+  if (P.outbox) {
+    if (lane == 0) dst = P.outbox + (size_t)P.slot * 4;
+  } else if (P.peers && lane < P.world) {
+    dst = P.peers[lane] + ((size_t)P.slot * P.world + P.rank) * 4;
+  }
+  if (dst) {
     const float vals[3] = {root_sum, root_min, P.size};
 #pragma unroll
     for (int q = 0; q < 3; ++q)
       asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1,%2};" ::"l"(dst + q), "r"(__float_as_uint(vals[q])),
                    "r"(P.tag)
                    : "memory");
+  }
+}
+// the courier: lane q copies this rank's outbox words of `slot` into rank q's inbox (side stream)
+__global__ void __launch_bounds__(32)
+    prb_courier_kernel(const uint2 *outbox, uint2 *const *peers, int rank, int world, unsigned int slot) {
+  const int q = threadIdx.x;
+  if (q >= world || q == rank) return;
+  const uint2 *src = outbox + (size_t)slot * 4;
+  uint2 *dst = peers[q] + ((size_t)slot * world + rank) * 4;
+#pragma unroll
+  for (int w = 0; w < 3; ++w) {
+    uint2 v;
+    asm volatile("ld.relaxed.sys.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(src + w) : "memory");
+    asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1,%2};" ::"l"(dst + w), "r"(v.x), "r"(v.y) : "memory");
   }
 }
 
@@ -182,7 +212,7 @@ struct SampleArgs {
   long long *dbg;
   // sharded, peer-memory exchange (mailbox == NULL: off)
   PublishArgs pub;       // kPublishOnSample: this kernel stores the rank's statistics itself (pub.peers != NULL)
-  const uint2 *mailbox;  // this rank's mailbox
+  uint2 *mailbox;        // this rank's mailbox (inbox first)
   uint32_t slot, expect; // words to read: slot, and the tag they must carry
   ShardDiag *diag;
   int *err;              // raised when the poll times out
@@ -238,6 +268,18 @@ __global__ void __launch_bounds__(kSampleWarps * 32)
   // kPublishOnSample: this rank's root statistics go straight into every rank's mailbox now, so that the
   // NVLink latency hides behind the descent
   if (blockIdx.x == 0 && threadIdx.x < 32) publish_root(S.pub, threadIdx.x, root_sum, w_min);
+  // First look at the inbox NOW: with kPublishOnMutation the peers' words landed a step ago, so this look is
+  // normally the only one, and its latency (the lines were written over NVLink: an L2 miss, 0.4 us; 2 us when the
+  // 4096 warps of a C5-sized batch all ask for the same three words) runs behind the descent.
+  const bool polls = S.mailbox && lane < S.world && lane != S.pub.rank;
+  const uint2 *inbox = nullptr;
+  uint2 ia = make_uint2(0u, 0u), ib = ia, ic = ia;
+  if (polls) {
+    inbox = S.mailbox + ((size_t)S.slot * S.world + lane) * 4;
+    asm volatile("ld.relaxed.sys.global.v2.u32 {%0,%1}, [%2];" : "=r"(ia.x), "=r"(ia.y) : "l"(inbox) : "memory");
+    asm volatile("ld.relaxed.sys.global.v2.u32 {%0,%1}, [%2];" : "=r"(ib.x), "=r"(ib.y) : "l"(inbox + 1) : "memory");
+    asm volatile("ld.relaxed.sys.global.v2.u32 {%0,%1}, [%2];" : "=r"(ic.x), "=r"(ic.y) : "l"(inbox + 2) : "memory");
+  }
   const float u = S.uniforms ? __ldg(S.uniforms + i) : mrl_uniform01(S.seed, S.ctr + (uint64_t)i);
   float w_sum = root_sum, w_size = (float)S.size;
   if (S.gstats) {
@@ -377,16 +419,11 @@ __global__ void __launch_bounds__(kSampleWarps * 32)
     long long c0 = 0;
     if (timing) c0 = clock64();
     bool first_miss = false;
-    if (lane < S.world && lane != S.pub.rank) {
-      const uint2 *src = S.mailbox + ((size_t)S.slot * S.world + lane) * 4;
-      uint2 a, b, c;
+    if (polls) {
+      uint2 a = ia, b = ib, c = ic;
       long long t0 = 0;
       unsigned int spins = 0;
-      while (true) {
-        asm volatile("ld.relaxed.sys.global.v2.u32 {%0,%1}, [%2];" : "=r"(a.x), "=r"(a.y) : "l"(src) : "memory");
-        asm volatile("ld.relaxed.sys.global.v2.u32 {%0,%1}, [%2];" : "=r"(b.x), "=r"(b.y) : "l"(src + 1) : "memory");
-        asm volatile("ld.relaxed.sys.global.v2.u32 {%0,%1}, [%2];" : "=r"(c.x), "=r"(c.y) : "l"(src + 2) : "memory");
-        if (a.y == S.expect && b.y == S.expect && c.y == S.expect) break;
+      while (!(a.y == S.expect && b.y == S.expect && c.y == S.expect)) {
         first_miss = true;
         if ((++spins & 1023u) == 0u) {  // the global timer costs ~1 us to read: only on the slow path
           long long now;
@@ -399,6 +436,9 @@ __global__ void __launch_bounds__(kSampleWarps * 32)
             break;
           }
         }
+        asm volatile("ld.relaxed.sys.global.v2.u32 {%0,%1}, [%2];" : "=r"(a.x), "=r"(a.y) : "l"(inbox) : "memory");
+        asm volatile("ld.relaxed.sys.global.v2.u32 {%0,%1}, [%2];" : "=r"(b.x), "=r"(b.y) : "l"(inbox + 1) : "memory");
+        asm volatile("ld.relaxed.sys.global.v2.u32 {%0,%1}, [%2];" : "=r"(c.x), "=r"(c.y) : "l"(inbox + 2) : "memory");
       }
       ps = __uint_as_float(a.x), pm = __uint_as_float(b.x), pz = __uint_as_float(c.x);
     }
@@ -1347,7 +1387,8 @@ static PublishArgs make_publication(PrbBuffer *b, int64_t size_after, bool bump 
   PublishArgs P;
   ShardLink &k = b->link;
   if (k.peer_dev && k.mode == kPublishOnMutation) {
-    P.peers = k.peer_dev, P.rank = k.rank, P.world = k.world;
+    P.outbox = k.mailbox + (size_t)2 * k.world * 4;
+    P.rank = k.rank, P.world = k.world;
     P.slot = k.epoch & 1u;
     P.tag = bump ? ++k.version : k.version;
     P.size = (float)size_after;
@@ -1355,12 +1396,23 @@ static PublishArgs make_publication(PrbBuffer *b, int64_t size_after, bool bump 
   }
   return P;
 }
-static int publish_tail(PrbBuffer *b, cudaStream_t st, bool bump = true) {
-  const PublishArgs P = make_publication(b, b->size, bump);
-  if (!P.peers) return MRL_OK;
-  prb_publish_kernel<<<1, 32, 0, st>>>(b->sum, b->mn, P);
+// behind the kernel on `st` that has just written outbox slot P.slot: the courier on the handle's side stream
+// carries the words to the peers (nothing to do when P is empty or the rank is alone)
+static int dispatch_courier(PrbBuffer *b, const PublishArgs &P, cudaStream_t st) {
+  ShardLink &k = b->link;
+  if (!P.outbox || k.world < 2) return MRL_OK;
+  MRL_CUDA(cudaEventRecord(k.mutated, st));
+  MRL_CUDA(cudaStreamWaitEvent(k.courier, k.mutated, 0));
+  prb_courier_kernel<<<1, 32, 0, k.courier>>>(P.outbox, k.peer_dev, k.rank, k.world, P.slot);
   MRL_LAUNCHED();
   return MRL_OK;
+}
+static int publish_tail(PrbBuffer *b, cudaStream_t st, bool bump = true) {
+  const PublishArgs P = make_publication(b, b->size, bump);
+  if (!P.outbox) return MRL_OK;
+  prb_publish_kernel<<<1, 32, 0, st>>>(b->sum, b->mn, P);
+  MRL_LAUNCHED();
+  return dispatch_courier(b, P, st);
 }
 
 static int rebuild_range(PrbBuffer *b, int64_t lo, int64_t hi, cudaStream_t st) {
@@ -1393,12 +1445,12 @@ static int prb_push_batch_impl(PrbBuffer *b, int64_t nrows, void *const *src, cu
     ColTable tab;
     fill_table(tab, b, src);
     const int64_t size_after = b->size < cap ? b->size + 1 : b->size;
-    prb_push_kernel<<<1, 32, 0, st>>>(b->sum, b->mn, b->state, b->cap2, b->levels, slot, tab,
-                                      make_publication(b, size_after));
+    const PublishArgs P = make_publication(b, size_after);
+    prb_push_kernel<<<1, 32, 0, st>>>(b->sum, b->mn, b->state, b->cap2, b->levels, slot, tab, P);
     MRL_LAUNCHED();
     b->head = slot;
     b->size = size_after;
-    return MRL_OK;
+    return dispatch_courier(b, P, st);
   }
   const int64_t pos = (b->head + 1) % cap;
   const int64_t skip = nrows > cap ? nrows - cap : 0;
@@ -1546,7 +1598,7 @@ static int prb_update_impl(PrbBuffer *b, const int64_t *indices, const float *pr
     prb_update_kernel<<<1, 1024, 0, st>>>(U);
   }
   MRL_LAUNCHED();
-  return MRL_OK;
+  return dispatch_courier(b, U.pub, st);
 }
 
 }  // namespace mrl
@@ -1568,6 +1620,11 @@ static void link_free(PrbBuffer *b) {
   if (k.mailbox) cudaFree(k.mailbox);
   if (k.diag) cudaFree(k.diag);
   if (k.err_host) cudaFreeHost(k.err_host);
+  if (k.courier) {
+    cudaStreamSynchronize(k.courier);
+    cudaStreamDestroy(k.courier);
+  }
+  if (k.mutated) cudaEventDestroy(k.mutated);
   k = ShardLink();
 }
 
@@ -1923,7 +1980,7 @@ extern "C" int mrl_prb_shard_init(int64_t handle, int32_t rank, int32_t world, v
   link_free(b);
   ShardLink &k = b->link;
   k.rank = rank, k.world = world;
-  const size_t bytes = sizeof(uint2) * 2 * (size_t)world * 4;
+  const size_t bytes = sizeof(uint2) * (2 * (size_t)world * 4 + 2 * 4);  // inbox [2][world][4] + outbox [2][4]
   MRL_CUDA(cudaMalloc((void **)&k.mailbox, bytes));
   MRL_CUDA(cudaMemset(k.mailbox, 0, bytes));  // tag 0 never matches a call (tags start at 1)
   MRL_CUDA(cudaMalloc((void **)&k.diag, sizeof(ShardDiag)));
@@ -1931,6 +1988,8 @@ extern "C" int mrl_prb_shard_init(int64_t handle, int32_t rank, int32_t world, v
   MRL_CUDA(cudaHostAlloc((void **)&k.err_host, sizeof(int), cudaHostAllocMapped));
   *k.err_host = 0;
   MRL_CUDA(cudaHostGetDevicePointer((void **)&k.err_dev, k.err_host, 0));
+  MRL_CUDA(cudaStreamCreateWithFlags(&k.courier, cudaStreamNonBlocking));
+  MRL_CUDA(cudaEventCreateWithFlags(&k.mutated, cudaEventDisableTiming));
   MRL_CUDA(cudaDeviceSynchronize());
   cudaIpcMemHandle_t h;
   MRL_CUDA(cudaIpcGetMemHandle(&h, k.mailbox));

@@ -132,7 +132,9 @@ struct StripCfg {
 // of tile k+1 run while tile k is chained, replayed and stored (a lone group of 8 warps is latency-bound
 // on its own dependent chain).  The running carry passes between the groups through shared memory and
 // one mbarrier per tile parity.
-template <int OP, bool HD, int COLS, int RPU, int NG>
+// MOM: the kernel also accumulates the moments of `out` (ScanArgs.mom).  A template parameter, not a runtime
+// flag: the predicate alone in the replay loop cost the moment-less kernels 3 us of 25 (measured, round 2).
+template <int OP, bool HD, int COLS, int RPU, int NG, bool MOM>
 __global__ void __launch_bounds__((NG * kWarps + 1) * 32)
     scan_tm_strip_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_v,
                          const __grid_constant__ CUtensorMap tm_v1, const __grid_constant__ CUtensorMap tm_d,
@@ -195,9 +197,8 @@ __global__ void __launch_bounds__((NG * kWarps + 1) * 32)
     else X = l;
   }
   const bool want_ret = OP == OP_GAE && A.ret != nullptr;
-  const bool mom = NG == 1 && A.mom != nullptr;  // moments of `out` for the normalisation that follows
   const bool colok = col < A.N;
-  double msum = 0.0, msq = 0.0;
+  double msum = 0.0, msq = 0.0;  // (MOM) moments of `out` for the normalisation that follows
   float *my_out = ostage + warp * (n_obufs * C::kNOut * C::kWarpOut);
   int s = grp;  // (n_stages >= 2 >= NG)
   uint32_t ph = 0;
@@ -295,7 +296,7 @@ __global__ void __launch_bounds__((NG * kWarps + 1) * 32)
       x = fstep(ea[i], eb[i], x);
       oa[(h * RPU + i) * COLS + c] = x;
       if (want_ret) oa[C::kWarpOut + (h * RPU + i) * COLS + c] = __fadd_rn(x, aux[i]);
-      if (mom && colok && (k > 0 || (n_tiles - 1) * C::kRows + unit * RPU + i < T)) {
+      if (MOM && colok && (k > 0 || (n_tiles - 1) * C::kRows + unit * RPU + i < T)) {
         const double xd = (double)x;
         msum += xd;
         msq = fma(xd, xd, msq);
@@ -314,7 +315,7 @@ __global__ void __launch_bounds__((NG * kWarps + 1) * 32)
     s += NG;
     if (s >= n_stages) s -= n_stages, ph ^= 1u;
   }
-  if (NG == 1 && mom) {  // fixed-order fold: lanes, then the 8 warps in order -> one partial per CTA
+  if (MOM && NG == 1) {  // fixed-order fold: lanes, then the 8 warps in order -> one partial per CTA
 #pragma unroll
     for (int off = 16; off; off >>= 1) {
       msum += __shfl_xor_sync(0xffffffffu, msum, off);
@@ -381,7 +382,7 @@ bool make_map(CUtensorMap *m, const void *base, bool is_u8, int64_t rows, int64_
 
 bool al16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-template <int OP, bool HD, int COLS, int RPU, int NG>
+template <int OP, bool HD, int COLS, int RPU, int NG, bool MOM = false>
 int strip_launch(ScanArgs A, cudaStream_t st, int *mom_parts) {
   using C = StripCfg<OP, HD, COLS, RPU, NG>;
   static_assert(C::kRows <= 256 && C::smem_bytes(2, 1) <= (NG == 1 && RPU <= 16 ? 111 : 225) * 1024, "tile too large");
@@ -395,11 +396,12 @@ int strip_launch(ScanArgs A, cudaStream_t st, int *mom_parts) {
   mr = mo;
   if (OP == OP_GAE && A.ret && !make_map(&mr, A.ret, false, A.T, A.N, COLS, C::kWarpRows))
     return kScanNotApplicable;
-  if (first_use_on_device((const void *)scan_tm_strip_kernel<OP, HD, COLS, RPU, NG>))
-    MRL_CUDA(cudaFuncSetAttribute(scan_tm_strip_kernel<OP, HD, COLS, RPU, NG>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
   const int64_t n_strips = (A.N + COLS - 1) / COLS;
-  if (NG != 1 || n_strips > kMomentSlots) A.mom = nullptr;
+  if (MOM && n_strips > kMomentSlots) return strip_launch<OP, HD, COLS, RPU, NG, false>(A, st, mom_parts);
+  if (!MOM) A.mom = nullptr;
+  if (first_use_on_device((const void *)scan_tm_strip_kernel<OP, HD, COLS, RPU, NG, MOM>))
+    MRL_CUDA(cudaFuncSetAttribute(scan_tm_strip_kernel<OP, HD, COLS, RPU, NG, MOM>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
   const int n_tiles = (int)((A.T + C::kRows - 1) / C::kRows);
   if (RPU > 16 && n_strips > sm_count()) return kScanNotApplicable;  // 256-step tiles need the whole SM
   const int budget = ((NG == 2 || n_strips <= sm_count()) ? 226 : 112) * 1024 - 1024;
@@ -408,7 +410,7 @@ int strip_launch(ScanArgs A, cudaStream_t st, int *mom_parts) {
   stages = stages > kMaxStages ? kMaxStages : stages;
   stages = stages > n_tiles ? (n_tiles < 2 ? 2 : n_tiles) : stages;
   if (g_strip_stages > 0 && g_strip_stages < stages) stages = (int)(g_strip_stages < 2 ? 2 : g_strip_stages);
-  scan_tm_strip_kernel<OP, HD, COLS, RPU, NG><<<(unsigned)n_strips, C::kThreads, C::smem_bytes(stages, obufs), st>>>(
+  scan_tm_strip_kernel<OP, HD, COLS, RPU, NG, MOM><<<(unsigned)n_strips, C::kThreads, C::smem_bytes(stages, obufs), st>>>(
       ma, mv, mv1, md, mo, mr, A, n_tiles, stages, obufs);
   if (mom_parts) *mom_parts = A.mom ? (int)n_strips : 0;
   return MRL_OK;
@@ -416,9 +418,19 @@ int strip_launch(ScanArgs A, cudaStream_t st, int *mom_parts) {
 
 template <int OP, bool HD>
 int strip_launch_cols(const ScanArgs &A, int cols, int rpu, cudaStream_t st, int *mp) {
+  // moments (ScanArgs.mom) are produced by the default shapes of the two scans that get normalised afterwards
+  // (GAE: ppo.py:361-368; DiscountedReturn: a2c.py:190-192); any other configuration leaves them to a separate pass
+  if (A.mom && OP != OP_AFFINE && cols == 32 && g_strip_groups != 2) {
+    if (rpu == 32) {
+      const int rc = strip_launch<OP, HD, 32, 32, 1, OP != OP_AFFINE>(A, st, mp);
+      if (rc != kScanNotApplicable) return rc;
+      rpu = 16;
+    }
+    if (rpu == 16) return strip_launch<OP, HD, 32, 16, 1, OP != OP_AFFINE>(A, st, mp);
+  }
   // two consumer groups per CTA: opt-in (measured equal to one group at 4096 x 2048: once the ring is
   // deep enough the strips are bound by HBM, not by the consumers' dependent chain)
-  const bool two = g_strip_groups == 2 && !A.mom;
+  const bool two = g_strip_groups == 2;
   if (cols == 32 && rpu == 16 && two) return strip_launch<OP, HD, 32, 16, 2>(A, st, mp);
   if (cols == 32 && rpu == 32) {
     const int rc = strip_launch<OP, HD, 32, 32, 1>(A, st, mp);
@@ -489,7 +501,7 @@ struct RowCfg {
   }
 };
 
-template <int OP, bool HD, bool NVF>
+template <int OP, bool HD, bool NVF, bool MOM>
 __global__ void __launch_bounds__(kThreads)
     scan_bm_row_kernel(const __grid_constant__ ScanArgs A, int n_chunks, int n_stages) {
   using C = RowCfg<OP, HD, NVF>;
@@ -544,8 +556,7 @@ __global__ void __launch_bounds__(kThreads)
   // warp w owns positions [256w, 256w+256) of the tile, lane l the 8 consecutive steps 256w+8l..+7
   constexpr unsigned FULL = 0xffffffffu;
   const bool want_ret = OP == OP_GAE && A.ret != nullptr;
-  const bool mom = A.mom != nullptr;  // moments of `out` for the normalisation that follows
-  double msum = 0.0, msq = 0.0;
+  double msum = 0.0, msq = 0.0;  // (MOM) moments of `out` for the normalisation that follows
   const bool use_last = A.last != nullptr && !(OP == OP_GAE && NVF);
   float *my_out = ostage + warp * (2 * C::kNOut * C::kWarpOut);
   float X = 0.0f, v_after = 0.0f;
@@ -670,7 +681,7 @@ __global__ void __launch_bounds__(kThreads)
         o[q] = xe;
         o2[q] = __fadd_rn(xe, aux[q]);
       }
-      if (mom) {
+      if (MOM) {
 #pragma unroll
         for (int q = 0; q < 8; ++q)
           if (p0 + q < len) {
@@ -703,7 +714,7 @@ __global__ void __launch_bounds__(kThreads)
     if (++c == n_chunks) c = 0, row += G;
     if (++s == n_stages) s = 0, ph ^= 1u;
   }
-  if (mom) {  // fixed-order fold: lanes, then the 8 warps in order -> one partial per CTA
+  if (MOM) {  // fixed-order fold: lanes, then the 8 warps in order -> one partial per CTA
 #pragma unroll
     for (int off = 16; off; off >>= 1) {
       msum += __shfl_xor_sync(FULL, msum, off);
@@ -722,11 +733,12 @@ __global__ void __launch_bounds__(kThreads)
   if (lane == 0) bulk_wait_all();
 }
 
-template <int OP, bool HD, bool NVF>
-int row_launch(const ScanArgs &A, cudaStream_t st, int *mom_parts) {
+template <int OP, bool HD, bool NVF, bool MOM>
+int row_launch_m(ScanArgs A, cudaStream_t st, int *mom_parts) {
   using C = RowCfg<OP, HD, NVF>;
-  if (first_use_on_device((const void *)scan_bm_row_kernel<OP, HD, NVF>))
-    MRL_CUDA(cudaFuncSetAttribute(scan_bm_row_kernel<OP, HD, NVF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  if (!MOM) A.mom = nullptr;
+  if (first_use_on_device((const void *)scan_bm_row_kernel<OP, HD, NVF, MOM>))
+    MRL_CUDA(cudaFuncSetAttribute(scan_bm_row_kernel<OP, HD, NVF, MOM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   C::smem_bytes(kMaxStages) < 226 * 1024 ? C::smem_bytes(kMaxStages) : 226 * 1024));
   const int n_chunks = (int)((A.T + BM_L - 1) / BM_L);
   // ring depth: the SM's shared memory split between g_row_ctas_per_sm resident CTAs
@@ -741,9 +753,15 @@ int row_launch(const ScanArgs &A, cudaStream_t st, int *mom_parts) {
   const int64_t max_ctas = (int64_t)sm_count() * fit;
   const int64_t per = (A.N + max_ctas - 1) / max_ctas;
   const int64_t ctas = (A.N + per - 1) / per;
-  scan_bm_row_kernel<OP, HD, NVF><<<(unsigned)ctas, kThreads, smem, st>>>(A, n_chunks, stages);
-  if (mom_parts) *mom_parts = A.mom ? (int)ctas : 0;  // (ctas <= 7 * SMs < kMomentSlots)
+  scan_bm_row_kernel<OP, HD, NVF, MOM><<<(unsigned)ctas, kThreads, smem, st>>>(A, n_chunks, stages);
+  if (mom_parts) *mom_parts = MOM ? (int)ctas : 0;  // (ctas <= 7 * SMs < kMomentSlots)
   return MRL_OK;
+}
+
+template <int OP, bool HD, bool NVF>
+int row_launch(const ScanArgs &A, cudaStream_t st, int *mom_parts) {
+  if (A.mom && OP != OP_AFFINE) return row_launch_m<OP, HD, NVF, OP != OP_AFFINE>(A, st, mom_parts);
+  return row_launch_m<OP, HD, NVF, false>(A, st, mom_parts);
 }
 
 }  // namespace
