@@ -440,14 +440,27 @@ def bench_per(ctx, name, rows, batch, steps, warmup, primary, sharded=None, pari
         t_gather, _ = ctx.timed(only_gather, ksteps, 3)
         kern["gather_bulk_kernel"] = {"ms": t_gather / ksteps, "bytes": 2 * sum(rows[c] for c in wide) * batch}
         ffi.check(L.mrl_urb_destroy(uh.value))
+
+        # what the step actually launches for these rows: descent + DMA ring in ONE kernel
+        def only_sample_rows(i):
+            ffi.check(L.mrl_prb_sample(h, batch, BETA, None, idx.data_ptr(), w.data_ptr(), out_tab, st))
+
+        l0 = ffi.launch_count()
+        t_fused, _ = ctx.timed(only_sample_rows, ksteps, 3)
+        per_call = (ffi.launch_count() - l0) / (ksteps + 3)
+        kern["prb_sample_gather_kernel(descent+weights+row gather)"] = {
+            "ms": t_fused / ksteps, "bytes": (4 * L_1M + 16 + 2 * R) * batch, "launches_per_call": per_call}
     else:
         kern["prb_sample_kernel(descent+weights)"]["bytes"] += 0
     # the roofline is quoted for the bandwidth-bound kernel of the step when there is one (the row gather
     # of the Atari-shaped buffer), else for the slowest (latency-bound) tree kernel
-    dom = "gather_bulk_kernel" if "gather_bulk_kernel" in kern else max(kern, key=lambda k: kern[k]["ms"])
+    fused_key = "prb_sample_gather_kernel(descent+weights+row gather)"
+    dom = fused_key if fused_key in kern and kern[fused_key].get("launches_per_call") == 1 else (
+        "gather_bulk_kernel" if "gather_bulk_kernel" in kern else max(kern, key=lambda k: kern[k]["ms"]))
     ach = kern[dom]["bytes"] / (kern[dom]["ms"] * 1e-3) / 1e9
     tkey = ("c3:" if R > 512 else "c2:") + {"prb_sample_kernel(descent+weights)": "prb_sample_kernel",
-                                             "gather_bulk_kernel": "gather_bulk_kernel<4>"}.get(dom, dom)
+                                             "gather_bulk_kernel": "gather_bulk_kernel<4>",
+                                             fused_key: "prb_sample_gather_kernel<4>"}.get(dom, dom)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm, "unit": "GB/s",
                 "frac": ach / hbm, "traffic": ncu_traffic(tkey), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": kern[dom]["bytes"],
@@ -455,7 +468,9 @@ def bench_per(ctx, name, rows, batch, steps, warmup, primary, sharded=None, pari
                 "ncu": {k: ncu_latency_evidence(("c3:" if R > 512 else "c2:") + k)
                         for k in ("prb_sample_kernel", "prb_update_sub_kernel")},
                 "note": ("tree kernels are dependent-load latency bound (L2/HBM round trips), "
-                         "not bandwidth bound" if R <= 512 else "row gather is HBM-bandwidth bound")}
+                         "not bandwidth bound" if R <= 512 else
+                         "row gather is HBM-bandwidth bound; since round 2 the descent and the DMA ring are one kernel "
+                         "(kernel_ms also lists the former sample and gather kernels timed alone)")}
 
     # ---- e2e through the *_host entry points with pinned host buffers --------------------
     h_idx = pinned(ctx, (batch,), torch.int64)

@@ -82,6 +82,8 @@ int64_t mrl_launch_count(void);
 /* tunables (defaults in brackets; every one of them only selects among kernels that give the same results):
  *   "gather_path" [0] 0 auto, 1 register path only, 2 TMA ring whenever aligned; "bulk_min_row" [2048],
  *   "bulk_chunk" [8192], "bulk_ctas_per_sm" [4], "bulk_stages" [4] (2/4/8/12): the TMA-ring gather
+ *   "fused_gather" [1]: PER sample of wide (TMA-gathered) rows runs the descent and the DMA ring in ONE kernel when
+ *       the batch fits it (a CTA's share of the copy touches at most two samples: batch <= SMs * bulk_ctas_per_sm)
  *   "pdl" [1]: programmatic dependent launch of the PER sample / gather / update kernels
  *   "tree_prefetch" [1]: the PER sample / update kernels prefetch the tree lines of their later dependent
  *       round trips (depth 10 and 15 of the descent, depth 11 of the top rebuild) into L2 at kernel start

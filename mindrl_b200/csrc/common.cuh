@@ -159,6 +159,8 @@ int copy_segments(const ColTable &tab, int64_t dst_row, int64_t src_row, int64_t
 constexpr size_t kDirectHostBytes = 256 << 10;
 int copy_segments_dir(const ColTable &tab, int64_t ring_row, int64_t io_row, int64_t nrows,
                       int to_ring, cudaStream_t st);
+// tunables of the TMA-ring copies (copy.cu; options "gather_path", "bulk_*")
+extern int64_t g_gather_path, g_bulk_min_row, g_bulk_chunk, g_bulk_ctas_per_sm, g_bulk_stages;
 // mrl_prb_sample with beta read from DEVICE memory by the kernel (the AOT shim gets beta as a tensor)
 int prb_sample_beta_dev(int64_t handle, int64_t n, const float *beta_dev, int64_t *indices, float *weights,
                         void *const *out_cols, cudaStream_t st);

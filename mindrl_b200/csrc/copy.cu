@@ -14,7 +14,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
-#include "common.cuh"
+#include "bulk.cuh"
 
 namespace mrl {
 
@@ -161,53 +161,6 @@ struct BulkPlan {
   int64_t item_begin[MRL_MAX_COLS + 1];  // items of column k: [item_begin[k], item_begin[k+1])
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-               "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes,
-                                         uint64_t *bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
-          "r"(smem_u32(smem_dst)),
-      "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
-      : "memory");
-}
-__device__ __forceinline__ void bulk_s2g(void *gdst, const void *smem_src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
-               "r"(smem_u32(smem_src)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() {
-  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-
 struct BulkItem {
   const uint8_t *src;
   uint8_t *dst;
@@ -300,15 +253,16 @@ static int64_t env_i64(const char *name, int64_t dflt) {
   const char *e = getenv(name);
   return e ? atoll(e) : dflt;
 }
-static int64_t g_gather_path = env_i64("MRL_GATHER_PATH", 0);
-static int64_t g_bulk_min_row = env_i64("MRL_BULK_MIN_ROW", 2048);
-static int64_t g_bulk_chunk = env_i64("MRL_BULK_CHUNK", 8192);
-static int64_t g_bulk_ctas_per_sm = env_i64("MRL_BULK_CTAS_PER_SM", 4);
-static int64_t g_bulk_stages = env_i64("MRL_BULK_STAGES", 4);
+int64_t g_gather_path = env_i64("MRL_GATHER_PATH", 0);
+int64_t g_bulk_min_row = env_i64("MRL_BULK_MIN_ROW", 2048);
+int64_t g_bulk_chunk = env_i64("MRL_BULK_CHUNK", 8192);
+int64_t g_bulk_ctas_per_sm = env_i64("MRL_BULK_CTAS_PER_SM", 4);
+int64_t g_bulk_stages = env_i64("MRL_BULK_STAGES", 4);
 
 extern long long *g_debug_timers;  // prb.cu
 extern bool g_no_inline_update;    // prb.cu
 extern bool g_host_zero_copy;      // prb.cu
+extern bool g_fused_gather;        // prb.cu
 extern long long g_shard_timeout_ns;  // prb.cu
 bool g_pdl = true;                 // programmatic dependent launch of the PER-path kernels
 bool g_tree_prefetch = true;       // tree kernels pull the lines of their later round trips into L2 first
@@ -329,6 +283,10 @@ int set_copy_option(const char *key, int64_t value) {
   }
   if (k == "host_zero_copy" && (value == 0 || value == 1)) {
     g_host_zero_copy = value == 1;
+    return MRL_OK;
+  }
+  if (k == "fused_gather" && (value == 0 || value == 1)) {
+    g_fused_gather = value == 1;
     return MRL_OK;
   }
   if (k == "shard_timeout_ms" && value >= 1 && value <= 3600000) {

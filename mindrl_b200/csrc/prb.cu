@@ -40,7 +40,7 @@
 
 #include <utility>
 
-#include "common.cuh"
+#include "bulk.cuh"
 
 namespace mrl {
 
@@ -239,78 +239,26 @@ __device__ __forceinline__ float4 hop_load(const float *sum, int64_t node, int h
   return v;
 }
 
-__global__ void __launch_bounds__(kSampleWarps * 32)
-    prb_sample_kernel(const __grid_constant__ SampleArgs S, const __grid_constant__ ColTable tab) {
-  // Before anything is known about the masses: pull the lines the 2nd hop can land on (all of depth 14 =
-  // 64 KB) into L2, spread over the grid.  L2 is the point of coherence, so this may run ahead of the
-  // predecessor kernel (before griddepcontrol.wait); with a cold L2 one of the three dependent round
-  // trips of the descent becomes an L2 hit.
-  if (S.prefetch && S.levels > 2 * kHop) {
-    const int64_t gthreads = (int64_t)gridDim.x * blockDim.x;
-    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t lines = (1LL << (2 * kHop)) / 32;
-    for (int64_t q = gid; q < lines && q < gid + 4 * gthreads; q += gthreads)
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(S.sum + (1LL << (2 * kHop)) + 32 * q));
-  }
-  pdl_prologue();
-  dbg_mark(S.dbg, 0);
-  const int lane = threadIdx.x & 31;
-  const int64_t i = (int64_t)blockIdx.x * kSampleWarps + (threadIdx.x >> 5);
-  if (i >= S.n) return;
+// Warp descent from the root to the leaf that holds `mass`, h <= 7 levels per coalesced load of the 2^h
+// descendants h levels below the node (512 bytes: lane l holds descendants 4l..4l+3).  The sums in between are
+// rebuilt exactly as they are stored -- every parent is fl(left + right) -- two levels inside the lane, five with
+// shuffles; the walk then takes five shuffle-compare steps to the lane and two inside its quad.  20 levels = 3
+// dependent round trips.  (Staging the top 11 levels in shared memory first was measured slower: 3.3 us for the
+// staging alone against ~0.5 us per hop; the top lines are shared by all warps.)  hop0 = the first hop's line,
+// requested by the caller before the mass was known.  Returns the leaf (slot), its priority in leaf_p.
+__device__ __forceinline__ int64_t prb_descend(const float *sum, int levels, int64_t cap2, int64_t size, float mass,
+                                               const float4 hop0, float root_sum, int lane, float &leaf_p_out) {
   constexpr unsigned FULL = 0xffffffffu;
-
-  // everything that does not depend on the descent is requested first: the root, and the line of the
-  // first hop (its address does not depend on the mass)
-  const float root_sum = __ldcg(S.sum + 1);
-  float w_min = __ldcg(S.mn + 1);
-  float4 hop0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-  if (S.levels > 0) hop0 = hop_load(S.sum, 1, S.levels < kHop ? S.levels : kHop, lane);
-  // kPublishOnSample: this rank's root statistics go straight into every rank's mailbox now, so that the
-  // NVLink latency hides behind the descent
-  if (blockIdx.x == 0 && threadIdx.x < 32) publish_root(S.pub, threadIdx.x, root_sum, w_min);
-  // First look at the inbox NOW: with kPublishOnMutation the peers' words landed a step ago, so this look is
-  // normally the only one, and its latency (the lines were written over NVLink: an L2 miss, 0.4 us; 2 us when the
-  // 4096 warps of a C5-sized batch all ask for the same three words) runs behind the descent.
-  const bool polls = S.mailbox && lane < S.world && lane != S.pub.rank;
-  const uint2 *inbox = nullptr;
-  uint2 ia = make_uint2(0u, 0u), ib = ia, ic = ia;
-  if (polls) {
-    inbox = S.mailbox + ((size_t)S.slot * S.world + lane) * 4;
-    asm volatile("ld.relaxed.sys.global.v2.u32 {%0,%1}, [%2];" : "=r"(ia.x), "=r"(ia.y) : "l"(inbox) : "memory");
-    asm volatile("ld.relaxed.sys.global.v2.u32 {%0,%1}, [%2];" : "=r"(ib.x), "=r"(ib.y) : "l"(inbox + 1) : "memory");
-    asm volatile("ld.relaxed.sys.global.v2.u32 {%0,%1}, [%2];" : "=r"(ic.x), "=r"(ic.y) : "l"(inbox + 2) : "memory");
-  }
-  const float u = S.uniforms ? __ldg(S.uniforms + i) : mrl_uniform01(S.seed, S.ctr + (uint64_t)i);
-  float w_sum = root_sum, w_size = (float)S.size;
-  if (S.gstats) {
-    w_sum = 0.0f, w_min = FLT_MAX, w_size = 0.0f;
-    for (int r = 0; r < S.world; ++r) {
-      w_sum = __fadd_rn(w_sum, __ldg(S.gstats + 4 * r));
-      const float m = __ldg(S.gstats + 4 * r + 1);
-      w_min = m < w_min ? m : w_min;
-      w_size = __fadd_rn(w_size, __ldg(S.gstats + 4 * r + 2));
-    }
-  }
-  const float seg = __fdiv_rn(root_sum, (float)S.n);
-  float mass = __fmul_rn(__fadd_rn(u, (float)i), seg);
-  dbg_mark(S.dbg, 1);
-
-  // Warp hops from the root, h <= 7 levels per coalesced load of the 2^h descendants h levels below the
-  // node (512 bytes: lane l holds descendants 4l..4l+3).  The sums in between are rebuilt exactly as they
-  // are stored -- every parent is fl(left + right) -- two levels inside the lane, five with shuffles; the
-  // walk then takes five shuffle-compare steps to the lane and two inside its quad.  20 levels = 3
-  // dependent round trips.  (Staging the top 11 levels in shared memory first was measured slower: 3.3 us
-  // for the staging alone against ~0.5 us per hop; the top lines are shared by all warps.)
   int64_t node = 1;
   float leaf_p = root_sum;  // capacity 1: the root is the leaf
-  int remaining = S.levels;
+  int remaining = levels;
 #pragma unroll 1
   while (remaining > 0) {
     const int h = remaining < kHop ? remaining : kHop;
     const int wl = h > 5 ? h - 5 : 0;  // levels inside a lane (0, 1 or 2)
     const int hx = h - wl;             // levels across lanes
     const int64_t base = node << h;
-    const float4 v = node == 1 ? hop0 : hop_load(S.sum, node, h, lane);
+    const float4 v = node == 1 ? hop0 : hop_load(sum, node, h, lane);
     const float s01 = __fadd_rn(v.x, v.y), s23 = __fadd_rn(v.z, v.w);
     float p[6];
     p[0] = wl == 2 ? __fadd_rn(s01, s23) : (wl == 1 ? s01 : v.x);
@@ -355,11 +303,78 @@ __global__ void __launch_bounds__(kSampleWarps * 32)
   // A mass that rounds past the total walks into the empty part of the tree (leaves >= size, priority 0):
   // the newest valid leaf is returned instead, so that index, weight and row always belong together and
   // the index is safe to hand back to update_priorities (a decision of the parity checker too).
-  int64_t leaf = node - S.cap2;
-  if (leaf >= S.size) {
-    leaf = S.size - 1;
-    leaf_p = __ldcg(S.sum + S.cap2 + leaf);
+  int64_t leaf = node - cap2;
+  if (leaf >= size) {
+    leaf = size - 1;
+    leaf_p = __ldcg(sum + cap2 + leaf);
   }
+  leaf_p_out = leaf_p;
+  return leaf;
+}
+
+__global__ void __launch_bounds__(kSampleWarps * 32)
+    prb_sample_kernel(const __grid_constant__ SampleArgs S, const __grid_constant__ ColTable tab) {
+  // Before anything is known about the masses: pull the lines the 2nd hop can land on (all of depth 14 =
+  // 64 KB) into L2, spread over the grid.  L2 is the point of coherence, so this may run ahead of the
+  // predecessor kernel (before griddepcontrol.wait); with a cold L2 one of the three dependent round
+  // trips of the descent becomes an L2 hit.
+  if (S.prefetch && S.levels > 2 * kHop) {
+    const int64_t gthreads = (int64_t)gridDim.x * blockDim.x;
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t lines = (1LL << (2 * kHop)) / 32;
+    for (int64_t q = gid; q < lines && q < gid + 4 * gthreads; q += gthreads)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(S.sum + (1LL << (2 * kHop)) + 32 * q));
+  }
+  pdl_prologue();
+  dbg_mark(S.dbg, 0);
+  const int lane = threadIdx.x & 31;
+  // (warps past the end of the batch shadow its last sample -- same loads, same values stored -- instead of
+  // leaving: the sharded path meets at a block barrier)
+  const int64_t i_raw = (int64_t)blockIdx.x * kSampleWarps + (threadIdx.x >> 5);
+  const int64_t i = i_raw < S.n ? i_raw : S.n - 1;
+  constexpr unsigned FULL = 0xffffffffu;
+  __shared__ float s_tot[4];  // sharded: the global {sum, min, size}, formed by warp 0 of the CTA
+
+  // everything that does not depend on the descent is requested first: the root, and the line of the
+  // first hop (its address does not depend on the mass)
+  const float root_sum = __ldcg(S.sum + 1);
+  float w_min = __ldcg(S.mn + 1);
+  float4 hop0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  if (S.levels > 0) hop0 = hop_load(S.sum, 1, S.levels < kHop ? S.levels : kHop, lane);
+  // kPublishOnSample: this rank's root statistics go straight into every rank's mailbox now, so that the
+  // NVLink latency hides behind the descent
+  if (blockIdx.x == 0 && threadIdx.x < 32) publish_root(S.pub, threadIdx.x, root_sum, w_min);
+  // First look at the inbox NOW: with kPublishOnMutation the peers' words landed a step ago, so this look is
+  // normally the only one, and its latency (the lines were written over NVLink: an L2 miss, 0.4 us; 2 us when the
+  // 4096 warps of a C5-sized batch all ask for the same three words) runs behind the descent.
+  // ONE warp per CTA looks (every warp asking -- 4096 warps x 7 peers x 3 words at C5's batch on 8 GPUs -- made
+  // the sample kernel 4 us longer: they all hit the same few sectors); the CTA gets the totals through shared memory
+  const bool polls = S.mailbox && threadIdx.x < 32 && lane < S.world && lane != S.pub.rank;
+  const uint2 *inbox = nullptr;
+  uint2 ia = make_uint2(0u, 0u), ib = ia, ic = ia;
+  if (polls) {
+    inbox = S.mailbox + ((size_t)S.slot * S.world + lane) * 4;
+    asm volatile("ld.relaxed.sys.global.v2.u32 {%0,%1}, [%2];" : "=r"(ia.x), "=r"(ia.y) : "l"(inbox) : "memory");
+    asm volatile("ld.relaxed.sys.global.v2.u32 {%0,%1}, [%2];" : "=r"(ib.x), "=r"(ib.y) : "l"(inbox + 1) : "memory");
+    asm volatile("ld.relaxed.sys.global.v2.u32 {%0,%1}, [%2];" : "=r"(ic.x), "=r"(ic.y) : "l"(inbox + 2) : "memory");
+  }
+  const float u = S.uniforms ? __ldg(S.uniforms + i) : mrl_uniform01(S.seed, S.ctr + (uint64_t)i);
+  float w_sum = root_sum, w_size = (float)S.size;
+  if (S.gstats) {
+    w_sum = 0.0f, w_min = FLT_MAX, w_size = 0.0f;
+    for (int r = 0; r < S.world; ++r) {
+      w_sum = __fadd_rn(w_sum, __ldg(S.gstats + 4 * r));
+      const float m = __ldg(S.gstats + 4 * r + 1);
+      w_min = m < w_min ? m : w_min;
+      w_size = __fadd_rn(w_size, __ldg(S.gstats + 4 * r + 2));
+    }
+  }
+  const float seg = __fdiv_rn(root_sum, (float)S.n);
+  float mass = __fmul_rn(__fadd_rn(u, (float)i), seg);
+  dbg_mark(S.dbg, 1);
+
+  float leaf_p;
+  const int64_t leaf = prb_descend(S.sum, S.levels, S.cap2, S.size, mass, hop0, root_sum, lane, leaf_p);
   const int64_t slot = leaf;
   dbg_mark(S.dbg, 3);
 
@@ -414,49 +429,54 @@ __global__ void __launch_bounds__(kSampleWarps * 32)
     // the peer's matching sample kernel); this rank's own entry comes from its tree.  Then the totals are
     // formed in rank order (as the oracle does).  The poll is bounded: ADVICE r1 -- a rank that never makes
     // the matching call must not hang its peers' GPUs.
-    float ps = root_sum, pm = w_min, pz = (float)S.size;
-    const bool timing = S.diag && blockIdx.x == 0 && threadIdx.x == 0;
-    long long c0 = 0;
-    if (timing) c0 = clock64();
-    bool first_miss = false;
-    if (polls) {
-      uint2 a = ia, b = ib, c = ic;
-      long long t0 = 0;
-      unsigned int spins = 0;
-      while (!(a.y == S.expect && b.y == S.expect && c.y == S.expect)) {
-        first_miss = true;
-        if ((++spins & 1023u) == 0u) {  // the global timer costs ~1 us to read: only on the slow path
-          long long now;
-          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-          if (t0 == 0) t0 = now;
-          if (now - t0 > S.timeout_ns) {
-            if (S.err) *reinterpret_cast<volatile int *>(S.err) = 1 + lane;  // which peer was missing
-            if (S.diag && blockIdx.x == 0 && threadIdx.x < 32) atomicAdd(&S.diag->timeouts, 1ull);
-            a.x = b.x = c.x = 0x7fc00000u;  // NaN: the weights of this call are void
-            break;
+    if (threadIdx.x < 32) {
+      float ps = root_sum, pm = w_min, pz = (float)S.size;
+      const bool timing = S.diag && blockIdx.x == 0 && threadIdx.x == 0;
+      long long c0 = 0;
+      if (timing) c0 = clock64();
+      bool first_miss = false;
+      if (polls) {
+        uint2 a = ia, b = ib, c = ic;
+        long long t0 = 0;
+        unsigned int spins = 0;
+        while (!(a.y == S.expect && b.y == S.expect && c.y == S.expect)) {
+          first_miss = true;
+          if ((++spins & 1023u) == 0u) {  // the global timer costs ~1 us to read: only on the slow path
+            long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            if (now - t0 > S.timeout_ns) {
+              if (S.err) *reinterpret_cast<volatile int *>(S.err) = 1 + lane;  // which peer was missing
+              if (S.diag && blockIdx.x == 0 && threadIdx.x < 32) atomicAdd(&S.diag->timeouts, 1ull);
+              a.x = b.x = c.x = 0x7fc00000u;  // NaN: the weights of this call are void
+              break;
+            }
           }
+          asm volatile("ld.relaxed.sys.global.v2.u32 {%0,%1}, [%2];" : "=r"(a.x), "=r"(a.y) : "l"(inbox) : "memory");
+          asm volatile("ld.relaxed.sys.global.v2.u32 {%0,%1}, [%2];" : "=r"(b.x), "=r"(b.y) : "l"(inbox + 1) : "memory");
+          asm volatile("ld.relaxed.sys.global.v2.u32 {%0,%1}, [%2];" : "=r"(c.x), "=r"(c.y) : "l"(inbox + 2) : "memory");
         }
-        asm volatile("ld.relaxed.sys.global.v2.u32 {%0,%1}, [%2];" : "=r"(a.x), "=r"(a.y) : "l"(inbox) : "memory");
-        asm volatile("ld.relaxed.sys.global.v2.u32 {%0,%1}, [%2];" : "=r"(b.x), "=r"(b.y) : "l"(inbox + 1) : "memory");
-        asm volatile("ld.relaxed.sys.global.v2.u32 {%0,%1}, [%2];" : "=r"(c.x), "=r"(c.y) : "l"(inbox + 2) : "memory");
+        ps = __uint_as_float(a.x), pm = __uint_as_float(b.x), pz = __uint_as_float(c.x);
       }
-      ps = __uint_as_float(a.x), pm = __uint_as_float(b.x), pz = __uint_as_float(c.x);
-    }
-    if (S.diag && blockIdx.x == 0 && threadIdx.x < 32) {
-      const bool any_miss = __any_sync(FULL, first_miss);
-      if (timing) {
-        atomicAdd(&S.diag->wait_cycles, (unsigned long long)(clock64() - c0));
-        atomicAdd(&S.diag->polled_calls, 1ull);
-        if (any_miss) atomicAdd(&S.diag->waited_calls, 1ull);
+      if (S.diag && blockIdx.x == 0 && threadIdx.x < 32) {
+        const bool any_miss = __any_sync(FULL, first_miss);
+        if (timing) {
+          atomicAdd(&S.diag->wait_cycles, (unsigned long long)(clock64() - c0));
+          atomicAdd(&S.diag->polled_calls, 1ull);
+          if (any_miss) atomicAdd(&S.diag->waited_calls, 1ull);
+        }
       }
+      float t_sum = 0.0f, t_min = FLT_MAX, t_size = 0.0f;
+      for (int r = 0; r < S.world; ++r) {  // rank order, as the oracle
+        t_sum = __fadd_rn(t_sum, __shfl_sync(FULL, ps, r));
+        const float m = __shfl_sync(FULL, pm, r);
+        t_min = m < t_min ? m : t_min;
+        t_size = __fadd_rn(t_size, __shfl_sync(FULL, pz, r));
+      }
+      if (lane == 0) s_tot[0] = t_sum, s_tot[1] = t_min, s_tot[2] = t_size;
     }
-    w_sum = 0.0f, w_min = FLT_MAX, w_size = 0.0f;
-    for (int r = 0; r < S.world; ++r) {
-      w_sum = __fadd_rn(w_sum, __shfl_sync(FULL, ps, r));
-      const float m = __shfl_sync(FULL, pm, r);
-      w_min = m < w_min ? m : w_min;
-      w_size = __fadd_rn(w_size, __shfl_sync(FULL, pz, r));
-    }
+    __syncthreads();
+    w_sum = s_tot[0], w_min = s_tot[1], w_size = s_tot[2];
   }
   // lanes 0 and 1 evaluate the two powers side by side: (p/sum*size)^-beta and (min/sum*size)^-beta
   {
@@ -496,6 +516,186 @@ __global__ void __launch_bounds__(kSampleWarps * 32)
   }
   dbg_mark(S.dbg, 5);
 }
+// ---- sample with the wide-row gather fused in (Atari-shaped buffers) -----------------------------------------
+// The Atari-shaped step used to be three dependent launches (sample 9.9 us, TMA gather 14.3 us, update 12.3 us by
+// events after a flush, 29.5 us with PDL overlap).  Here the gather's DMA ring and the descent share ONE kernel:
+// the batch's copy items -- (sample, wide column, <= 8 KB chunk), ordered by sample -- are cut into gridDim.x
+// contiguous ranges, a range touches at most two samples, and the CTA's two warps each run the descent of one of
+// them (duplicated between the few CTAs that share a sample: two microseconds of L2-resident loads) and park the
+// slot in shared memory; one elected thread then drives the same cp.async.bulk ring as gather_bulk_kernel
+// (global -> shared with mbarrier complete_tx, shared -> global in bulk groups).  The copy starts as soon as the
+// CTA's own two indices are known, and a launch with its ~4 us of latency is gone.  The CTA whose range holds a
+// sample's first item also writes its index, weight and narrow columns.
+struct FusedPlan {
+  int32_t ncols;                         // wide columns
+  int32_t col_id[MRL_MAX_COLS];
+  int32_t chunk_bytes[MRL_MAX_COLS];
+  int32_t item_off[MRL_MAX_COLS + 1];    // first item of wide column k within a sample's item list
+  int32_t items_per_sample;
+};
+bool g_fused_gather = true;  // option "fused_gather"
+
+template <int STAGES>
+__global__ void __launch_bounds__(64)
+    prb_sample_gather_kernel(const __grid_constant__ SampleArgs S, const __grid_constant__ ColTable tab,
+                             const __grid_constant__ FusedPlan plan, int32_t stage_bytes) {
+  extern __shared__ __align__(128) uint8_t stage_mem[];
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ int64_t s_slot[2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr unsigned FULL = 0xffffffffu;
+  if (S.prefetch && S.levels > 2 * kHop) {  // (as prb_sample_kernel: the lines the 2nd hop can land on)
+    const int64_t gthreads = (int64_t)gridDim.x * blockDim.x;
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t lines = (1LL << (2 * kHop)) / 32;
+    for (int64_t q = gid; q < lines && q < gid + 4 * gthreads; q += gthreads)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(S.sum + (1LL << (2 * kHop)) + 32 * q));
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1);
+    fence_async_smem();
+  }
+  pdl_prologue();
+  const int ips = plan.items_per_sample;
+  const int64_t total = S.n * ips;
+  const int64_t lo = total * blockIdx.x / gridDim.x, hi = total * (blockIdx.x + 1) / gridDim.x;
+  const int64_t i0 = lo / ips;
+  const int64_t i = i0 + warp;  // this warp's sample
+  const bool active = hi > lo && i <= (hi - 1) / ips;
+  if (active) {
+    const float root_sum = __ldcg(S.sum + 1);
+    const float w_min = __ldcg(S.mn + 1);
+    float4 hop0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (S.levels > 0) hop0 = hop_load(S.sum, 1, S.levels < kHop ? S.levels : kHop, lane);
+    const float u = S.uniforms ? __ldg(S.uniforms + i) : mrl_uniform01(S.seed, S.ctr + (uint64_t)i);
+    const float seg = __fdiv_rn(root_sum, (float)S.n);
+    const float mass = __fmul_rn(__fadd_rn(u, (float)i), seg);
+    float leaf_p;
+    const int64_t leaf = prb_descend(S.sum, S.levels, S.cap2, S.size, mass, hop0, root_sum, lane, leaf_p);
+    if (lane == 0) s_slot[warp] = leaf;
+    if (i * ips >= lo) {  // the sample's first item is ours: index, weight, narrow columns
+      const float x = lane == 0 ? leaf_p : w_min;
+      float r = 0.0f;
+      const float beta = S.beta_dev ? __ldg(S.beta_dev) : S.beta;
+      if (lane < 2) r = mrl_is_weight(x, root_sum, (float)S.size, beta);
+      const float max_w = __shfl_sync(FULL, r, 1);
+      if (lane == 0) {
+        S.indices[i] = leaf;
+        S.weights[i] = __fdiv_rn(r, max_w);
+      }
+      for (int c = 0; c < tab.ncols; ++c) {
+        if (!((S.gather_mask >> c) & 1u)) continue;
+        const int64_t rb = tab.row_bytes[c];
+        const uint8_t *src = tab.col[c] + leaf * rb;
+        uint8_t *dst = tab.io[c] + i * rb;
+        if (tab.vec[c] >= 4) {
+          for (int64_t o = lane * 4; o < rb; o += 128)
+            *reinterpret_cast<uint32_t *>(dst + o) = *reinterpret_cast<const uint32_t *>(src + o);
+        } else {
+          for (int64_t o = lane; o < rb; o += 32) dst[o] = src[o];
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x != 0 || hi <= lo) return;
+
+  // ---- the DMA ring over items [lo, hi) ---------------------------------------------------------------------
+  const int64_t nmine = hi - lo;
+  uint8_t *dst_of[STAGES];
+  uint32_t bytes_of[STAGES];
+#pragma unroll 1
+  for (int64_t k = 0; k < nmine + STAGES - 1; ++k) {
+    if (k >= STAGES - 1) {  // drain: item j has landed -> write it out
+      const int64_t j = k - (STAGES - 1);
+      const int s = (int)(j % STAGES);
+      mbar_wait(&full_bar[s], (uint32_t)((j / STAGES) & 1));
+      fence_async_smem();
+#pragma unroll
+      for (int q = 0; q < STAGES; ++q)
+        if (q == s) bulk_s2g(dst_of[q], stage_mem + (size_t)q * stage_bytes, bytes_of[q]);
+      bulk_commit();
+    }
+    if (k < nmine) {  // fill: stage k % STAGES was last read by the store of item k - STAGES
+      const int64_t item = lo + k;
+      const int64_t si = item / ips;
+      const int r = (int)(item - si * ips);
+      int kc = 0;
+      while (kc + 1 < plan.ncols && r >= plan.item_off[kc + 1]) ++kc;
+      const int c = plan.col_id[kc];
+      const int64_t rb = tab.row_bytes[c];
+      const int64_t off = (int64_t)(r - plan.item_off[kc]) * plan.chunk_bytes[kc];
+      const int64_t rem = rb - off;
+      const uint32_t bytes = (uint32_t)(rem < plan.chunk_bytes[kc] ? rem : plan.chunk_bytes[kc]);
+      const int64_t slot = s_slot[si - i0];
+      const int s = (int)(k % STAGES);
+      if (k >= STAGES) bulk_wait_read<1>();
+#pragma unroll
+      for (int q = 0; q < STAGES; ++q)
+        if (q == s) {
+          dst_of[q] = tab.io[c] + si * rb + off;
+          bytes_of[q] = bytes;
+        }
+      mbar_expect_tx(&full_bar[s], bytes);
+      bulk_g2s(stage_mem + (size_t)s * stage_bytes, tab.col[c] + slot * rb + off, bytes, &full_bar[s]);
+    }
+  }
+  bulk_wait_all();
+}
+
+template <int STAGES>
+static int launch_fused(const SampleArgs &S, const ColTable &tab, const FusedPlan &plan, int32_t stage_bytes,
+                        int64_t blocks, cudaStream_t st) {
+  const size_t smem = (size_t)stage_bytes * STAGES;
+  if (first_use_on_device((const void *)prb_sample_gather_kernel<STAGES>)) {
+    cudaFuncAttributes fa;
+    MRL_CUDA(cudaFuncGetAttributes(&fa, prb_sample_gather_kernel<STAGES>));
+    MRL_CUDA(cudaFuncSetAttribute(prb_sample_gather_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  227 * 1024 - (int)fa.sharedSizeBytes));
+  }
+  MRL_CUDA(launch_pdl(prb_sample_gather_kernel<STAGES>, dim3((unsigned)blocks), dim3(64), smem, st, S, tab, plan,
+                      stage_bytes));
+  return MRL_OK;
+}
+
+// -> MRL_OK after launching the fused kernel, kNotFused when the shape does not fit it (the caller then runs
+// prb_sample_kernel + gather_rows)
+constexpr int kNotFused = -1001;
+static int try_fused_sample(const SampleArgs &S, const ColTable &tab, uint32_t wide, cudaStream_t st) {
+  if (!g_fused_gather || g_gather_path == 1 || S.levels <= 0) return kNotFused;
+  FusedPlan plan;
+  plan.ncols = 0;
+  plan.item_off[0] = 0;
+  int32_t stage_bytes = 0;
+  for (int c = 0; c < tab.ncols; ++c) {
+    if (!((wide >> c) & 1u)) continue;
+    const int64_t rb = tab.row_bytes[c];
+    if (tab.vec[c] != 16 || !(g_gather_path == 2 || rb >= g_bulk_min_row)) return kNotFused;  // (as gather_rows)
+    int64_t nch = (rb + g_bulk_chunk - 1) / g_bulk_chunk;
+    const int64_t chunk = ((rb + nch - 1) / nch + 15) / 16 * 16;
+    nch = (rb + chunk - 1) / chunk;
+    const int k = plan.ncols++;
+    plan.col_id[k] = c;
+    plan.chunk_bytes[k] = (int32_t)chunk;
+    plan.item_off[k + 1] = plan.item_off[k] + (int32_t)nch;
+    if (chunk > stage_bytes) stage_bytes = (int32_t)chunk;
+  }
+  if (plan.ncols == 0) return kNotFused;
+  plan.items_per_sample = plan.item_off[plan.ncols];
+  const int64_t total = S.n * plan.items_per_sample;
+  int64_t blocks = (int64_t)sm_count() * g_bulk_ctas_per_sm;
+  if (blocks > total) blocks = total;
+  // a CTA's contiguous range must touch at most two samples (one descent per warp)
+  if ((total + blocks - 1) / blocks > plan.items_per_sample) return kNotFused;
+  stage_bytes = (stage_bytes + 127) / 128 * 128;
+  int stages = (int)g_bulk_stages;
+  while (stages > 2 && (size_t)stage_bytes * stages > 200 * 1024) stages = stages == 12 ? 8 : stages / 2;
+  if (stages == 12) return launch_fused<12>(S, tab, plan, stage_bytes, blocks, st);
+  if (stages == 8) return launch_fused<8>(S, tab, plan, stage_bytes, blocks, st);
+  if (stages == 4) return launch_fused<4>(S, tab, plan, stage_bytes, blocks, st);
+  return launch_fused<2>(S, tab, plan, stage_bytes, blocks, st);
+}
+
 // ---- update ------------------------------------------------------------------------------
 struct UpdateArgs {
   float *sum;
@@ -1534,6 +1734,15 @@ static int prb_sample_impl(PrbBuffer *b, int64_t n, float beta, const float *uni
     for (int c = 0; c < b->ncols; ++c)
       if ((fused >> c) & 1u) ok = ok && tab.vec[c] >= 4, words += b->row_bytes[c] / 4;
     if (ok) S.word_units = (int32_t)words;
+  }
+  if (wide && !p2p && !gstats) {  // Atari-shaped rows: descent and DMA ring in one kernel when the batch fits it
+    const int rc = try_fused_sample(S, tab, wide, st);
+    if (rc != kNotFused) {
+      if (rc != MRL_OK) return rc;
+      MRL_LAUNCHED();
+      if (!uniforms) b->ctr += (uint64_t)n;
+      return MRL_OK;
+    }
   }
   const int64_t blocks = (n + kSampleWarps - 1) / kSampleWarps;
   MRL_CUDA(launch_pdl(prb_sample_kernel, dim3((unsigned)blocks), dim3(kSampleWarps * 32), 0, st, S, tab));

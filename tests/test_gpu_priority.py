@@ -545,3 +545,49 @@ def test_host_update_rejects_indices_outside_the_buffer():
     big[-1] = 5000
     with pytest.raises(ValueError):
         g.update_priorities(big, np.ones(600, np.float32))
+
+
+@pytest.mark.parametrize("batch", [1, 2, 37, 512, 592, 593, 2048])
+@pytest.mark.parametrize("row", [28224, 4096, 2064])
+def test_fused_sample_gather_equals_the_two_kernel_path_and_the_oracle(batch, row):
+    """Atari-shaped rows: prb_sample_gather_kernel (descent + DMA ring in one launch, batches that fit it) against
+    prb_sample_kernel + gather_bulk_kernel (option fused_gather = 0) and the oracle -- indices, weight bits, every
+    byte of every column; a partly filled ring; injected draws and the internal generator."""
+    rng = np.random.default_rng(batch * 31 + row)
+    cap, fill = 6000, 5000
+    rb = [row, 4, 4, 1, row]
+    shapes, types = [(r,) for r in rb], [np.uint8] * 5
+    rows = [O.fill_rows(fill, r, 50 + c) for c, r in enumerate(rb)]
+    pr = (np.abs(rng.normal(size=fill)) + 1e-3).astype(np.float32)
+    o = O.PriorityBufferOracle(0.6, cap, batch, shapes, types, 5, 6)
+    o.insert_batch(rows)
+    o.update_priorities(np.arange(fill), pr)
+    bufs = {}
+    try:
+        for fused in (1, 0):
+            _ffi.set_option("fused_gather", fused)
+            g = M.PriorityReplayBuffer(0.6, cap, batch, shapes, types, 5, 6)
+            g.insert(*[dev(c) for c in rows])
+            g.update_priorities(dev(np.arange(fill)), dev(pr))
+            bufs[fused] = g
+        for step in range(3):
+            u = None if step == 1 else rng.random(batch).astype(np.float32)
+            want = o.sample(0.4, uniforms=u)
+            newp = (np.abs(rng.normal(size=batch)) + 1e-3).astype(np.float32)
+            for fused, g in bufs.items():
+                _ffi.set_option("fused_gather", fused)
+                before = _ffi.launch_count()
+                got = g.sample(0.4, uniforms=None if u is None else dev(u))
+                launches = _ffi.launch_count() - before
+                same_sample(got, want)
+                assert np.array_equal(host(got[2])[:, :8].copy().view(np.int64)[:, 0], want[0])  # row carries its slot
+                if fused and batch <= 592:
+                    assert launches == 1, launches  # one kernel: descent and copy
+                elif not fused:
+                    assert launches >= 2
+                g.update_priorities(got[0], dev(newp))
+            o.update_priorities(want[0], newp)
+        for g in bufs.values():
+            same_tree(g, o)
+    finally:
+        _ffi.set_option("fused_gather", 1)
