@@ -11,7 +11,7 @@
  *   double +,-,*,/ and fma in a fixed order, so gcc (-ffp-contract=off) and nvcc (-fmad=false)
  *   produce the same bits.  It is accurate to <1e-14 relative before the final rounding to
  *   float, i.e. it equals the correctly rounded (float)pow((double)x,(double)y) except for
- *   ~1e-7 of inputs, where it is off by one float ulp (checked in tests/test_arith.py).
+ *   ~1e-7 of inputs, where it is off by one float ulp (checked in tests/test_oracle.py::test_detpow_equals_correctly_rounded_pow).
  *
  *  mrl_hash32 / mrl_uniform01 / mrl_uniform_below: counter-based generator used when the caller
  *   does not inject its own uniform draws (splitmix64 finaliser over seed + counter).

@@ -1602,8 +1602,19 @@ static int scan_host_pipelined(const HostScan &H, cudaStream_t st, Launch launch
   uint8_t *s;
   int rc = scratch(piece * (size_t)K, &s, st);
   if (rc) return rc;
-  static cudaStream_t s_in = nullptr, s_out = nullptr;
-  static cudaEvent_t ev_in[16], ev_k[16], ev_start = nullptr, ev_done = nullptr;
+  // copy streams and events of the CURRENT device (streams and events belong to the device they were created on)
+  struct HostPipe {
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[16], ev_k[16], ev_start = nullptr, ev_done = nullptr;
+  };
+  static HostPipe pipes[64];
+  int dev = 0;
+  MRL_CUDA(cudaGetDevice(&dev));
+  MRL_REQUIRE(dev >= 0 && dev < 64, "device index out of range");
+  HostPipe &P = pipes[dev];
+  cudaStream_t &s_in = P.s_in, &s_out = P.s_out;
+  cudaEvent_t(&ev_in)[16] = P.ev_in, (&ev_k)[16] = P.ev_k;
+  cudaEvent_t &ev_start = P.ev_start, &ev_done = P.ev_done;
   if (!s_in) {
     MRL_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
     MRL_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));

@@ -18,8 +18,8 @@ struct ScanArgs {
   int64_t st, sc;       // element strides along t and along the column index
   int64_t dst, dsc;     // same for done (indexed by column / E)
   float gamma, gl;      // gl = fl(gamma*lambda)
-  // != NULL: the kernel also accumulates (sum, sum of squares) of everything it stores to `out`, in float64
-  // and a fixed order, one partial per CTA at mom[blockIdx.x] -- the moments PPO / A2C normalise with right
+  // != NULL: the kernel also accumulates (sum, sum of squares) of everything it stores to `out` (fp32 over a
+  // lane's 8..32 consecutive steps, float64 beyond that) in a fixed order, one partial per CTA at mom[blockIdx.x] -- the moments PPO / A2C normalise with right
   // after the scan (ppo.py:361-368, a2c.py:190-192) without another pass over the array.  Honoured by the
   // TMA kernels (scan_tma.cu); the launchers report how many partials were written.
   double2 *mom;

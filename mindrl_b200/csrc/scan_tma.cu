@@ -54,6 +54,9 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
       "l"(map), "r"(x), "r"(y), "r"(s32(bar))
       : "memory");
 }
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap *map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, int x, int y, const void *src) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map),
                "r"(x), "r"(y), "r"(s32(src))
@@ -161,6 +164,16 @@ __global__ void __launch_bounds__((NG * kWarps + 1) * 32)
     mbar_init(&cbar[0], 1);
     mbar_init(&cbar[1], 1);
     fence_async_smem();
+  } else if (threadIdx.x == NG * kWarps * 32) {
+    // the descriptors live in the kernel's parameter block: have them in the TMA unit's cache before the first
+    // load is issued (their fetch is otherwise the first thing every CTA's pipeline waits for)
+    prefetch_tensormap(&tm_a);
+    if (OP != OP_DR) prefetch_tensormap(&tm_v);
+    if (OP == OP_GAE) prefetch_tensormap(&tm_v1);
+    if (HD) prefetch_tensormap(&tm_d);
+  } else if (threadIdx.x == 32) {
+    prefetch_tensormap(&tm_out);
+    if (OP == OP_GAE) prefetch_tensormap(&tm_ret);
   }
   __syncthreads();
 
@@ -291,16 +304,20 @@ __global__ void __launch_bounds__((NG * kWarps + 1) * 32)
     }
     __syncwarp();
     x = xin;
+    float tsum = 0.0f, tsq = 0.0f;
 #pragma unroll
     for (int i = RPU - 1; i >= 0; --i) {
       x = fstep(ea[i], eb[i], x);
       oa[(h * RPU + i) * COLS + c] = x;
       if (want_ret) oa[C::kWarpOut + (h * RPU + i) * COLS + c] = __fadd_rn(x, aux[i]);
       if (MOM && colok && (k > 0 || (n_tiles - 1) * C::kRows + unit * RPU + i < T)) {
-        const double xd = (double)x;
-        msum += xd;
-        msq = fma(xd, xd, msq);
+        tsum = __fadd_rn(tsum, x);  // fp32 over this lane's RPU steps of the tile, float64 across tiles:
+        tsq = __fmaf_rn(x, x, tsq);  // per-element float64 cost the kernel 4 us of 24
       }
+    }
+    if (MOM) {
+      msum += (double)tsum;
+      msq += (double)tsq;
     }
     fence_async_smem();
     __syncwarp();
@@ -363,9 +380,50 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
+// A tensor map is a pure function of (base, element size, rows, cols, box): learners call the scans on the same
+// trajectory buffers every iteration, and six cuTensorMapEncodeTiled calls are ~2 us of host time in front of
+// a 14 us kernel (they sit between the caller's event and the launch when the GPU is idle).  Small direct-mapped
+// cache, per thread (no locking; a stale entry can only be hit by identical arguments, which encode identically).
+struct MapKey {
+  const void *base;
+  int64_t rows, cols;
+  int32_t box_cols, box_rows, is_u8;
+  bool operator==(const MapKey &o) const {
+    return base == o.base && rows == o.rows && cols == o.cols && box_cols == o.box_cols && box_rows == o.box_rows &&
+           is_u8 == o.is_u8;
+  }
+};
+struct MapSlot {
+  MapKey key;
+  CUtensorMap map;
+  bool valid = false;
+};
+constexpr int kMapSlots = 64;
+
+bool make_map_uncached(CUtensorMap *m, const void *base, bool is_u8, int64_t rows, int64_t cols, int box_cols,
+                       int box_rows);
+
 // row-major [rows, cols] array of `esize`-byte elements, box = box_rows x box_cols
 bool make_map(CUtensorMap *m, const void *base, bool is_u8, int64_t rows, int64_t cols, int box_cols,
               int box_rows) {
+  static thread_local MapSlot cache[kMapSlots];
+  const MapKey key{base, rows, cols, box_cols, box_rows, is_u8 ? 1 : 0};
+  uint64_t h = reinterpret_cast<uintptr_t>(base) >> 4;
+  h ^= (uint64_t)rows * 0x9E3779B97F4A7C15ull ^ (uint64_t)cols * 0xC2B2AE3D27D4EB4Full ^
+       ((uint64_t)box_rows << 20) ^ ((uint64_t)box_cols << 8) ^ (uint64_t)key.is_u8;
+  h ^= h >> 29;
+  MapSlot &sl = cache[h % kMapSlots];
+  if (sl.valid && sl.key == key) {
+    *m = sl.map;
+    return true;
+  }
+  if (!make_map_uncached(m, base, is_u8, rows, cols, box_cols, box_rows)) return false;
+  sl.key = key, sl.map = *m, sl.valid = true;
+  return true;
+}
+
+bool make_map_uncached(CUtensorMap *m, const void *base, bool is_u8, int64_t rows, int64_t cols, int box_cols,
+                       int box_rows) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
   const int esize = is_u8 ? 1 : 4;
@@ -681,14 +739,16 @@ __global__ void __launch_bounds__(kThreads)
         o[q] = xe;
         o2[q] = __fadd_rn(xe, aux[q]);
       }
-      if (MOM) {
+      if (MOM) {  // fp32 over the lane's 8 steps, float64 across tiles
+        float tsum = 0.0f, tsq = 0.0f;
 #pragma unroll
         for (int q = 0; q < 8; ++q)
           if (p0 + q < len) {
-            const double xd = (double)o[q];
-            msum += xd;
-            msq = fma(xd, xd, msq);
+            tsum = __fadd_rn(tsum, o[q]);
+            tsq = __fmaf_rn(o[q], o[q], tsq);
           }
+        msum += (double)tsum;
+        msq += (double)tsq;
       }
       float4 *dst = reinterpret_cast<float4 *>(oa + 8 * lane);
       dst[0] = make_float4(o[0], o[1], o[2], o[3]);
