@@ -96,6 +96,11 @@ int64_t mrl_launch_count(void);
  *   "bm_kernel" [0]: batch-major scans: 0 auto, 1 warp-per-row register kernel, 2 TMA rows whenever aligned;
  *       "row_ctas_per_sm" [4], "row_stages" [0 = from row_ctas_per_sm]
  *   "host_scan_chunks" [0 = ~16 MB of input per piece]: pieces of the *_host scans (1 = no pipelining)
+ *   "shard_weights" [0]: importance weights of the SHARDED sample.  0: against the global sum,
+ *       minimum and size, (p / sum_all * N)^-beta / (min_all / sum_all * N)^-beta -- exact when all shards carry the
+ *       same priority mass.  1: against the probability the sample was really drawn with -- every rank draws its
+ *       batch from its own tree, P(i) = p_i / (world * S_rank) -- normalised by the largest such weight over all
+ *       ranks: unbiased for shards of unequal mass.  Set it identically on every rank.
  *   "shard_timeout_ms" [10000]: how long a sharded sample kernel polls for a peer's root statistics
  *   "debug_timers": device pointer to >= 32 int64 phase marks of the tree kernels (0 = off) */
 int mrl_set_option(const char *key, int64_t value);

@@ -9,6 +9,13 @@ sharded buffer; the only collective it uses next to a buffer is AllGather of who
 episode (example/ppo/src/distribute_policy_1/fragments.py:124-177).
 
 Global index = rank * local_capacity + local_index.
+
+Importance weights.  Every rank draws its whole batch from its OWN tree, so transition i of rank r is drawn with
+probability p_i / (world * S_r), not p_i / S_global.  By default the weights are nevertheless
+formed against the global sum, minimum and size -- exact when the shards carry equal priority mass, which uniform
+routing of new transitions gives in expectation.  `mindrl_b200._ffi.set_option("shard_weights", 1)` (on every rank)
+switches to weights against the true probability, normalised by the largest weight over all ranks: unbiased for any
+split of the mass (tests/test_oracle.py::test_exact_shard_weights_undo_the_sampling_probability).
 """
 import numpy as np
 

@@ -263,6 +263,7 @@ extern long long *g_debug_timers;  // prb.cu
 extern bool g_no_inline_update;    // prb.cu
 extern bool g_host_zero_copy;      // prb.cu
 extern bool g_fused_gather;        // prb.cu
+extern bool g_exact_shard_weights; // prb.cu
 extern long long g_shard_timeout_ns;  // prb.cu
 bool g_pdl = true;                 // programmatic dependent launch of the PER-path kernels
 bool g_tree_prefetch = true;       // tree kernels pull the lines of their later round trips into L2 first
@@ -283,6 +284,10 @@ int set_copy_option(const char *key, int64_t value) {
   }
   if (k == "host_zero_copy" && (value == 0 || value == 1)) {
     g_host_zero_copy = value == 1;
+    return MRL_OK;
+  }
+  if (k == "shard_weights" && (value == 0 || value == 1)) {
+    g_exact_shard_weights = value == 1;
     return MRL_OK;
   }
   if (k == "fused_gather" && (value == 0 || value == 1)) {

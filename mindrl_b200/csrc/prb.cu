@@ -218,6 +218,7 @@ struct SampleArgs {
   int *err;              // raised when the poll times out
   long long timeout_ns;
   const float *beta_dev; // != NULL: beta is read from device memory (AOT shim: beta arrives as a tensor)
+  int32_t exact_weights; // sharded: weights from the probability the sample was really drawn with (option "shard_weights")
   int32_t prefetch;  // option "tree_prefetch"
   int32_t word_units;  // > 0: every fused column is made of aligned 4-byte words; their total per row
 };
@@ -359,15 +360,26 @@ __global__ void __launch_bounds__(kSampleWarps * 32)
     asm volatile("ld.relaxed.sys.global.v2.u32 {%0,%1}, [%2];" : "=r"(ic.x), "=r"(ic.y) : "l"(inbox + 2) : "memory");
   }
   const float u = S.uniforms ? __ldg(S.uniforms + i) : mrl_uniform01(S.seed, S.ctr + (uint64_t)i);
-  float w_sum = root_sum, w_size = (float)S.size;
+  // Denominators of the importance weights: (p / w_sum * w_size)^-beta for the sample, (w_min / m_sum * w_size)^-beta
+  // for the largest weight.  One buffer: its own root.  Sharded, default: global sum, global minimum,
+  // global size.  Sharded with "shard_weights" = 1: the probability the sample was REALLY drawn with -- every rank
+  // draws its batch from its own tree, so P(i) = p_i / (world * S_rank) -- and the largest weight over all ranks,
+  // (min_q / (world * S_q) * N)^-beta at the rank q where that ratio is smallest (first in rank order).
+  float w_sum = root_sum, w_size = (float)S.size, m_sum = root_sum;
   if (S.gstats) {
-    w_sum = 0.0f, w_min = FLT_MAX, w_size = 0.0f;
+    float t_sum = 0.0f, t_min = FLT_MAX, best = FLT_MAX, star_min = FLT_MAX, star_sum = 1.0f;
+    w_size = 0.0f;
     for (int r = 0; r < S.world; ++r) {
-      w_sum = __fadd_rn(w_sum, __ldg(S.gstats + 4 * r));
-      const float m = __ldg(S.gstats + 4 * r + 1);
-      w_min = m < w_min ? m : w_min;
+      const float sr = __ldg(S.gstats + 4 * r), m = __ldg(S.gstats + 4 * r + 1);
+      t_sum = __fadd_rn(t_sum, sr);
+      t_min = m < t_min ? m : t_min;
       w_size = __fadd_rn(w_size, __ldg(S.gstats + 4 * r + 2));
+      const float den = __fmul_rn((float)S.world, sr);
+      const float ratio = __fdiv_rn(m, den);
+      if (sr > 0.0f && ratio < best) best = ratio, star_min = m, star_sum = den;
     }
+    if (S.exact_weights) w_sum = __fmul_rn((float)S.world, root_sum), w_min = star_min, m_sum = star_sum;
+    else w_sum = t_sum, w_min = t_min, m_sum = t_sum;
   }
   const float seg = __fdiv_rn(root_sum, (float)S.n);
   float mass = __fmul_rn(__fadd_rn(u, (float)i), seg);
@@ -466,24 +478,32 @@ __global__ void __launch_bounds__(kSampleWarps * 32)
           if (any_miss) atomicAdd(&S.diag->waited_calls, 1ull);
         }
       }
-      float t_sum = 0.0f, t_min = FLT_MAX, t_size = 0.0f;
+      float t_sum = 0.0f, t_min = FLT_MAX, t_size = 0.0f, best = FLT_MAX, star_min = FLT_MAX, star_sum = 1.0f;
       for (int r = 0; r < S.world; ++r) {  // rank order, as the oracle
-        t_sum = __fadd_rn(t_sum, __shfl_sync(FULL, ps, r));
-        const float m = __shfl_sync(FULL, pm, r);
+        const float sr = __shfl_sync(FULL, ps, r), m = __shfl_sync(FULL, pm, r);
+        t_sum = __fadd_rn(t_sum, sr);
         t_min = m < t_min ? m : t_min;
         t_size = __fadd_rn(t_size, __shfl_sync(FULL, pz, r));
+        const float den = __fmul_rn((float)S.world, sr);
+        const float ratio = __fdiv_rn(m, den);
+        if (sr > 0.0f && ratio < best) best = ratio, star_min = m, star_sum = den;
       }
-      if (lane == 0) s_tot[0] = t_sum, s_tot[1] = t_min, s_tot[2] = t_size;
+      if (lane == 0) {
+        if (S.exact_weights) s_tot[0] = star_sum, s_tot[1] = star_min;
+        else s_tot[0] = t_sum, s_tot[1] = t_min;
+        s_tot[2] = t_size;
+      }
     }
     __syncthreads();
-    w_sum = s_tot[0], w_min = s_tot[1], w_size = s_tot[2];
+    m_sum = s_tot[0], w_min = s_tot[1], w_size = s_tot[2];
+    w_sum = S.exact_weights ? __fmul_rn((float)S.world, root_sum) : m_sum;
   }
   // lanes 0 and 1 evaluate the two powers side by side: (p/sum*size)^-beta and (min/sum*size)^-beta
   {
     const float x = lane == 0 ? leaf_p : w_min;
     float r = 0.0f;
     const float beta = S.beta_dev ? __ldg(S.beta_dev) : S.beta;
-    if (lane < 2) r = mrl_is_weight(x, w_sum, w_size, beta);
+    if (lane < 2) r = mrl_is_weight(x, lane == 0 ? w_sum : m_sum, w_size, beta);
     const float max_w = __shfl_sync(FULL, r, 1);
     if (lane == 0) {
       S.indices[i] = leaf;
@@ -534,6 +554,7 @@ struct FusedPlan {
   int32_t items_per_sample;
 };
 bool g_fused_gather = true;  // option "fused_gather"
+bool g_exact_shard_weights = false;  // option "shard_weights"
 
 template <int STAGES>
 __global__ void __launch_bounds__(64)
@@ -1714,6 +1735,7 @@ static int prb_sample_impl(PrbBuffer *b, int64_t n, float beta, const float *uni
   S.indices = indices, S.weights = weights;
   S.n = n, S.cap2 = b->cap2, S.capacity = b->capacity, S.size = b->size;
   S.levels = b->levels, S.world = world, S.beta = beta;
+  S.exact_weights = g_exact_shard_weights ? 1 : 0;
   S.seed = b->seed, S.ctr = b->ctr;
   // narrow columns are copied by the warp that found the leaf; wide ones go to the TMA gather
   uint32_t fused = 0, wide = 0;

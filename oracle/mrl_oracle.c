@@ -300,23 +300,45 @@ static int64_t orc_tree_descend(const orc_prb *b, float mass) {
  * gstats = world x {sum, min, size, max_priority}: weights against the global totals
  * (sharded buffer): Sum = sum over ranks in rank order, Min = min over ranks,
  * Size = sum of sizes. */
+/* sharded buffers: 0 = weights against the global sum / minimum / size; 1 = against the
+ * probability a sample is really drawn with, p_i / (world * S_rank), normalised by the largest such weight
+ * over all ranks (the first form is biased when shards differ in priority mass) */
+static int orc_exact_shard_weights = 0;
+void orc_set_shard_weights(int exact) { orc_exact_shard_weights = exact; }
+
 static int orc_prb_sample_impl(orc_prb *b, int64_t n, float beta, const float *uniforms,
                                const float *gstats, int32_t world, int64_t *indices,
                                float *weights, void *const *out_cols) {
   if (n <= 0 || b->size <= 0) return 1; /* nothing to sample from */
   const float root_sum = b->sum[1];
-  float w_sum = root_sum, w_min = b->mn[1], w_size = (float)b->size;
+  float w_sum = root_sum, w_min = b->mn[1], w_size = (float)b->size, m_sum = root_sum;
   if (gstats) {
-    w_sum = 0.0f;
-    w_min = FLT_MAX;
+    float t_sum = 0.0f, t_min = FLT_MAX, best = FLT_MAX, star_min = FLT_MAX, star_sum = 1.0f;
     w_size = 0.0f;
     for (int r = 0; r < world; ++r) {
-      w_sum = w_sum + gstats[4 * r + 0];
-      w_min = gstats[4 * r + 1] < w_min ? gstats[4 * r + 1] : w_min;
+      const float sr = gstats[4 * r + 0], m = gstats[4 * r + 1];
+      t_sum = t_sum + sr;
+      t_min = m < t_min ? m : t_min;
       w_size = w_size + gstats[4 * r + 2];
+      const float den = (float)world * sr;
+      const float ratio = m / den;
+      if (sr > 0.0f && ratio < best) {
+        best = ratio;
+        star_min = m;
+        star_sum = den;
+      }
+    }
+    if (orc_exact_shard_weights) {
+      w_sum = (float)world * root_sum;
+      w_min = star_min;
+      m_sum = star_sum;
+    } else {
+      w_sum = t_sum;
+      w_min = t_min;
+      m_sum = t_sum;
     }
   }
-  const float max_w = mrl_is_weight(w_min, w_sum, w_size, beta);
+  const float max_w = mrl_is_weight(w_min, m_sum, w_size, beta);
   const float seg = root_sum / (float)n;
   for (int64_t i = 0; i < n; ++i) {
     const float u = uniforms ? uniforms[i] : mrl_uniform01(b->seed, b->ctr + (uint64_t)i);

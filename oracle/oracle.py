@@ -430,6 +430,11 @@ def uniform01(seed, ctr):
     return lib().orc_uniform01(seed, ctr)
 
 
+def set_shard_weights(exact):
+    """0: sharded weights against the global sum / min / size; 1: against the true per-shard sampling probability"""
+    lib().orc_set_shard_weights(int(bool(exact)))
+
+
 def td_lambda_targets(rewards, terminated, mask, target_qs, gamma, td_lambda, max_t=None):
     """C oracle of coma.py:489-501; target_qs [B, Tq, A], the others [B, Tr, 1 or A]"""
     q = _f32(target_qs)

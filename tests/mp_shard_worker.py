@@ -96,6 +96,13 @@ def main():
                 for s in sh.values():
                     s.local.update_priorities(dev(idx), dev(newp))
                 o.update_priorities(idx, newp)
+        # weights against the true per-shard sampling probability (option "shard_weights"), all three exchanges
+        _ffi.set_option("shard_weights", 1)
+        O.set_shard_weights(1)
+        outs, want = sample_all(0.6, rng.random(batch).astype(np.float32))
+        _ffi.set_option("shard_weights", 0)
+        O.set_shard_weights(0)
+        update_all(outs, want, (rng.random(batch) + 0.05).astype(np.float32))
         for k, b in bufs.items():
             gs, gm = b.tree()
             os_, om = o.tree()

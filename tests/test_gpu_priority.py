@@ -227,6 +227,17 @@ def test_sharded_weights_against_oracle():
     got = g.sample(0.4, uniforms=dev(u), gstats=dev(gstats))
     want = o.sample(0.4, uniforms=u, gstats=gstats)
     same_sample(got, want)
+    # option "shard_weights" = 1: weights against the true sampling probability p / (world * S_rank)
+    try:
+        _ffi.set_option("shard_weights", 1)
+        O.set_shard_weights(1)
+        got1 = g.sample(0.4, uniforms=dev(u), gstats=dev(gstats))
+        want1 = o.sample(0.4, uniforms=u, gstats=gstats)
+        same_sample(got1, want1)
+        assert np.array_equal(host(got1[0]), host(got[0])) and not np.array_equal(host(got1[1]), host(got[1]))
+    finally:
+        _ffi.set_option("shard_weights", 0)
+        O.set_shard_weights(0)
 
 
 def test_checkpoint_round_trip():

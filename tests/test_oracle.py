@@ -427,3 +427,37 @@ def test_priority_pow_and_weights_against_an_independent_float64_restatement():
     w64 = np.power(prob * cap, -np.float64(np.float32(beta))) / np.power(leaves64.min() / cum[-1] * cap, -np.float64(np.float32(beta)))
     assert np.allclose(w, w64, rtol=3e-6, atol=0)
     assert w.max() <= 1.0 + 1e-6
+
+
+def test_exact_shard_weights_undo_the_sampling_probability():
+    """with shards of unequal priority mass the default sharded weights (global sum) do not cancel the
+    probability a sample is really drawn with, p_i / (world * S_rank).  With shard_weights = 1 they do: at beta = 1,
+    w_i * P(i) is one constant over all samples of all ranks (the definition of an importance weight); with the
+    default it differs between the ranks by the ratio of their masses."""
+    rng = np.random.default_rng(17)
+    world, cap, batch = 2, 256, 64
+    bufs, stats = [], []
+    for r in range(world):
+        b = O.PriorityBufferOracle(1.0, cap, batch, [(1,)], [np.int32], 1, r)
+        b.insert_batch([np.arange(cap, dtype=np.int32)[:, None]])
+        b.update_priorities(np.arange(cap), (rng.random(cap) * (1 + 4 * r) + 0.05).astype(np.float32))  # rank 1: ~5x the mass
+        bufs.append(b)
+        stats.append(b.root_stats())
+    g = np.stack(stats)
+    u = rng.random(batch).astype(np.float32)
+    try:
+        spread = {}
+        for exact in (0, 1):
+            O.set_shard_weights(exact)
+            prod = []
+            for r, b in enumerate(bufs):
+                idx, w = b.sample(1.0, uniforms=u, gather=False, gstats=g)
+                p = b.tree()[0][cap + idx].astype(np.float64)
+                prod.append(w.astype(np.float64) * p / (world * float(stats[r][0])))
+                assert w.max() <= 1.0 + 1e-6
+            allp = np.concatenate(prod)
+            spread[exact] = allp.max() / allp.min()
+        assert spread[1] < 1.0 + 1e-5, spread
+        assert spread[0] > 2.0, spread  # the masses differ ~5x
+    finally:
+        O.set_shard_weights(0)
