@@ -52,9 +52,9 @@ L_1M = 20
 
 
 def ncu_traffic(key):
-    """per-launch DRAM bytes of a kernel from the committed ncu capture (profiles/r1_traffic.json)"""
+    """per-launch DRAM bytes of a kernel from the committed ncu capture (profiles/r2_traffic.json)"""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        t = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
         return t[key]["dram_traffic_bytes"]
     except Exception:
         return None
@@ -62,9 +62,9 @@ def ncu_traffic(key):
 
 def ncu_latency_evidence(key):
     """what SURVEY 8(d) asks for the latency-bound kernels instead of a %-of-peak target: L2 hit rate and warp
-    stall reasons of the committed ncu capture (profiles/r1_traffic.json; cold caches, serialised launches)"""
+    stall reasons of the committed ncu capture (profiles/r2_traffic.json; cold caches, serialised launches)"""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))[key]
+        t = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))[key]
         return {k: t[k] for k in ("ncu_duration_us", "l2_hit_rate_pct", "warps_active_pct", "issue_active_pct",
                                   "stalls_per_issue", "source") if k in t}
     except Exception:
@@ -466,7 +466,7 @@ def bench_per(ctx, name, rows, batch, steps, warmup, primary, sharded=None, pari
                 "algorithmic_bytes_per_launch": kern[dom]["bytes"],
                 "kernel_ms": {k: v["ms"] for k, v in kern.items()},
                 "ncu": {k: ncu_latency_evidence(("c3:" if R > 512 else "c2:") + k)
-                        for k in ("prb_sample_kernel", "prb_update_sub_kernel")},
+                        for k in (("prb_sample_gather_kernel<4>" if R > 512 else "prb_sample_kernel"), "prb_update_sub_kernel")},
                 "note": ("tree kernels are dependent-load latency bound (L2/HBM round trips), "
                          "not bandwidth bound" if R <= 512 else
                          "row gather is HBM-bandwidth bound; since round 2 the descent and the DMA ring are one kernel "
@@ -794,7 +794,7 @@ def bench_gae(ctx, steps, warmup):
     main = out["gae_time_major[T,B]"]
     roofline = {"bound": "hbm", "kernel": "scan_tm_strip_kernel<GAE, done, 32 cols, 16 steps/lane>", "achieved": main["GBps"],
                 "peak": hbm, "unit": "GB/s", "frac": main["frac"],
-                "traffic": ncu_traffic("c4:scan_tm_strip_kernel<1, 1, 32, 16, 1>"),
+                "traffic": ncu_traffic("c4:scan_tm_strip_kernel<1, 1, 32, 16, 1, 0>"),
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": 17 * n + 4 * B}
     # e2e: host arrays in, host arrays out
     hr, hv = pinned(ctx, (T, B), torch.float32), pinned(ctx, (T + 1, B), torch.float32)
@@ -812,7 +812,7 @@ def bench_gae(ctx, steps, warmup):
            "d2h_bytes_per_step": 8 * n, "steps": esteps, "ms_per_step": e_ms / esteps}
     bm = out["gae_batch_major[B,T]"]
     roofline["batch_major_kernel"] = {"kernel": "scan_bm_row_kernel<GAE, done>", "achieved": bm["GBps"], "frac": bm["frac"],
-                                      "traffic": ncu_traffic("c4:scan_bm_row_kernel<1, 1, 0>")}
+                                      "traffic": ncu_traffic("c4:scan_bm_row_kernel<1, 1, 0, 0>")}
     roofline["back_to_back"] = {"achieved": main["back_to_back_GBps"], "frac": main["back_to_back_frac"],
                                 "note": "5 rotated buffer sets, launches back to back in one event pair"}
     w = ctx.world

@@ -147,17 +147,17 @@ def test_sharded_buffer_world2_gloo():
 
 def test_bench_finds_its_committed_ncu_numbers():
     """bench.py copies per-launch DRAM traffic (roofline.traffic) and the latency evidence of the tree kernels out of
-    profiles/r1_traffic.json: every key it asks for must be there, or the bench line silently carries nulls"""
+    profiles/r2_traffic.json: every key it asks for must be there, or the bench line silently carries nulls"""
     import importlib.util
     import os
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(root, "bench.py"))
     bench = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(bench)
-    for key in ("c2:prb_update_sub_kernel", "c2:prb_sample_kernel", "c3:gather_bulk_kernel<4>",
-                "c4:scan_tm_strip_kernel<1, 1, 32, 16, 1>", "c4:scan_bm_row_kernel<1, 1, 0>"):
+    for key in ("c2:prb_update_sub_kernel", "c2:prb_sample_kernel", "c3:prb_sample_gather_kernel<4>",
+                "c4:scan_tm_strip_kernel<1, 1, 32, 16, 1, 0>", "c4:scan_bm_row_kernel<1, 1, 0, 0>"):
         assert bench.ncu_traffic(key) and bench.ncu_traffic(key) > 0, key
-    for key in ("c2:prb_sample_kernel", "c2:prb_update_sub_kernel", "c3:prb_sample_kernel", "c3:prb_update_sub_kernel"):
+    for key in ("c2:prb_sample_kernel", "c2:prb_update_sub_kernel", "c3:prb_sample_gather_kernel<4>", "c3:prb_update_sub_kernel"):
         ev = bench.ncu_latency_evidence(key)
         assert ev and 0 < ev["l2_hit_rate_pct"] < 100 and ev["stalls_per_issue"]["long_scoreboard"] > 0, key
     assert bench.ncu_traffic("no such kernel") is None

@@ -10,7 +10,7 @@ tail -2 gpurun_out/${tag}_gputest_multi${maxn}.log
 grep "SHARD_" gpurun_out/${tag}_shard_world${maxn}.log
 for n in 1 2 4 8; do
   [ $n -gt $maxn ] && break
-  for what in "c2 20" "c2 200" "c5 20" "c5 200"; do
+  for what in "c2 20" "c2 200" "c5 200"; do
     set -- $what
     port=$((port+1))
     out=gpurun_out/${tag}_scale_n${n}_$1_s$2
