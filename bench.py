@@ -160,6 +160,7 @@ class Ctx:
         self.clocks = ClockSampler(self.local_rank)
         self.args = args
         self.align_buf = torch.zeros(1, dtype=torch.float32, device="cuda") if self.world > 1 else None
+        self.align = False  # set by the sharded benches (see flush())
 
     def flush(self):
         # write 256 MiB (evicts everything), then read another 256 MiB so that the L2 is left holding
@@ -167,10 +168,13 @@ class Ctx:
         self.flush_val = (self.flush_val + 1) & 0xFF
         self.flush_buf.fill_(self.flush_val)
         self.flush_src.sum()
-        if self.world > 1 and os.environ.get("MRL_BENCH_ALIGN", "0") == "1":
-            # opt-in experiment: re-align the ranks after the flush with an (untimed) all-reduce.  Measured at
-            # N=8: WORSE (33.8 us/step against 28.7 free-running) -- the ranks leave the all-reduce further
-            # apart than the previous step's exchange left them.  Off by default.
+        if self.world > 1 and self.align:
+            # Opt-in (MRL_BENCH_ALIGN=1): re-align the ranks after the flush with an untimed 4-byte all-reduce.  The
+            # sharded step is lock-step across ranks with one step of slack, so the microseconds by which one rank's
+            # UNTIMED flush runs longer than another's come back as waits inside the other ranks' TIMED step (measured
+            # at N = 8: up to 2.7 us per step on the rank that waits most, exchange_wait_us).  Aligning removes those
+            # waits but the step that follows an NCCL kernel starts 1.7 us slower (measured at N = 2: 20.2 us aligned
+            # against 18.5 us free-running), as round 1 had found: the headline stays the free-running loop.
             self.dist.all_reduce(self.align_buf)
 
     def barrier(self):
@@ -389,7 +393,18 @@ def bench_per(ctx, name, rows, batch, steps, warmup, primary, sharded=None, pari
 
     if p2p:
         ffi.check(L.mrl_prb_shard_diag(h, None, None, None, None, 1, st))  # reset the exchange counters
+    free_running = None
+    if sharded and os.environ.get("MRL_BENCH_ALIGN", "0") == "1":
+        fr_ms, _ = ctx.timed(step, steps, warmup)
+        free_running = {"value": world_eff * batch * steps / (fr_ms * 1e-3), "ms_per_step": fr_ms / steps,
+                        "note": "the same loop without the untimed per-iteration all-reduce that re-aligns the ranks "
+                                "after the L2 flush: flush-time differences between the GPUs show up as waits in the "
+                                "timed sample step of the faster ranks"}
+        if p2p:
+            ffi.check(L.mrl_prb_shard_diag(h, None, None, None, None, 1, st))
+        ctx.align = True
     total_ms, launches = ctx.timed(step, steps, warmup, sample_clocks=primary)
+    ctx.align = False
     value = world_eff * batch * steps / (total_ms * 1e-3)
     exchange_info = None
     if p2p:
@@ -408,7 +423,7 @@ def bench_per(ctx, name, rows, batch, steps, warmup, primary, sharded=None, pari
         ffi.check(L.mrl_prb_destroy(h))
         return {"workload": name, "metric": "per_sample_update_samples_per_s", "value": value, "unit": "samples/s",
                 "ms_per_step": total_ms / steps, "steps": steps, "gpu_launches": launches,
-                "parity_check": check, "exchange": exchange_info}
+                "parity_check": check, "exchange": exchange_info, "free_running": free_running}
 
     # ---- per-kernel durations for the roofline (same flush discipline) -------------------
     ksteps = max(20, min(steps, 300))
@@ -504,7 +519,7 @@ def bench_per(ctx, name, rows, batch, steps, warmup, primary, sharded=None, pari
             "unit": "samples/s", "ms_per_step": total_ms / steps, "steps": steps,
             "gpu_launches": launches, "roofline": roofline, "e2e": e2e,
             "algorithmic_bytes_per_sample": 2 * R + 28 * L_1M + 36, "parity_check": check,
-            "exchange": exchange_info}
+            "exchange": exchange_info, "free_running": free_running}
 
 
 def bench_urb(ctx, steps, warmup):
@@ -970,7 +985,7 @@ def main():
         r = bench_per(ctx, C5_NAME, C2_ROWS, 4096, c5_steps, args.warmup, primary is None)
         c5 = {"workload": C5_NAME, "metric": r["metric"], "unit": r["unit"], "value": r["value"], "n_gpus": ctx.world,
               "ms_per_step": r["ms_per_step"], "steps": r["steps"], "e2e": r["e2e"]["value"],
-              "parity_check": r["parity_check"], "exchange": r["exchange"]}
+              "parity_check": r["parity_check"], "exchange": r["exchange"], "free_running": r["free_running"]}
         if ctx.world > 1:
             solo = bench_per(ctx, C5_NAME + " (un-sharded, every rank alone)", C2_ROWS, 4096, c5_steps, args.warmup,
                              False, sharded=False, parity=False, details=False)
@@ -1025,7 +1040,8 @@ def main():
         cfg = headline_config(ctx.world)
         cfg["workload"] = primary["workload"]
         if ctx.world > 1 and os.environ.get("MRL_BENCH_ALIGN", "0") == "1":
-            cfg["l2"] += "; ranks re-aligned after every flush by an untimed 4-byte NCCL all-reduce"
+            cfg["l2"] += ("; at N > 1 the ranks are re-aligned after every flush by an untimed 4-byte NCCL all-reduce "
+                          "(the free-running loop is reported as free_running)")
         line = {
             "metric": primary["metric"], "value": primary["value"], "unit": primary["unit"],
             "n_gpus": ctx.world, "steps": primary["steps"], "warmup": args.warmup,
@@ -1036,6 +1052,7 @@ def main():
             "e2e": primary["e2e"], "gpu_launches": primary.get("gpu_launches"),
             "roofline": primary.get("roofline"), "cpu_baseline": primary.get("cpu_baseline"),
             "parity_check": primary.get("parity_check"), "exchange": primary.get("exchange"),
+            "free_running": primary.get("free_running"),
             "algorithmic_bytes_per_sample": primary.get("algorithmic_bytes_per_sample"),
             "variants": primary.get("variants"),
             "c5": c5,

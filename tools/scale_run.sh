@@ -27,6 +27,7 @@ try:
     print(sys.argv[1], "N", d["n_gpus"], "value %.2fM" % (d["value"] / 1e6), "us/step %.2f" % (d["ms_per_step"] * 1e3),
           "e2e %.2fM" % (d["e2e"]["value"] / 1e6), "parity", (d.get("parity_check") or {}).get("ok"),
           "wait_us %.2f waited %s" % (ex.get("exchange_wait_us", 0), ex.get("calls_that_waited")),
+          "free %.2fM" % (((d.get("free_running") or {}).get("value") or 0) / 1e6),
           "c5eff", (d.get("c5") or {}).get("weak_scaling_efficiency_vs_same_run_single_gpu"))
 except Exception as e:
     print(sys.argv[1], "FAILED", e)
