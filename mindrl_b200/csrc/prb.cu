@@ -1586,6 +1586,34 @@ __global__ void prb_stats_kernel(const float *sum, const float *mn, const PrbSta
   out4[3] = state->max_priority;
 }
 
+// mrl_prb_shard_wait: one warp polls the local inbox until the words the NEXT sample will expect are there
+// (bounded like the sample kernel's own poll)
+__global__ void __launch_bounds__(32)
+    prb_shard_wait_kernel(const uint2 *mailbox, int world, int rank, unsigned int slot, unsigned int expect,
+                          long long timeout_ns, int *err) {
+  const int lane = threadIdx.x;
+  if (lane >= world || lane == rank) return;
+  const uint2 *src = mailbox + ((size_t)slot * world + lane) * 4;
+  long long t0 = 0;
+  unsigned int spins = 0;
+  while (true) {
+    uint2 a, b, c;
+    asm volatile("ld.relaxed.sys.global.v2.u32 {%0,%1}, [%2];" : "=r"(a.x), "=r"(a.y) : "l"(src) : "memory");
+    asm volatile("ld.relaxed.sys.global.v2.u32 {%0,%1}, [%2];" : "=r"(b.x), "=r"(b.y) : "l"(src + 1) : "memory");
+    asm volatile("ld.relaxed.sys.global.v2.u32 {%0,%1}, [%2];" : "=r"(c.x), "=r"(c.y) : "l"(src + 2) : "memory");
+    if (a.y == expect && b.y == expect && c.y == expect) return;
+    if ((++spins & 1023u) == 0u) {
+      long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      if (now - t0 > timeout_ns) {
+        if (err) *reinterpret_cast<volatile int *>(err) = 1 + lane;
+        return;
+      }
+    }
+  }
+}
+
 // tail of the mutating calls that have no single kernel which ends with the root in hand (batched push,
 // set_state, connect, and a sample that follows a sample): one warp reads the root and publishes it
 __global__ void __launch_bounds__(32) prb_publish_kernel(const float *sum, const float *mn, const PublishArgs pub) {
@@ -2267,6 +2295,22 @@ extern "C" int mrl_prb_shard_connect(int64_t handle, const void *all_ipc_handles
   // kPublishOnMutation: the state the buffer has now is publication number 1 (every peer's mailbox exists
   // since its own mrl_prb_shard_init, which precedes the exchange of the handles)
   return publish_tail(b, as_stream(stream));
+}
+
+extern "C" int mrl_prb_shard_wait(int64_t handle, void *stream) {
+  PRB_GET(b, handle);
+  ShardLink &k = b->link;
+  MRL_REQUIRE(k.peer_dev, "mrl_prb_shard_wait: mailboxes are not connected");
+  if (k.mode != kPublishOnMutation || k.world < 2) return MRL_OK;  // nothing is in flight between samples
+  cudaStream_t st = as_stream(stream);
+  if (k.published_epoch != k.epoch) {  // the coming sample's slot holds nothing yet: what the sample call would do
+    const int rc = publish_tail(b, st, false);
+    if (rc) return rc;
+  }
+  prb_shard_wait_kernel<<<1, 32, 0, st>>>(k.mailbox, k.world, k.rank, k.epoch & 1u, k.version, g_shard_timeout_ns,
+                                          k.err_dev);
+  MRL_LAUNCHED();
+  return MRL_OK;
 }
 
 extern "C" int mrl_prb_shard_diag(int64_t handle, int64_t *wait_cycles, int64_t *polled_calls,

@@ -78,8 +78,13 @@ def main():
 
         for step in range(steps):
             u = rng.random(batch).astype(np.float32)
+            if step % 2:  # the optional early wait for the peers (also in front of consecutive samples below)
+                for s in sh.values():
+                    s.wait_for_peers()
             outs, want = sample_all(0.4, u)
             if step % 3 == 1:  # a second sample with nothing in between: the statistics are re-published
+                if step % 2:
+                    sh["p2p"].wait_for_peers()
                 outs, want = sample_all(0.5, rng.random(batch).astype(np.float32))
             update_all(outs, want, (rng.random(batch) * 2 + 0.01).astype(np.float32))
             if step % 2 == 0:  # actors keep inserting between the learner's samples: single rows and a batch
