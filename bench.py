@@ -179,9 +179,12 @@ class Ctx:
             self.ffi.check(self.L.mrl_prb_shard_wait(self.align, self.stream))
 
     def barrier(self):
+        # (device work first: a rank must not pass the barrier -- and, say, free a mailbox its peers' courier
+        # kernels still write into -- while another rank's kernels are in flight)
+        self.torch.cuda.synchronize()
         if self.world > 1:
             self.dist.barrier()
-        self.torch.cuda.synchronize()
+            self.torch.cuda.synchronize()
 
     def max_over_ranks(self, x):
         if self.world == 1:

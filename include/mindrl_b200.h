@@ -244,6 +244,9 @@ int mrl_prb_sample_sharded(int64_t handle, int64_t n, float beta, const float *u
  *   5. mrl_prb_sample_sharded_p2p.  A kernel that sees no word from a peer for "shard_timeout_ms" gives up
  *      (weights NaN) and raises the link's error word: the *_host variant and every later call on the handle
  *      return MRL_ERR_STATE instead of hanging the GPU.
+ * Tear-down: the peers' kernels write into this rank's mailbox, so destroy a sharded buffer only after every rank
+ * has drained its streams (synchronise, then barrier) -- CUDA IPC leaves freeing exported memory that a peer still
+ * uses undefined.
  * mrl_prb_shard_diag reads (and optionally resets) the exchange counters: SM cycles warp 0 spent polling,
  * calls that polled, calls whose first look missed a word, timeouts.  Synchronises `stream`. */
 int mrl_prb_shard_init(int64_t handle, int32_t rank, int32_t world, void *ipc_handle_out);
