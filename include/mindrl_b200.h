@@ -94,7 +94,8 @@ int64_t mrl_launch_count(void);
  *       6 TMA strips whenever aligned; "strip_cols" [0 = 32], "strip_rpu" [0 = 32 steps per lane and tile, 16 for GAE with returns], "strip_groups" [0 = 1],
  *       "strip_stages" [0 = as many as fit], "strip_min_cols" [2048]
  *   "bm_kernel" [0]: batch-major scans: 0 auto, 1 warp-per-row register kernel, 2 TMA rows whenever aligned;
- *       "row_ctas_per_sm" [4], "row_stages" [0 = from row_ctas_per_sm]
+ *       "row_ctas_per_sm" [4], "row_stages" [0 = from row_ctas_per_sm], "row_spl" [8] steps per lane (16: four
+ *       consumer warps per CTA; measured slower)
  *   "host_scan_chunks" [0 = ~16 MB of input per piece]: pieces of the *_host scans (1 = no pipelining)
  *   "shard_weights" [0]: importance weights of the SHARDED sample.  0: against the global sum,
  *       minimum and size, (p / sum_all * N)^-beta / (min_all / sum_all * N)^-beta -- exact when all shards carry the

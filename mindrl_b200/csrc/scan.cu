@@ -1017,7 +1017,7 @@ static int ws_reserve(uint8_t **buf, size_t *have, size_t need, bool zero, cudaS
 static int g_tile_mode = -1;  // MRL_TM_KERNEL=chunked forces the two-pass kernel
 static int64_t g_host_chunks = 0;  // option "host_scan_chunks": pieces of the *_host scans, 0 = auto, 1 = no pipelining
 static int g_bm_mode = 0;     // 0 auto, 1 warp-per-row register kernel only, 2 TMA row kernel whenever it fits
-extern int64_t g_strip_cols, g_strip_rpu, g_strip_min_cols, g_strip_stages, g_strip_groups, g_row_ctas_per_sm, g_row_stages;  // scan_tma.cu
+extern int64_t g_strip_cols, g_strip_rpu, g_strip_min_cols, g_strip_stages, g_strip_groups, g_row_ctas_per_sm, g_row_stages, g_row_spl;  // scan_tma.cu
 
 // "tm_kernel": 0 auto, 2 two-pass chunked, 3 128-column CTA tiles, 5 warp tiles with look-back,
 // 6 TMA strips whenever the alignment allows; "strip_cols": 0 auto / 16 / 32; "bm_kernel": see g_bm_mode
@@ -1026,7 +1026,8 @@ int set_scan_option(const char *key, int64_t value) {
   if (k == "tm_kernel" && (value == 0 || value == 2 || value == 3 || value == 5 || value == 6)) g_tile_mode = (int)value;
   else if (k == "strip_cols" && (value == 0 || value == 16 || value == 32)) g_strip_cols = value;
   else if (k == "strip_rpu" && (value == 0 || value == 8 || value == 16 || value == 32)) g_strip_rpu = value;
-  else if (k == "row_ctas_per_sm" && value >= 1 && value <= 7) g_row_ctas_per_sm = value;
+  else if (k == "row_ctas_per_sm" && value >= 1 && value <= 12) g_row_ctas_per_sm = value;
+  else if (k == "row_spl" && (value == 8 || value == 16)) g_row_spl = value;
   else if (k == "row_stages" && value >= 0 && value <= 12) g_row_stages = value;
   else if (k == "strip_groups" && value >= 0 && value <= 2) g_strip_groups = value;
   else if (k == "strip_stages" && value >= 0 && value <= 12) g_strip_stages = value;

@@ -542,27 +542,37 @@ int scan_tm_strip_launch(const ScanArgs &A, int op, bool force, cudaStream_t st,
 namespace {
 
 constexpr int BM_L = 2048;
-constexpr int BM_SUB = 8;   // 256-step pieces per tile, one per warp
 
-template <int OP, bool HD, bool NVF>
+// SPL = consecutive steps a lane owns in a tile: 8 (8 consumer warps, the default) or 16 (4 consumer warps: half the
+// shuffle scans, barriers and chain links per element, 160-thread CTAs -- option "row_spl").  Measured at C4 (round 2,
+// tools/rows_sweep.sh): 16 steps per lane is SLOWER, GAE 32.9 against 28.4 us and DiscountedReturn 20.7 against 19.5 us
+// at any number of resident CTAs, and 4 steps per lane (16 warps) slower still (35 / 29 us): the rows are bound by the
+// latency of their own dependent chain per tile, which fewer warps hide worse, not by instruction issue.
+template <int OP, bool HD, bool NVF, int SPL>
 struct RowCfg {
+  static constexpr int kW = BM_L / (32 * SPL);  // consumer warps
+  static constexpr int kThreads = (kW + 1) * 32;
   static constexpr int kOffV = BM_L * 4;
   static constexpr int kOffNV = kOffV + (OP != OP_DR ? BM_L * 4 + 128 : 0);  // +: sv[BM_L] stays in bounds
   static constexpr int kOffD = kOffNV + (NVF ? BM_L * 4 : 0);
   static constexpr int kStage = kOffD + (HD ? BM_L : 0);
   static constexpr int kNOut = OP == OP_GAE ? 2 : 1;
-  static constexpr int kWarpOut = BM_L / kWarps;  // 256 floats
-  static constexpr int kOutBytes = kWarps * 2 * kNOut * kWarpOut * 4;
-  static constexpr int kCompBytes = 2 * BM_SUB * 8;
+  static constexpr int kWarpOut = BM_L / kW;  // floats a warp produces per tile and output array
+  static constexpr int kOutBytes = kW * 2 * kNOut * kWarpOut * 4;
+  static constexpr int kCompBytes = 2 * 16 * 8 > 16 * 16 ? 2 * 16 * 8 : 16 * 16;  // maps [2][16], or 16 double2 partials
   static constexpr int smem_bytes(int stages) {
     return stages * kStage + kOutBytes + kCompBytes + 2 * kMaxStages * 8;
   }
 };
 
-template <int OP, bool HD, bool NVF, bool MOM>
-__global__ void __launch_bounds__(kThreads)
+template <int NT>
+__device__ __forceinline__ void row_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
+
+template <int OP, bool HD, bool NVF, bool MOM, int SPL>
+__global__ void __launch_bounds__((BM_L / (32 * SPL) + 1) * 32)
     scan_bm_row_kernel(const __grid_constant__ ScanArgs A, int n_chunks, int n_stages) {
-  using C = RowCfg<OP, HD, NVF>;
+  using C = RowCfg<OP, HD, NVF, SPL>;
+  constexpr int W = C::kW;
   extern __shared__ __align__(1024) unsigned char row_raw[];
   unsigned char *stages = row_raw;
   float *ostage = reinterpret_cast<float *>(stages + n_stages * C::kStage);
@@ -578,13 +588,13 @@ __global__ void __launch_bounds__(kThreads)
   if (threadIdx.x == 0) {
     for (int s = 0; s < n_stages; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], kWarps);
+      mbar_init(&empty[s], W);
     }
     fence_async_smem();
   }
   __syncthreads();
 
-  if (warp == kWarps) {  // ---- producer ----
+  if (warp == W) {  // ---- producer ----
     if (lane == 0) {
       int64_t row = blockIdx.x;
       int c = 0;
@@ -611,7 +621,7 @@ __global__ void __launch_bounds__(kThreads)
   }
 
   // ---- consumers ----
-  // warp w owns positions [256w, 256w+256) of the tile, lane l the 8 consecutive steps 256w+8l..+7
+  // warp w owns positions [32*SPL*w, 32*SPL*(w+1)) of the tile, lane l the SPL consecutive steps from 32*SPL*w + SPL*l
   constexpr unsigned FULL = 0xffffffffu;
   const bool want_ret = OP == OP_GAE && A.ret != nullptr;
   double msum = 0.0, msq = 0.0;  // (MOM) moments of `out` for the normalisation that follows
@@ -621,7 +631,7 @@ __global__ void __launch_bounds__(kThreads)
   float last_next = (use_last && n_rows > 0) ? __ldg(A.last + blockIdx.x) : 0.0f;
   int64_t row = blockIdx.x;
   int c = 0;
-  const int p0 = warp * 256 + 8 * lane;
+  const int p0 = warp * (32 * SPL) + SPL * lane;
   int s = 0;
   uint32_t ph = 0;
 
@@ -637,50 +647,48 @@ __global__ void __launch_bounds__(kThreads)
     }
     mbar_wait(&full[s], ph);
     const unsigned char *sb = stages + s * C::kStage;
-    float ea[8], eb[8], aux[8];
+    float ea[SPL], eb[SPL], aux[SPL];
     float v_first = 0.0f;
     {
-      float rr[8], vq[9], nq[8];
-      uint2 dd = make_uint2(0u, 0u);
+      float rr[SPL], vq[SPL + 1], nq[SPL];
+      uint32_t dd[SPL / 4];
       float edge = 0.0f;
-      {
-        const float4 r0 = *reinterpret_cast<const float4 *>(sb + 4 * p0);
-        const float4 r1 = *reinterpret_cast<const float4 *>(sb + 4 * p0 + 16);
-        rr[0] = r0.x, rr[1] = r0.y, rr[2] = r0.z, rr[3] = r0.w, rr[4] = r1.x, rr[5] = r1.y, rr[6] = r1.z, rr[7] = r1.w;
+#pragma unroll
+      for (int q = 0; q < SPL / 4; ++q) {
+        const float4 r4 = *reinterpret_cast<const float4 *>(sb + 4 * p0 + 16 * q);
+        rr[4 * q] = r4.x, rr[4 * q + 1] = r4.y, rr[4 * q + 2] = r4.z, rr[4 * q + 3] = r4.w;
+        if (OP != OP_DR) {
+          const float4 v4 = *reinterpret_cast<const float4 *>(sb + C::kOffV + 4 * p0 + 16 * q);
+          vq[4 * q] = v4.x, vq[4 * q + 1] = v4.y, vq[4 * q + 2] = v4.z, vq[4 * q + 3] = v4.w;
+        }
+        if (NVF) {
+          const float4 n4 = *reinterpret_cast<const float4 *>(sb + C::kOffNV + 4 * p0 + 16 * q);
+          nq[4 * q] = n4.x, nq[4 * q + 1] = n4.y, nq[4 * q + 2] = n4.z, nq[4 * q + 3] = n4.w;
+        }
+        dd[q] = HD ? *reinterpret_cast<const uint32_t *>(sb + C::kOffD + p0 + 4 * q) : 0u;
       }
-      if (OP != OP_DR) {
-        const float4 v0 = *reinterpret_cast<const float4 *>(sb + C::kOffV + 4 * p0);
-        const float4 v1 = *reinterpret_cast<const float4 *>(sb + C::kOffV + 4 * p0 + 16);
-        vq[0] = v0.x, vq[1] = v0.y, vq[2] = v0.z, vq[3] = v0.w, vq[4] = v1.x, vq[5] = v1.y, vq[6] = v1.z, vq[7] = v1.w;
-      }
-      if (NVF) {
-        const float4 n0 = *reinterpret_cast<const float4 *>(sb + C::kOffNV + 4 * p0);
-        const float4 n1 = *reinterpret_cast<const float4 *>(sb + C::kOffNV + 4 * p0 + 16);
-        nq[0] = n0.x, nq[1] = n0.y, nq[2] = n0.z, nq[3] = n0.w, nq[4] = n1.x, nq[5] = n1.y, nq[6] = n1.z, nq[7] = n1.w;
-      }
-      if (HD) dd = *reinterpret_cast<const uint2 *>(sb + C::kOffD + p0);
       if (OP == OP_GAE && !NVF) {
-        if (lane == 31) edge = *reinterpret_cast<const float *>(sb + C::kOffV + 4 * (p0 + 8));
+        if (lane == 31) edge = *reinterpret_cast<const float *>(sb + C::kOffV + 4 * (p0 + SPL));
         v_first = *reinterpret_cast<const float *>(sb + C::kOffV);
       }
       release_stage(&empty[s], lane);
       const bool whole = len == BM_L;  // (block-uniform) no step of the tile lies past the chunk
       if (OP == OP_GAE && !NVF) {
         const float nb = __shfl_down_sync(FULL, vq[0], 1);
-        vq[8] = lane == 31 ? edge : nb;
-        if (p0 + 8 >= len) vq[8] = v_after;  // the chunk ends inside or right after this lane's run
+        vq[SPL] = lane == 31 ? edge : nb;
+        if (p0 + SPL >= len) vq[SPL] = v_after;  // the chunk ends inside or right after this lane's run
         if (!whole) {
 #pragma unroll
-          for (int q = 1; q < 8; ++q)
+          for (int q = 1; q < SPL; ++q)
             if (p0 + q >= len) vq[q] = v_after;  // only read as V[t+1] of the last valid step
         }
       }
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
+      for (int q = 0; q < SPL; ++q) {
         if (OP == OP_AFFINE) {
           ea[q] = rr[q], eb[q] = vq[q], aux[q] = 0.0f;
         } else {
-          const bool dn = HD && (((q < 4 ? dd.x : dd.y) >> (8 * (q & 3))) & 0xffu) != 0u;
+          const bool dn = HD && ((dd[q >> 2] >> (8 * (q & 3))) & 0xffu) != 0u;
           if (OP == OP_DR) {
             ea[q] = rr[q], eb[q] = dn ? 0.0f : A.gamma, aux[q] = 0.0f;
           } else {
@@ -693,14 +701,14 @@ __global__ void __launch_bounds__(kThreads)
       }
       if (!whole) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
+        for (int q = 0; q < SPL; ++q)
           if (p0 + q >= len) ea[q] = 0.0f, eb[q] = 1.0f;  // past the chunk: identity map
       }
     }
-    // per lane: 8 steps as one map; then a suffix scan over the lanes (later time = higher lane)
+    // per lane: SPL steps as one map; then a suffix scan over the lanes (later time = higher lane)
     float ca = 0.0f, cb = 1.0f;
 #pragma unroll
-    for (int q = 7; q >= 0; --q) {
+    for (int q = SPL - 1; q >= 0; --q) {
       ca = fstep(ea[q], eb[q], ca);
       cb = __fmul_rn(eb[q], cb);
     }
@@ -712,12 +720,12 @@ __global__ void __launch_bounds__(kThreads)
       ca = fstep(ca, cb, oa_);
       cb = __fmul_rn(cb, ob_);
     }
-    float2 *cbuf = comp + (k & 1) * BM_SUB;
+    float2 *cbuf = comp + (k & 1) * 16;
     if (lane == 0) cbuf[warp] = make_float2(ca, cb);
-    consumer_barrier();
+    row_barrier<32 * W>();
     float x = X, xin = X;
 #pragma unroll
-    for (int u = kWarps - 1; u >= 0; --u) {
+    for (int u = W - 1; u >= 0; --u) {
       if (u == warp) xin = x;
       const float2 m = cbuf[u];
       x = fstep(m.x, m.y, x);
@@ -732,17 +740,17 @@ __global__ void __launch_bounds__(kThreads)
       const float x_here = fstep(ca, cb, xin);            // x at this lane's first step
       float xe = __shfl_down_sync(FULL, x_here, 1);       // x right after this lane's run
       if (lane == 31) xe = xin;
-      float o[8], o2[8];
+      float o[SPL], o2[SPL];
 #pragma unroll
-      for (int q = 7; q >= 0; --q) {
+      for (int q = SPL - 1; q >= 0; --q) {
         xe = fstep(ea[q], eb[q], xe);
         o[q] = xe;
         o2[q] = __fadd_rn(xe, aux[q]);
       }
-      if (MOM) {  // fp32 over the lane's 8 steps, float64 across tiles
+      if (MOM) {  // fp32 over the lane's steps, float64 across tiles
         float tsum = 0.0f, tsq = 0.0f;
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
+        for (int q = 0; q < SPL; ++q)
           if (p0 + q < len) {
             tsum = __fadd_rn(tsum, o[q]);
             tsq = __fmaf_rn(o[q], o[q], tsq);
@@ -750,13 +758,13 @@ __global__ void __launch_bounds__(kThreads)
         msum += (double)tsum;
         msq += (double)tsq;
       }
-      float4 *dst = reinterpret_cast<float4 *>(oa + 8 * lane);
-      dst[0] = make_float4(o[0], o[1], o[2], o[3]);
-      dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+      float4 *dst = reinterpret_cast<float4 *>(oa + SPL * lane);
+#pragma unroll
+      for (int q = 0; q < SPL / 4; ++q) dst[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
       if (want_ret) {
-        float4 *dst2 = reinterpret_cast<float4 *>(oa + C::kWarpOut + 8 * lane);
-        dst2[0] = make_float4(o2[0], o2[1], o2[2], o2[3]);
-        dst2[1] = make_float4(o2[4], o2[5], o2[6], o2[7]);
+        float4 *dst2 = reinterpret_cast<float4 *>(oa + C::kWarpOut + SPL * lane);
+#pragma unroll
+        for (int q = 0; q < SPL / 4; ++q) dst2[q] = make_float4(o2[4 * q], o2[4 * q + 1], o2[4 * q + 2], o2[4 * q + 3]);
       }
     }
     fence_async_smem();
@@ -774,31 +782,31 @@ __global__ void __launch_bounds__(kThreads)
     if (++c == n_chunks) c = 0, row += G;
     if (++s == n_stages) s = 0, ph ^= 1u;
   }
-  if (MOM) {  // fixed-order fold: lanes, then the 8 warps in order -> one partial per CTA
+  if (MOM) {  // fixed-order fold: lanes, then the warps in order -> one partial per CTA
 #pragma unroll
     for (int off = 16; off; off >>= 1) {
       msum += __shfl_xor_sync(FULL, msum, off);
       msq += __shfl_xor_sync(FULL, msq, off);
     }
     double2 *red = reinterpret_cast<double2 *>(comp);
-    consumer_barrier();  // every warp has read its last maps
+    row_barrier<32 * W>();  // every warp has read its last maps
     if (lane == 0) red[warp] = make_double2(msum, msq);
-    consumer_barrier();
+    row_barrier<32 * W>();
     if (warp == 0 && lane == 0) {
       double a = 0.0, b = 0.0;
-      for (int w = 0; w < kWarps; ++w) a += red[w].x, b += red[w].y;
+      for (int w = 0; w < W; ++w) a += red[w].x, b += red[w].y;
       A.mom[blockIdx.x] = make_double2(a, b);
     }
   }
   if (lane == 0) bulk_wait_all();
 }
 
-template <int OP, bool HD, bool NVF, bool MOM>
+template <int OP, bool HD, bool NVF, bool MOM, int SPL>
 int row_launch_m(ScanArgs A, cudaStream_t st, int *mom_parts) {
-  using C = RowCfg<OP, HD, NVF>;
+  using C = RowCfg<OP, HD, NVF, SPL>;
   if (!MOM) A.mom = nullptr;
-  if (first_use_on_device((const void *)scan_bm_row_kernel<OP, HD, NVF, MOM>))
-    MRL_CUDA(cudaFuncSetAttribute(scan_bm_row_kernel<OP, HD, NVF, MOM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  if (first_use_on_device((const void *)scan_bm_row_kernel<OP, HD, NVF, MOM, SPL>))
+    MRL_CUDA(cudaFuncSetAttribute(scan_bm_row_kernel<OP, HD, NVF, MOM, SPL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   C::smem_bytes(kMaxStages) < 226 * 1024 ? C::smem_bytes(kMaxStages) : 226 * 1024));
   const int n_chunks = (int)((A.T + BM_L - 1) / BM_L);
   // ring depth: the SM's shared memory split between g_row_ctas_per_sm resident CTAs
@@ -809,19 +817,30 @@ int row_launch_m(ScanArgs A, cudaStream_t st, int *mom_parts) {
   const int smem = C::smem_bytes(stages);
   // as many CTAs as fit at once, trimmed so that every CTA gets the same number of rows
   int fit = (227 * 1024) / (smem + 1024);
-  fit = fit > 7 ? 7 : (fit < 1 ? 1 : fit);  // 2048 threads per SM / 288
+  const int by_threads = 2048 / C::kThreads;
+  fit = fit > by_threads ? by_threads : (fit < 1 ? 1 : fit);
   const int64_t max_ctas = (int64_t)sm_count() * fit;
   const int64_t per = (A.N + max_ctas - 1) / max_ctas;
   const int64_t ctas = (A.N + per - 1) / per;
-  scan_bm_row_kernel<OP, HD, NVF, MOM><<<(unsigned)ctas, kThreads, smem, st>>>(A, n_chunks, stages);
-  if (mom_parts) *mom_parts = MOM ? (int)ctas : 0;  // (ctas <= 7 * SMs < kMomentSlots)
+  scan_bm_row_kernel<OP, HD, NVF, MOM, SPL><<<(unsigned)ctas, C::kThreads, smem, st>>>(A, n_chunks, stages);
+  if (mom_parts) *mom_parts = MOM ? (int)ctas : 0;  // (ctas <= 12 * SMs < kMomentSlots)
   return MRL_OK;
 }
 
+}  // namespace
+int64_t g_row_spl = 8;  // option "row_spl": steps per lane of the batch-major rows (8 or 16)
+namespace {
+
 template <int OP, bool HD, bool NVF>
 int row_launch(const ScanArgs &A, cudaStream_t st, int *mom_parts) {
-  if (A.mom && OP != OP_AFFINE) return row_launch_m<OP, HD, NVF, OP != OP_AFFINE>(A, st, mom_parts);
-  return row_launch_m<OP, HD, NVF, false>(A, st, mom_parts);
+  constexpr bool kMomOk = OP != OP_AFFINE;
+  if (g_row_spl == 16) {
+    if (A.mom && kMomOk) return row_launch_m<OP, HD, NVF, kMomOk, 16>(A, st, mom_parts);
+    return row_launch_m<OP, HD, NVF, false, 16>(A, st, mom_parts);
+  }
+
+  if (A.mom && kMomOk) return row_launch_m<OP, HD, NVF, kMomOk, 8>(A, st, mom_parts);
+  return row_launch_m<OP, HD, NVF, false, 8>(A, st, mom_parts);
 }
 
 }  // namespace

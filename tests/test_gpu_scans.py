@@ -259,7 +259,7 @@ def test_normalize_advantage(n):
 class _options:
     """sets library options for the duration of a test and restores the defaults afterwards"""
     DEFAULTS = {"host_scan_chunks": 0, "tm_kernel": 0, "strip_cols": 0, "strip_rpu": 0, "strip_groups": 0, "strip_stages": 0,
-                "bm_kernel": 0, "row_stages": 0}
+                "bm_kernel": 0, "row_stages": 0, "row_spl": 8}
 
     def __init__(self, **kw):
         self.kw = kw
@@ -316,10 +316,12 @@ def test_tma_strip_kernels(cols, rpu, groups, stages):
                   O.affine_scan(r, b, lv, layout=0))
 
 
+@pytest.mark.parametrize("spl", [8, 16])
 @pytest.mark.parametrize("stages", [0, 2, 3])
-def test_tma_row_kernel(stages):
-    """batch-major rows: several chunks per environment, a partial last chunk, T below one tile"""
-    with _options(bm_kernel=2, row_stages=stages):
+def test_tma_row_kernel(stages, spl):
+    """batch-major rows: several chunks per environment, a partial last chunk, T below one tile; 8 steps per lane
+    (8 consumer warps) and 16 steps per lane (4 consumer warps)"""
+    with _options(bm_kernel=2, row_stages=stages, row_spl=spl):
         for B, T in [(1, 4), (3, 16), (7, 128), (30, 1000), (17, 144), (64, 2048), (5, 4096), (9, 2064), (2, 4112),
                      (300, 512), (3, 6160), (8, 16384)]:
             rng = np.random.default_rng(B * 1009 + T)
