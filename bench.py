@@ -1074,7 +1074,7 @@ def main():
             "parity_check": primary.get("parity_check"), "exchange": primary.get("exchange"),
             "free_running": primary.get("free_running"),
             "algorithmic_bytes_per_sample": primary.get("algorithmic_bytes_per_sample"),
-            "variants": primary.get("variants"),
+            "variants": primary.get("variants"), "scan_error": primary.get("scan_error"),
             "c5": c5,
             "also": also,
         }

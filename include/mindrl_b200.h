@@ -91,7 +91,7 @@ int64_t mrl_launch_count(void);
  *       pinned memory (0: device arena + one DMA; measured 6 us slower per call)
  *   "inline_update" [1]: mrl_prb_update_host passes batches <= 256 in the kernel parameter block
  *   "tm_kernel" [0]: time-major scans: 0 auto, 2 two-pass, 3 128-column tiles, 5 warp tiles + look-back,
- *       6 TMA strips whenever aligned; "strip_cols" [0 = 32], "strip_rpu" [0 = 32 steps per lane and tile, 16 for GAE with returns], "strip_groups" [0 = 1],
+ *       6 TMA strips whenever aligned; "strip_cols" [0 = 32] (16, 28: measured slower), "strip_rpu" [0 = 32 steps per lane and tile, 16 for GAE with returns], "strip_groups" [0 = 1],
  *       "strip_stages" [0 = as many as fit], "strip_min_cols" [2048]
  *   "bm_kernel" [0]: batch-major scans: 0 auto, 1 warp-per-row register kernel, 2 TMA rows whenever aligned;
  *       "row_ctas_per_sm" [4], "row_stages" [0 = from row_ctas_per_sm], "row_spl" [8] steps per lane (16: four

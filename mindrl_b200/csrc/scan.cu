@@ -1024,7 +1024,7 @@ extern int64_t g_strip_cols, g_strip_rpu, g_strip_min_cols, g_strip_stages, g_st
 int set_scan_option(const char *key, int64_t value) {
   std::string k(key);
   if (k == "tm_kernel" && (value == 0 || value == 2 || value == 3 || value == 5 || value == 6)) g_tile_mode = (int)value;
-  else if (k == "strip_cols" && (value == 0 || value == 16 || value == 32)) g_strip_cols = value;
+  else if (k == "strip_cols" && (value == 0 || value == 16 || value == 28 || value == 32)) g_strip_cols = value;
   else if (k == "strip_rpu" && (value == 0 || value == 8 || value == 16 || value == 32)) g_strip_rpu = value;
   else if (k == "row_ctas_per_sm" && value >= 1 && value <= 12) g_row_ctas_per_sm = value;
   else if (k == "row_spl" && (value == 8 || value == 16)) g_row_spl = value;

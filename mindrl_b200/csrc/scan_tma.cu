@@ -114,9 +114,13 @@ struct StripCfg {
   static constexpr int kRows = kUnits * RPU;              // steps per tile (64 .. 256)
   static constexpr int kVRows = OP == OP_GAE ? kRows + 1 : (OP == OP_AFFINE ? kRows : 0);
   static constexpr int kOffV = kRows * COLS * 4;
+  // done bytes per row in shared memory.  A TMA box starts on a 16-byte boundary and is a multiple of 16 bytes wide:
+  // a 28-column strip's flags start at byte 28k, so it loads the 48 bytes from the boundary below (an unaligned start
+  // is an illegal instruction, found the hard way) and reads them at an offset of 0, 4, 8 or 12
+  static constexpr int kDW = COLS % 16 == 0 ? COLS : (COLS + 30) / 16 * 16;
   static constexpr int kOffD = kOffV + (kVRows * COLS * 4 + 127) / 128 * 128;
-  static constexpr int kStage = kOffD + (HD ? kRows * COLS : 0);
-  static constexpr int kTx = kRows * COLS * 4 + kVRows * COLS * 4 + (HD ? kRows * COLS : 0);
+  static constexpr int kStage = kOffD + (HD ? kRows * kDW : 0);
+  static constexpr int kTx = kRows * COLS * 4 + kVRows * COLS * 4 + (HD ? kRows * kDW : 0);
   static constexpr int kNOut = OP == OP_GAE ? 2 : 1;
   static constexpr int kWarpRows = RPU * kUPW;            // rows one warp produces per tile
   static constexpr int kWarpOut = kWarpRows * COLS;       // floats per output array
@@ -191,7 +195,7 @@ __global__ void __launch_bounds__((NG * kWarps + 1) * 32)
         if (OP != OP_DR) tma_load_2d(sb + C::kOffV, &tm_v, col0, row0, &full[s]);
         // V of the first step after the tile (a box may have at most 256 rows, so it travels alone)
         if (OP == OP_GAE) tma_load_2d(sb + C::kOffV + C::kRows * COLS * 4, &tm_v1, col0, row0 + C::kRows, &full[s]);
-        if (HD) tma_load_2d(sb + C::kOffD, &tm_d, col0, row0, &full[s]);
+        if (HD) tma_load_2d(sb + C::kOffD, &tm_d, col0 & ~15, row0, &full[s]);
         if (++s == n_stages) s = 0, ph ^= 1u;
       }
     }
@@ -199,7 +203,8 @@ __global__ void __launch_bounds__((NG * kWarps + 1) * 32)
   }
 
   // ---- consumers ----
-  const int c = lane % COLS, h = lane / COLS;
+  // (COLS = 28: lanes 28..31 shadow lanes 0..3 -- same loads, same values to the same shared-memory words)
+  const int c = lane % COLS, h = (lane / COLS) % C::kUPW;
   const int grp = warp / kWarps, wl = warp % kWarps;
   const int unit = wl * C::kUPW + h;
   const int col = col0 + c;
@@ -210,7 +215,7 @@ __global__ void __launch_bounds__((NG * kWarps + 1) * 32)
     else X = l;
   }
   const bool want_ret = OP == OP_GAE && A.ret != nullptr;
-  const bool colok = col < A.N;
+  const bool colok = col < A.N && lane < C::kUPW * COLS;
   double msum = 0.0, msq = 0.0;  // (MOM) moments of `out` for the normalisation that follows
   float *my_out = ostage + warp * (n_obufs * C::kNOut * C::kWarpOut);
   int s = grp;  // (n_stages >= 2 >= NG)
@@ -234,9 +239,9 @@ __global__ void __launch_bounds__((NG * kWarps + 1) * 32)
         for (int i = 0; i < RPU + (OP == OP_GAE ? 1 : 0); ++i) vv[i] = sv[i * COLS];
       }
       if (HD) {
-        const unsigned char *sd = sb + C::kOffD + e0;
+        const unsigned char *sd = sb + C::kOffD + unit * RPU * C::kDW + (col0 & 15) + c;
 #pragma unroll
-        for (int i = 0; i < RPU; ++i) dd[i] = sd[i * COLS];
+        for (int i = 0; i < RPU; ++i) dd[i] = sd[i * C::kDW];
       }
       release_stage(&empty[s], lane);
       const int g0 = (n_tiles - 1 - k) * C::kRows + unit * RPU;  // global step of this lane's first row
@@ -449,7 +454,7 @@ int strip_launch(ScanArgs A, cudaStream_t st, int *mom_parts) {
   mv = ma, mv1 = ma, md = ma;
   if (OP != OP_DR && !make_map(&mv, A.v, false, A.T, A.N, COLS, C::kRows)) return kScanNotApplicable;
   if (OP == OP_GAE && !make_map(&mv1, A.v, false, A.T, A.N, COLS, 1)) return kScanNotApplicable;
-  if (HD && !make_map(&md, A.done, true, A.T, A.N, COLS, C::kRows)) return kScanNotApplicable;
+  if (HD && !make_map(&md, A.done, true, A.T, A.N, C::kDW, C::kRows)) return kScanNotApplicable;
   if (!make_map(&mo, A.out, false, A.T, A.N, COLS, C::kWarpRows)) return kScanNotApplicable;
   mr = mo;
   if (OP == OP_GAE && A.ret && !make_map(&mr, A.ret, false, A.T, A.N, COLS, C::kWarpRows))
@@ -499,6 +504,17 @@ int strip_launch_cols(const ScanArgs &A, int cols, int rpu, cudaStream_t st, int
   return rpu == 16 ? strip_launch<OP, HD, 32, 16, 1>(A, st, mp) : strip_launch<OP, HD, 32, 8, 1>(A, st, mp);
 }
 
+// 28-column strips: 4096 columns make 147 strips -- one per SM on all 148 -- where 32-column strips make 128
+template <int OP, bool HD>
+int strip_launch_28(const ScanArgs &A, int rpu, cudaStream_t st, int *mp) {
+  constexpr bool kMomOk = OP != OP_AFFINE;
+  if (rpu == 32) {
+    const int rc = (A.mom && kMomOk) ? strip_launch<OP, HD, 28, 32, 1, kMomOk>(A, st, mp) : strip_launch<OP, HD, 28, 32, 1>(A, st, mp);
+    if (rc != kScanNotApplicable) return rc;
+  }
+  return (A.mom && kMomOk) ? strip_launch<OP, HD, 28, 16, 1, kMomOk>(A, st, mp) : strip_launch<OP, HD, 28, 16, 1>(A, st, mp);
+}
+
 }  // namespace
 
 int64_t g_strip_cols = 0;     // 0 = auto, 16, 32
@@ -524,6 +540,11 @@ int scan_tm_strip_launch(const ScanArgs &A, int op, bool force, cudaStream_t st,
   // way and keeps the deeper ring of the 128-step tiles.  (Falls back to 16 when the strips do not get an SM each.)
   if (rpu == 0) rpu = (op == OP_GAE && A.ret) ? 16 : 32;
   int *mp = mom_parts;
+  if (cols == 28) {
+    if (op == OP_DR) return hd ? strip_launch_28<OP_DR, true>(A, rpu, st, mp) : strip_launch_28<OP_DR, false>(A, rpu, st, mp);
+    if (op == OP_GAE) return hd ? strip_launch_28<OP_GAE, true>(A, rpu, st, mp) : strip_launch_28<OP_GAE, false>(A, rpu, st, mp);
+    return strip_launch_28<OP_AFFINE, false>(A, rpu, st, mp);
+  }
   if (op == OP_DR)
     return hd ? strip_launch_cols<OP_DR, true>(A, cols, rpu, st, mp) : strip_launch_cols<OP_DR, false>(A, cols, rpu, st, mp);
   if (op == OP_GAE)

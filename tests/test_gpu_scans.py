@@ -280,7 +280,7 @@ TM_SHAPES = [(1, 16), (5, 16), (64, 32), (65, 48), (127, 80), (128, 64), (300, 4
 
 
 @pytest.mark.parametrize("cols,rpu,groups,stages", [(32, 16, 1, 0), (32, 16, 2, 0), (32, 16, 1, 2), (32, 8, 1, 0),
-                                                    (16, 8, 1, 0), (16, 16, 1, 2), (32, 32, 1, 0), (32, 32, 1, 2)])
+                                                    (16, 8, 1, 0), (16, 16, 1, 2), (32, 32, 1, 0), (32, 32, 1, 2), (28, 16, 1, 0), (28, 32, 1, 0), (28, 16, 1, 2)])
 def test_tma_strip_kernels(cols, rpu, groups, stages):
     """time-major strips: ragged T (partial first tile), ragged N (clipped last strip), bootstrap row,
     with and without done flags, every recurrence; ring depth 2 forces stage reuse on the small shapes"""
