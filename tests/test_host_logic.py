@@ -127,6 +127,27 @@ def _worker(rank, world, port, q):
     gathered = [None] * world
     dist.all_gather_object(gathered, g.numpy().tolist())
     ok = ok and all(x == gathered[0] for x in gathered)
+
+    # exchange="auto" must take the peer mailboxes only if EVERY rank could map every peer: here rank 1
+    # fails to connect, so all ranks -- also rank 0, whose own connect succeeded -- fall back to the all-gather
+    class Mailboxed(Local):
+        def shard_init(self, rank_, world_, publish="mutation"):
+            return bytes(64)
+
+        def shard_connect(self, handles):
+            assert len(handles) == 64 * world
+            if rank == 1:
+                raise RuntimeError("cannot map the mailbox of rank 0")
+
+    sh2 = ShardedPriorityReplayBuffer(Mailboxed(), 256, exchange="auto")
+    ok = ok and sh2.p2p is False and sh2.exchange == "nccl"
+    idx2, w2, _ = sh2.sample(0.4, uniforms=u)
+    ok = ok and idx2.shape == (16,)
+    try:
+        ShardedPriorityReplayBuffer(Mailboxed(), 256, exchange="p2p")
+        ok = False  # an explicit request must fail loudly on every rank
+    except RuntimeError:
+        pass
     q.put((rank, ok))
     dist.destroy_process_group()
 
