@@ -1212,6 +1212,23 @@ __global__ void __launch_bounds__(256)
                       const double2 *__restrict__ part, int nparts) {
   __shared__ double ra[8], rb[8];
   __shared__ float s_mean, s_inv;
+  // (launched as a programmatic dependent of the scan that produced x and the partials: resident while that kernel
+  // drains, released when its memory is flushed; a no-op after an ordinary launch)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool vec = ((((uintptr_t)x) | ((uintptr_t)out)) & 15) == 0;
+  const int64_t n4 = vec ? n / 4 : 0;
+  // the first two quads of this thread are requested BEFORE the partials are folded: the fold (a dependent chain
+  // of loads, shuffles and a barrier, ~2 us) then runs under their latency instead of in front of the stream
+  constexpr int U = 2;
+  float4 pre[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int64_t i = gid + u * stride;
+    pre[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < n4) pre[u] = __ldcs(reinterpret_cast<const float4 *>(x) + i);
+  }
   {
     // 256 threads, contiguous runs of the partials, folded in index order (same in every CTA)
     const int per = (nparts + 255) / 256;
@@ -1239,20 +1256,27 @@ __global__ void __launch_bounds__(256)
   }
   __syncthreads();
   const float mean = s_mean, inv = s_inv;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (((((uintptr_t)x) | ((uintptr_t)out)) & 15) == 0) {
-    const int64_t n4 = n / 4;
-    for (int64_t i = gid; i < n4; i += stride) {
-      const float4 v = __ldcs(reinterpret_cast<const float4 *>(x) + i);
-      __stcs(reinterpret_cast<float4 *>(out) + i,
-             make_float4(__fmul_rn(__fsub_rn(v.x, mean), inv), __fmul_rn(__fsub_rn(v.y, mean), inv),
-                         __fmul_rn(__fsub_rn(v.z, mean), inv), __fmul_rn(__fsub_rn(v.w, mean), inv)));
+  auto norm4 = [&](const float4 v) {
+    return make_float4(__fmul_rn(__fsub_rn(v.x, mean), inv), __fmul_rn(__fsub_rn(v.y, mean), inv),
+                       __fmul_rn(__fsub_rn(v.z, mean), inv), __fmul_rn(__fsub_rn(v.w, mean), inv));
+  };
+  for (int64_t i0 = gid; i0 < n4; i0 += U * stride) {
+    float4 nxt[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {  // the next round's loads go out before this round's stores
+      const int64_t i = i0 + (U + u) * stride;
+      nxt[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < n4) nxt[u] = __ldcs(reinterpret_cast<const float4 *>(x) + i);
     }
-    for (int64_t i = n4 * 4 + gid; i < n; i += stride) out[i] = __fmul_rn(__fsub_rn(x[i], mean), inv);
-  } else {
-    for (int64_t i = gid; i < n; i += stride) out[i] = __fmul_rn(__fsub_rn(x[i], mean), inv);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < n4) __stcs(reinterpret_cast<float4 *>(out) + i, norm4(pre[u]));
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) pre[u] = nxt[u];
   }
+  for (int64_t i = n4 * 4 + gid; i < n; i += stride) out[i] = __fmul_rn(__fsub_rn(x[i], mean), inv);
 }
 
 static int moments_ws(cudaStream_t st, double2 **p) {
@@ -1279,7 +1303,8 @@ static int normalize_impl(const float *x, float *out, int64_t n, float eps, doub
     norm_partial_kernel<<<nparts, 256, 0, st>>>(x, n, part);
     MRL_LAUNCHED();
   }
-  norm_apply_kernel<<<(unsigned)ctas, 256, 0, st>>>(x, out, n, eps, part, nparts);
+  MRL_CUDA(launch_pdl(norm_apply_kernel, dim3((unsigned)ctas), dim3(256), 0, st, x, out, n, eps,
+                      (const double2 *)part, nparts));
   MRL_LAUNCHED();
   return MRL_OK;
 }

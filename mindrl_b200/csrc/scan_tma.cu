@@ -159,6 +159,7 @@ __global__ void __launch_bounds__((NG * kWarps + 1) * 32)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int col0 = blockIdx.x * COLS;
   const int T = (int)A.T;
+  if (MOM) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the apply pass may become resident
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < n_stages; ++s) {
@@ -603,6 +604,7 @@ __global__ void __launch_bounds__((BM_L / (32 * SPL) + 1) * 32)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t T = A.T;
   const int64_t G = gridDim.x;
+  if (MOM) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the apply pass may become resident
   const int64_t n_rows = A.N > (int64_t)blockIdx.x ? (A.N - blockIdx.x + G - 1) / G : 0;
   const int64_t n_items = n_rows * n_chunks;
 
