@@ -39,6 +39,7 @@ __device__ __forceinline__ void copy_units(const uint8_t *__restrict__ src,
 
 __global__ void __launch_bounds__(256)
     copy_seg_kernel(ColTable tab, int64_t ring_row, int64_t io_row, int64_t nrows, int to_ring) {
+  pdl_prologue();  // (the DQN loop's insert -> sample pair: the launch latencies of the two overlap)
   const int c = blockIdx.y;
   const int64_t rb = tab.row_bytes[c];
   uint8_t *ring = tab.col[c] + ring_row * rb;
@@ -75,7 +76,7 @@ int copy_segments_dir(const ColTable &tab, int64_t ring_row, int64_t io_row, int
   if (blocks < 1) blocks = 1;
   if (blocks > sm_count() * 8) blocks = sm_count() * 8;
   dim3 grid((unsigned)blocks, (unsigned)tab.ncols);
-  copy_seg_kernel<<<grid, 256, 0, st>>>(tab, ring_row, io_row, nrows, to_ring);
+  MRL_CUDA(launch_pdl(copy_seg_kernel, grid, dim3(256), 0, st, tab, ring_row, io_row, nrows, to_ring));
   MRL_LAUNCHED();
   return MRL_OK;
 }
@@ -119,6 +120,7 @@ __device__ __forceinline__ void gather_units(const uint8_t *__restrict__ col,
 __global__ void __launch_bounds__(256)
     gather_ldg_kernel(ColTable tab, const int64_t *__restrict__ slots, int64_t n,
                       int64_t capacity, uint32_t col_mask) {
+  pdl_prologue();
   int c = blockIdx.y;
   // blockIdx.y enumerates the set bits of col_mask
   {
@@ -383,7 +385,7 @@ int gather_rows(const ColTable &tab, const int64_t *slots, int64_t n, int64_t ca
     int64_t blocks = (max_units + 256 * 4 - 1) / (256 * 4);
     if (blocks > sm_count() * 8) blocks = sm_count() * 8;
     dim3 grid((unsigned)blocks, (unsigned)ncols);
-    gather_ldg_kernel<<<grid, 256, 0, st>>>(tab, slots, n, capacity, ldg_mask);
+    MRL_CUDA(launch_pdl(gather_ldg_kernel, grid, dim3(256), 0, st, tab, slots, n, capacity, ldg_mask));
     MRL_LAUNCHED();
   }
   return MRL_OK;

@@ -1485,6 +1485,7 @@ __global__ void __launch_bounds__(kSubThreads) prb_update_sub_kernel(const __gri
 __global__ void __launch_bounds__(32)
     prb_push_kernel(float *sum, float *mn, const PrbState *state, int64_t cap2, int32_t levels,
                     int64_t slot, const __grid_constant__ ColTable tab, const PublishArgs pub) {
+  pdl_prologue();  // (actor inserts between the learner's sample / update: the launch latencies overlap)
   const int lane = threadIdx.x;
   constexpr unsigned FULL = 0xffffffffu;
   // row write (io -> ring)
@@ -1695,7 +1696,8 @@ static int prb_push_batch_impl(PrbBuffer *b, int64_t nrows, void *const *src, cu
     fill_table(tab, b, src);
     const int64_t size_after = b->size < cap ? b->size + 1 : b->size;
     const PublishArgs P = make_publication(b, size_after);
-    prb_push_kernel<<<1, 32, 0, st>>>(b->sum, b->mn, b->state, b->cap2, b->levels, slot, tab, P);
+    MRL_CUDA(launch_pdl(prb_push_kernel, dim3(1), dim3(32), 0, st, b->sum, b->mn, (const PrbState *)b->state, b->cap2,
+                        b->levels, slot, tab, P));
     MRL_LAUNCHED();
     b->head = slot;
     b->size = size_after;

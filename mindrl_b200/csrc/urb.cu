@@ -66,6 +66,7 @@ static void fill_table(ColTable &tab, int32_t ncols, uint8_t *const *cols, const
 // Philox-free counter generator: slot j of a draw = mrl_uniform_below(seed, ctr + j, count)
 __global__ void __launch_bounds__(256)
     urb_draw_kernel(int64_t *slots, int64_t n, uint64_t seed, uint64_t ctr, int64_t count) {
+  pdl_prologue();
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j < n) slots[j] = mrl_uniform_below(seed, ctr + (uint64_t)j, count);
 }
@@ -74,6 +75,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     urb_sample_fused_kernel(const __grid_constant__ ColTable tab, int64_t *slots_out, int64_t n,
                             uint64_t seed, uint64_t ctr, int64_t count, int word_units) {
+  pdl_prologue();  // resident while the insert in front of it drains (DQN loop: insert 1 row, sample a batch)
   const int lane = threadIdx.x & 31;
   const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (j >= n) return;
@@ -181,8 +183,8 @@ static int urb_sample_impl(UrbBuffer *b, int64_t n, int64_t *slots_out, void *co
     int64_t words = 0;
     bool whole = true;
     for (int c = 0; c < b->ncols; ++c) whole = whole && ftab.vec[c] >= 4, words += b->row_bytes[c] / 4;
-    urb_sample_fused_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(ftab, slots_out, n, b->seed,
-                                                                          b->ctr, b->count, whole ? (int)words : 0);
+    MRL_CUDA(launch_pdl(urb_sample_fused_kernel, dim3((unsigned)((n * 32 + 255) / 256)), dim3(256), 0, st, ftab, slots_out, n,
+                        b->seed, b->ctr, (int64_t)b->count, whole ? (int)words : 0));
     MRL_LAUNCHED();
     b->ctr += (uint64_t)n;
     return MRL_OK;
@@ -193,7 +195,8 @@ static int urb_sample_impl(UrbBuffer *b, int64_t n, int64_t *slots_out, void *co
     if (rc) return rc;
     slots = b->slots_dev;
   }
-  urb_draw_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(slots, n, b->seed, b->ctr, b->count);
+  MRL_CUDA(launch_pdl(urb_draw_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, slots, n, b->seed, b->ctr,
+                      (int64_t)b->count));
   MRL_LAUNCHED();
   b->ctr += (uint64_t)n;
   ColTable tab;
