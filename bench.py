@@ -839,7 +839,7 @@ def bench_gae(ctx, steps, warmup):
     bm = out["gae_batch_major[B,T]"]
     roofline["batch_major_kernel"] = {"kernel": "scan_bm_row_kernel<GAE, done>", "achieved": bm["back_to_back_GBps"],
                                       "frac": bm["back_to_back_frac"], "after_flush_frac": bm["frac"],
-                                      "traffic": ncu_traffic("c4:scan_bm_row_kernel<1, 1, 0, 0>")}
+                                      "traffic": ncu_traffic("c4:scan_bm_row_kernel<1, 1, 0, 0, 8>")}
     roofline["discounted_return"] = {
         "time_major": {"kernel": "scan_tm_strip_kernel<DR, done, 32 cols, 32 steps/lane>",
                        "frac": out["discounted_return_time_major"]["back_to_back_frac"],

@@ -176,7 +176,7 @@ def test_bench_finds_its_committed_ncu_numbers():
     bench = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(bench)
     for key in ("c2:prb_update_sub_kernel", "c2:prb_sample_kernel", "c3:prb_sample_gather_kernel<4>",
-                "c4:scan_tm_strip_kernel<1, 1, 32, 16, 1, 0>", "c4:scan_bm_row_kernel<1, 1, 0, 0>"):
+                "c4:scan_tm_strip_kernel<1, 1, 32, 16, 1, 0>", "c4:scan_bm_row_kernel<1, 1, 0, 0, 8>"):
         assert bench.ncu_traffic(key) and bench.ncu_traffic(key) > 0, key
     for key in ("c2:prb_sample_kernel", "c2:prb_update_sub_kernel", "c3:prb_sample_gather_kernel<4>", "c3:prb_update_sub_kernel"):
         ev = bench.ncu_latency_evidence(key)
