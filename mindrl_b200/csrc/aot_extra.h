@@ -22,82 +22,62 @@
 #include <cstddef>
 #include <cstdint>
 #include <string>
+#include <type_traits>
 #include <vector>
 
-// base of whatever an operator parks between its Init and its calls
-class AotKernelData {
- public:
+// base of whatever an operator parks between its Init and its calls (deleted through this base)
+struct AotKernelData {
   AotKernelData() = default;
   virtual ~AotKernelData() = default;
 };
 
 class AotExtra {
  public:
+  using IntRow = std::vector<int64_t>;
+  using FloatRow = std::vector<float>;
+
   AotExtra() = default;
-  virtual ~AotExtra() = default;
-  virtual bool HasAttr(std::string name) = 0;
+  virtual ~AotExtra() = default;                 // vtable slots 0, 1
+  virtual bool HasAttr(std::string key) = 0;     // slot 2
 
-  // typed read of a registered attribute; the specialisations below route to the virtual getters
+  // typed read of a registered attribute: routed to the virtual getter of that type (slots 3..10)
   template <typename T>
-  inline T Attr(std::string name) {
-    return T();
+  T Attr(std::string key) {
+    if constexpr (std::is_same<T, bool>::value) return GetAttrBool(key);
+    else if constexpr (std::is_same<T, int64_t>::value) return GetAttrInt(key);
+    else if constexpr (std::is_same<T, float>::value) return GetAttrFloat(key);
+    else if constexpr (std::is_same<T, std::string>::value) return GetAttrStr(key);
+    else if constexpr (std::is_same<T, IntRow>::value) return GetAttrIntVec(key);
+    else if constexpr (std::is_same<T, FloatRow>::value) return GetAttrFloatVec(key);
+    else if constexpr (std::is_same<T, std::vector<IntRow>>::value) return GetAttrInt2DVec(key);
+    else if constexpr (std::is_same<T, std::vector<FloatRow>>::value) return GetAttrFloat2DVec(key);
+    else return T();
   }
 
-  void SetWorkSpace(const std::vector<size_t> &sizes) { workspace_ = sizes; }
-  const std::vector<size_t> &WorkSpace() const { return workspace_; }
-  void SetKernelData(AotKernelData *data) { kernel_data_ = data; }
-  AotKernelData *KernelData() const { return kernel_data_; }
+  // per-operator data and workspace sizes travel with the object between Init and the calls
+  AotKernelData *KernelData() const { return data_; }
+  void SetKernelData(AotKernelData *d) { data_ = d; }
   void DestructKernelData() {
-    delete kernel_data_;
-    kernel_data_ = nullptr;
+    if (data_) delete data_;
+    data_ = nullptr;
   }
+  const std::vector<size_t> &WorkSpace() const { return scratch_sizes_; }
+  void SetWorkSpace(const std::vector<size_t> &sizes) { scratch_sizes_ = sizes; }
 
  private:
-  // (declaration order = vtable order: do not reorder)
-  virtual bool GetAttrBool(std::string name) = 0;
-  virtual int64_t GetAttrInt(std::string name) = 0;
-  virtual float GetAttrFloat(std::string name) = 0;
-  virtual std::string GetAttrStr(std::string name) = 0;
-  virtual std::vector<int64_t> GetAttrIntVec(std::string name) = 0;
-  virtual std::vector<float> GetAttrFloatVec(std::string name) = 0;
-  virtual std::vector<std::vector<int64_t>> GetAttrInt2DVec(std::string name) = 0;
-  virtual std::vector<std::vector<float>> GetAttrFloat2DVec(std::string name) = 0;
+  // one getter per attribute type -- declaration order is vtable order, it must not change
+  virtual bool GetAttrBool(std::string key) = 0;                                // 3
+  virtual int64_t GetAttrInt(std::string key) = 0;                              // 4
+  virtual float GetAttrFloat(std::string key) = 0;                              // 5
+  virtual std::string GetAttrStr(std::string key) = 0;                          // 6
+  virtual IntRow GetAttrIntVec(std::string key) = 0;                            // 7
+  virtual FloatRow GetAttrFloatVec(std::string key) = 0;                        // 8
+  virtual std::vector<IntRow> GetAttrInt2DVec(std::string key) = 0;             // 9
+  virtual std::vector<FloatRow> GetAttrFloat2DVec(std::string key) = 0;         // 10
 
-  std::vector<size_t> workspace_;
-  AotKernelData *kernel_data_{nullptr};
+  // data members behind the vptr, in this order: workspace sizes (24 bytes), then the operator's data (8)
+  std::vector<size_t> scratch_sizes_;
+  AotKernelData *data_ = nullptr;
 };
-
-template <>
-inline bool AotExtra::Attr<bool>(std::string name) {
-  return GetAttrBool(name);
-}
-template <>
-inline int64_t AotExtra::Attr<int64_t>(std::string name) {
-  return GetAttrInt(name);
-}
-template <>
-inline float AotExtra::Attr<float>(std::string name) {
-  return GetAttrFloat(name);
-}
-template <>
-inline std::string AotExtra::Attr<std::string>(std::string name) {
-  return GetAttrStr(name);
-}
-template <>
-inline std::vector<int64_t> AotExtra::Attr<std::vector<int64_t>>(std::string name) {
-  return GetAttrIntVec(name);
-}
-template <>
-inline std::vector<float> AotExtra::Attr<std::vector<float>>(std::string name) {
-  return GetAttrFloatVec(name);
-}
-template <>
-inline std::vector<std::vector<int64_t>> AotExtra::Attr<std::vector<std::vector<int64_t>>>(std::string name) {
-  return GetAttrInt2DVec(name);
-}
-template <>
-inline std::vector<std::vector<float>> AotExtra::Attr<std::vector<std::vector<float>>>(std::string name) {
-  return GetAttrFloat2DVec(name);
-}
 
 #endif  // MINDRL_B200_AOT_EXTRA_H_
