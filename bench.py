@@ -36,7 +36,6 @@ import ctypes as C
 import json
 import os
 import sys
-import threading
 import time
 
 import numpy as np
@@ -89,8 +88,6 @@ class ClockSampler:
 
     def __init__(self, index):
         self.samples, self.reasons, self.max_mhz = [], set(), None
-        self._stop = threading.Event()
-        self._t = None
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -100,32 +97,33 @@ class ClockSampler:
         except Exception:
             self.nv = None
 
-    def _run(self):
-        while not self._stop.is_set():
+    def sample_once(self):
+        """one NVML reading of the SM clock and the clock-event reasons, taken by the CALLING thread.
+        Called from inside the timed loop at iteration boundaries, in front of the (untimed) L2 flush: the host is
+        several iterations ahead of the GPU there, so the GPU is under the loop's load while NVML reads it, and the
+        pause falls between two timed regions, never inside one.  (A sampling THREAD, as in round 1, made the
+        20-step runs at N = 8 up to 30 % slower: eight processes' NVML calls serialise in the driver and stall the
+        launches of the process that shares them -- measured: 78.7 M samples/s with the thread against 110.3 M in the
+        same run without it.)"""
+        if self.nv is None:
+            return
+        try:
+            self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
             try:
-                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
-                try:
-                    mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                except Exception:
-                    mask = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for bit, name in self.REASONS.items():
-                    if mask & bit and name != "gpu_idle":
-                        self.reasons.add(name)
+                mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
             except Exception:
-                pass
-            self._stop.wait(0.02)
+                mask = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for bit, name in self.REASONS.items():
+                if mask & bit and name != "gpu_idle":
+                    self.reasons.add(name)
+        except Exception:
+            pass
 
     def start(self):
-        if self.nv is not None and self._t is None:
-            self._stop.clear()
-            self._t = threading.Thread(target=self._run, daemon=True)
-            self._t.start()
+        pass
 
     def stop(self):
-        if self._t is not None:
-            self._stop.set()
-            self._t.join()
-            self._t = None
+        pass
 
     def summary(self):
         if not self.samples:
@@ -202,18 +200,17 @@ class Ctx:
         self.barrier()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
               for _ in range(steps)]
-        if sample_clocks:
-            self.clocks.start()
         l0 = self.ffi.launch_count()
+        every = max(1, steps // 5)
         for i in range(steps):
+            if sample_clocks and i % every == every // 2:
+                self.clocks.sample_once()  # (see there: between two timed regions, GPU under load)
             self.flush()
             ev[i][0].record()
             step(warmup + i)
             ev[i][1].record()
         self.barrier()
         launches = self.ffi.launch_count() - l0
-        if sample_clocks:
-            self.clocks.stop()
         total_ms = sum(a.elapsed_time(b) for a, b in ev)
         return self.max_over_ranks(total_ms), launches
 
