@@ -392,7 +392,12 @@ extern "C" int PriorityReplayBufferPush(int nparam, void **params, int *ndims, i
   (void)ndims, (void)shapes, (void)dtypes;
   HandleOpData *d = kernel_data<HandleOpData>(extra);
   if (!d || nparam < 2) return kAotError;
-  if (mrl_prb_push(d->handle, params, stream) != MRL_OK) return kAotError;  // (the column count is the buffer's)
+  if (prb_column_count(d->handle) != nparam - 1) {
+    set_error("PriorityReplayBufferPush: %d transition tensors for a buffer of %d columns", nparam - 1,
+              prb_column_count(d->handle));
+    return kAotError;
+  }
+  if (mrl_prb_push(d->handle, params, stream) != MRL_OK) return kAotError;
   return write_handle(params[nparam - 1], d->handle, stream);
 }
 
@@ -407,6 +412,11 @@ extern "C" int PriorityReplayBufferSample(int nparam, void **params, int *ndims,
   if (!d || nparam < 4) return kAotError;
   const int64_t batch = ndims[1] >= 1 ? shapes[1][0] : 0;  // indices [B]
   if (batch < 1) return kAotError;
+  if (prb_column_count(d->handle) != nparam - 3) {
+    set_error("PriorityReplayBufferSample: %d column outputs for a buffer of %d columns", nparam - 3,
+              prb_column_count(d->handle));
+    return kAotError;
+  }
   if (prb_sample_beta_dev(d->handle, batch, (const float *)params[0], (int64_t *)params[1], (float *)params[2],
                           params + 3, as_stream(stream)) != MRL_OK)
     return kAotError;

@@ -161,6 +161,8 @@ int copy_segments_dir(const ColTable &tab, int64_t ring_row, int64_t io_row, int
                       int to_ring, cudaStream_t st);
 // tunables of the TMA-ring copies (copy.cu; options "gather_path", "bulk_*")
 extern int64_t g_gather_path, g_bulk_min_row, g_bulk_chunk, g_bulk_ctas_per_sm, g_bulk_stages;
+// number of columns of a PriorityReplayBuffer, -1 for an unknown handle (the AOT shims check their parameter lists)
+int prb_column_count(int64_t handle);
 // mrl_prb_sample with beta read from DEVICE memory by the kernel (the AOT shim gets beta as a tensor)
 int prb_sample_beta_dev(int64_t handle, int64_t n, const float *beta_dev, int64_t *indices, float *weights,
                         void *const *out_cols, cudaStream_t st);

@@ -2026,6 +2026,11 @@ extern "C" int mrl_prb_sample(int64_t handle, int64_t n, float beta, const float
                          as_stream(stream));
 }
 
+int mrl::prb_column_count(int64_t handle) {
+  PrbBuffer *b = g_prb.get(handle);
+  return b ? b->ncols : -1;
+}
+
 int mrl::prb_sample_beta_dev(int64_t handle, int64_t n, const float *beta_dev, int64_t *indices, float *weights,
                              void *const *out_cols, cudaStream_t st) {
   PRB_GET(b, handle);

@@ -84,6 +84,7 @@ def test_priority_buffer_ops_against_oracle():
         assert push([t(c[i]) for c in drows] + [t(out_h)], stream()) == 0
         o.insert(*[c[i] for c in rows])
     assert int(out_h.item()) == handle
+    assert push([t(drows[0][0]), t(out_h)], stream()) == 2  # one tensor for a buffer of four columns
     # the internal generator draws the uniforms on both sides (same seed, same counter)
     for step in range(6):
         beta = torch.tensor([0.4 + 0.1 * step], dtype=torch.float32, device="cuda")
