@@ -20,8 +20,9 @@
 //                          inside its quad: 3 dependent loads for 2^20 leaves.  Importance weights (two
 //                          pows side by side on two lanes) and the narrow columns (one list of words,
 //                          requested before the weights are computed) are fused behind the descent; in
-//                          the sharded buffer the kernel also exchanges the ranks' root statistics
-//                          through peer mailboxes.
+//                          the sharded buffer one warp per CTA reads the peers' root statistics out of the
+//                          local inbox (delivered a step earlier by the peers' courier kernels).
+//   prb_sample_gather_kernel  the same descent and the TMA row gather of Atari-shaped rows in ONE kernel.
 //   prb_update_sub_kernel  128..512 CTAs own the subtrees below level 11.  Normal case (a share of <= 32
 //                          entries): one warp -- all path siblings in one round trip, who-meets-whom from
 //                          one shuffle pass (highest differing bit of two leaf numbers), branch-free
